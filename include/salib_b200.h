@@ -1,0 +1,163 @@
+/*
+ * salib_b200 -- C ABI of the B200-native Sobol'/Saltelli hot path.
+ *
+ * The reference (SALib) has no FFI: its "plugin" boundary is the pair of Python callables
+ *   SALib.sample.sobol.sample(problem, N, ...)        src/SALib/sample/sobol.py:11-189
+ *   SALib.analyze.sobol.analyze(problem, Y, ...)      src/SALib/analyze/sobol.py:23-206
+ * (and the deprecated alias src/SALib/sample/saltelli.py:12-203).  This header is what a
+ * maintainer would bind from inside those two functions (ctypes stub in INTEGRATION.md): every
+ * entry point replaces a numbered span of the reference, cited next to it.
+ *
+ * Conventions
+ *   - plain C types only; every `d_` pointer is DEVICE memory owned by the caller, every `h_`
+ *     pointer is HOST memory.  The library never allocates or frees result buffers.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated.
+ *   - return value: 0 = ok; < 0 = argument error (SA_ERR_*); > 0 = cudaError_t of the failed
+ *     CUDA call.  sa_last_error() returns a thread-local message for the last non-zero status.
+ *   - no global mutable state; calls on different streams may run concurrently.
+ */
+#ifndef SALIB_B200_H
+#define SALIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SA_OK 0
+#define SA_ERR_ARG (-1)         /* null pointer / negative size / inconsistent shape      */
+#define SA_ERR_RANGE (-2)       /* Sobol' index range beyond 2^30 points or > 21201 dims  */
+#define SA_ERR_UNSUPPORTED (-3) /* shape outside what the kernels implement               */
+#define SA_ERR_WORKSPACE (-4)   /* workspace too small                                    */
+
+#define SA_SOBOL_BITS 30     /* scipy.stats.qmc.Sobol word size (sample/sobol.py:107)     */
+#define SA_SOBOL_MAXDIM 21201 /* new-joe-kuo-6.21201 (sample/directions.py)               */
+
+/* Number of accumulated sums per resample: 5 scalars + 2*Dg (+ Dg*(Dg-1)/2 pair sums). */
+#define SA_NACC(Dg, second_order) (5 + 2 * (Dg) + ((second_order) ? (Dg) * ((Dg)-1) / 2 : 0))
+/* Number of estimates per resample: S1[Dg], ST[Dg] (, S2[pairs]). */
+#define SA_NEST(Dg, second_order) (2 * (Dg) + ((second_order) ? (Dg) * ((Dg)-1) / 2 : 0))
+
+int sa_version(void);
+const char *sa_last_error(void);
+
+/* ---- direction numbers (host) -------------------------------------------------------------
+ * Replaces the recurrence of sample/sobol_sequence.py:62-84 (== scipy's _initialize_v reached
+ * from sample/sobol.py:107).  Inputs are the Joe-Kuo table columns for dimensions 2..dims
+ * (a: polynomial bits, s: degree, m: [dims-1][18] initial numbers); output h_sv[dims][30]
+ * uint32, h_sv[d][j] = V_{j+1} << (30 - (j+1)).                                              */
+int sa_direction_vectors(const uint32_t *h_a, const uint8_t *h_s, const uint32_t *h_m, int dims,
+                         uint32_t *h_sv);
+
+/* ---- Saltelli sample: fused Sobol' draw + cross-matrix + uniform scaling ------------------
+ * Replaces sample/sobol.py:107-188 (qmc.Sobol -> fast_forward -> random -> the A/AB/BA/B
+ * triple loop :149-186 -> util/__init__.py:49-53 scaling).  Base row i (0 <= i < n) uses Sobol'
+ * point first_index + i in 2*D dimensions: dims 0..D-1 -> A, D..2D-1 -> B.
+ *   d_sv     [2D][30] direction vectors (plain, or LMS-scrambled by the host)
+ *   d_shift  [2D] digital shift (zeros when unscrambled), may be NULL
+ *   d_group_of_col [D] group index of each column (NULL = ungrouped, Dg must equal D)
+ *   d_lb, d_span   [D] lower bound and (ub - lb), both already rounded to f64 on the host
+ *   d_out    [(step*n), D] row-major f64, step = 2*Dg+2 (second_order) or Dg+2; 16-byte aligned
+ * Values are computed as round(round(x * span) + lb) -- no FMA contraction.      */
+int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                           uint64_t first_index, uint64_t n, int D, int Dg,
+                           const int32_t *d_group_of_col, int second_order, const double *d_lb,
+                           const double *d_span, double *d_out);
+
+/* ---- test functions on the path -----------------------------------------------------------
+ * sa_eval_ishigami_f64 replaces test_functions/Ishigami.py:55-59, sa_eval_sobol_g_f64 replaces
+ * test_functions/Sobol_G.py:66-86 (X -> Y).  d_flag (int32, may be NULL) is OR-ed with 1 if any
+ * value < 0 and 2 if any value > 1 (the reference raises ValueError, Sobol_G.py:68-74).       */
+int sa_eval_ishigami_f64(void *stream, const double *d_X, uint64_t rows, double A, double B,
+                         double *d_Y);
+int sa_eval_sobol_g_f64(void *stream, const double *d_X, uint64_t rows, int D, const double *d_a,
+                        const double *d_delta, const double *d_alpha, double *d_Y, int32_t *d_flag);
+
+/* Fused variants: Sobol' indices -> Y without materialising X (same arguments as
+ * sa_saltelli_sample_f64; d_Y is [step*n]).  Ishigami requires D == 3.                       */
+int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                 uint64_t first_index, uint64_t n, int D, int Dg,
+                                 const int32_t *d_group_of_col, int second_order,
+                                 const double *d_lb, const double *d_span, const double *d_a,
+                                 const double *d_delta, const double *d_alpha, double *d_Y,
+                                 int32_t *d_flag);
+int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                  uint64_t first_index, uint64_t n, int Dg,
+                                  const int32_t *d_group_of_col, int second_order,
+                                  const double *d_lb, const double *d_span, double A, double B,
+                                  double *d_Y);
+
+/* ---- analyze: normalisation ---------------------------------------------------------------
+ * sa_moments_f64 replaces Y.mean() / Y.std() of analyze/sobol.py:141 (two-pass, population
+ * std).  d_stats[8] = {mean, std, min, max, minAB, maxAB, 0, 0}; minAB/maxAB are taken over
+ * the A and B columns only (the ptp test of analyze/sobol.py:214-217).  d_work needs
+ * sa_moments_workspace_bytes() bytes.                                                         */
+size_t sa_moments_workspace_bytes(void);
+int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double *d_stats,
+                   void *d_work, size_t work_bytes);
+
+/* Layout of the normalised model output used by the accumulate kernels ("analysis layout"):
+ * row i of length sa_row_stride(Dg, second_order) doubles =
+ *   [ AB_0..AB_{Dg-1} 0.. | BA_0..BA_{Dg-1} 0.. | A B 0 0 0 0 0 0 ]   (second order)
+ *   [ AB_0..AB_{Dg-1} 0.. | A B 0 0 0 0 0 0 ]                         (first/total only)
+ * with each column block padded with zeros to a multiple of 8 doubles (64 B).                */
+int sa_row_stride(int Dg, int second_order);
+/* Replaces (Y - mean)/std and separate_output_values (analyze/sobol.py:141,267-279):
+ * d_Y [N*step] reference order [A, AB_0.., (BA_0..,) B] -> d_Yn [N*stride (+8 doubles slack)]
+ * in analysis layout; if d_Yt != NULL also writes the column-major copy d_Yt[col][Npad]
+ * (cols: A, B, AB_0..AB_{Dg-1}), Npad = sa_pad_rows(N), used by the first-order kernel.      */
+uint64_t sa_pad_rows(uint64_t N);
+int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                     const double *d_stats, double *d_Yn, double *d_Yt);
+
+/* ---- analyze: resample multiplicities -----------------------------------------------------
+ * A bootstrap resample c is the multiset of rows r[:, c] (analyze/sobol.py:144).  The kernels
+ * consume it as multiplicities w[c][i] = #{t : r[t, c] == i} (uint8, row pitch sa_pad_rows(N)),
+ * which gives the same sums as gathering A[r], AB[r], BA[r], B[r].
+ *   sa_counts_from_indices: d_r int64 [N, R] C-order as numpy draws it; resamples
+ *                           [c0, c0+count) -> d_w[count][Npad].  d_w must be zeroed by the call
+ *                           (it is: the function memsets it on `stream`).
+ *   sa_counts_philox:       device Philox4x32-10 draw of N iid uniform indices per resample,
+ *                           keyed by (seed, global resample id c0+c, draw t): independent of
+ *                           how resamples are sharded over GPUs.
+ * d_overflow (int32, may be NULL) is set to 1 if any multiplicity exceeded 255.               */
+int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
+                           uint64_t count, uint8_t *d_w, int32_t *d_overflow);
+int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                     uint8_t *d_w, int32_t *d_overflow);
+
+/* ---- analyze: accumulate / finalize -------------------------------------------------------
+ * sa_sobol_accumulate_f64 replaces the gathers and reductions inside first_order / total_order
+ * / second_order (analyze/sobol.py:209-246) for `count` resamples at once.  For resample c it
+ * produces, per row split sp, SA_NACC sums over rows i with weight w = d_w[c][i]:
+ *   [0..4]  sum w*A, sum w*B, sum w*A^2, sum w*B^2, sum w*A*B
+ *   [5+j]   sum w*B*(AB_j - A)            [5+Dg+j] sum w*(A - AB_j)^2
+ *   [5+2Dg+p(j,k)] sum w*BA_j*AB_k, j<k, p = j*Dg - j*(j+1)/2 + (k-j-1)
+ * into d_psum[nsplit][count][SA_NACC].  d_w == NULL means weight 1 for every row (the point
+ * estimate; count must be 1).  nsplit row ranges of equal size let small `count` fill the GPU.
+ * d_Yt is required when second_order == 0 (first-order kernel), ignored otherwise.            */
+int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
+                            int Dg, int second_order, const uint8_t *d_w, uint64_t count,
+                            int nsplit, double *d_psum);
+/* Same, with an explicit kernel choice for tests: algo 0 = auto, 1 = generic (any shape),
+ * 2 = second-order 8x8 register-tile kernel (Dg <= 64), 3 = first/total-order kernel.        */
+int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
+                               int Dg, int second_order, const uint8_t *d_w, uint64_t count,
+                               int nsplit, double *d_psum, int algo);
+/* Sums the splits and applies the estimator algebra of analyze/sobol.py:219,232,242-246:
+ * d_est[count][SA_NEST] = {S1_j, ST_j, S2_jk}.  If d_stats says ptp([A;B]) == 0 every estimate
+ * is 0 (the `return 0.0` branches :214-217,227-230,238-240).                                  */
+int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg, int second_order,
+                          uint64_t count, int nsplit, const double *d_stats, double *d_est);
+/* conf = z * std(d_est[:, col], ddof=1) over R resamples (analyze/sobol.py:159,173,180-182);
+ * d_conf[SA_NEST].                                                                            */
+int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
+                      double *d_conf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALIB_B200_H */

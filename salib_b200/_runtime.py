@@ -1,0 +1,73 @@
+"""Device plumbing: PyTorch owns device memory and streams, nothing else.
+
+Every helper here raises if CUDA is unavailable -- there is no CPU path.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("salib_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _lib.lib()
+
+
+def device():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def to_device(a, dtype=None):
+    """numpy / torch -> contiguous device tensor (no copy if already there)."""
+    dev = device()
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=dev, dtype=dtype) if (a.device != dev or (dtype and a.dtype != dtype)) else a
+        return t.contiguous()
+    arr = np.ascontiguousarray(a)
+    t = torch.from_numpy(arr)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(dev, non_blocking=False)
+
+
+def empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def zeros(shape, dtype):
+    return torch.zeros(shape, dtype=dtype, device=device())
+
+
+def world():
+    """(rank, world_size) of the torch.distributed job, (0, 1) when not initialised."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous [lo, hi) share of `total` units for `rank` (first ranks get the remainder)."""
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default

@@ -1,0 +1,365 @@
+"""Drop-in for ``SALib.analyze.sobol`` on B200 (reference: src/SALib/analyze/sobol.py:23-206).
+
+``analyze`` keeps the reference signature and returns the same ``ResultDict``
+(``S1, S1_conf, ST, ST_conf[, S1_conf_all, ST_conf_all][, S2, S2_conf]``, ``.problem``, bound ``.to_df``).
+All arithmetic runs in the CUDA library through the C ABI (include/salib_b200.h):
+
+    moments -> normalise/re-layout -> point estimate (weights = 1)
+            -> per batch of resamples: multiplicities -> weighted sums -> estimator algebra
+            -> Z * std(ddof=1) over resamples
+
+Resample indices.  The reference draws ``r = rng.integers(N, size=(N, R))`` on the host
+(:113-117,144).  ``RESAMPLE_MODE``:
+  * ``"numpy"``  -- draw exactly that matrix on the host (same seed semantics, ``seed`` falsy -> legacy
+                    global RNG), upload it, build multiplicities on the device: results match the
+                    reference to ~1e-13;
+  * ``"philox"`` -- device Philox4x32-10 keyed by (seed, resample id, draw): statistically
+                    equivalent CIs, independent of the number of GPUs, no N*R host array;
+  * ``"auto"``   -- numpy while N*R <= NUMPY_RESAMPLE_MAX, else philox (the reference cannot even
+                    allocate ``r`` there: 84 GB at N=2^20, R=10^4).
+
+Multi-GPU: when a ``torch.distributed`` job is initialised, resamples are sharded by resample id
+across ranks and the per-rank estimates are all-gathered (NCCL); every rank returns the full result.
+"""
+import os
+from itertools import combinations
+from types import MethodType
+from warnings import warn
+
+import numpy as np
+import pandas as pd
+import torch
+from scipy.stats import norm
+
+from .. import _lib, _runtime as rt
+from ..util import ResultDict, extract_group_names
+
+__all__ = ["analyze", "to_df", "Si_to_pandas_dict", "CONST_RESULT_MSG"]
+
+CONST_RESULT_MSG = (
+    "Constant values encountered, indicating model evaluations "
+    "(or subset of evaluations) produced identical values."
+)
+
+RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
+NUMPY_RESAMPLE_MAX = 2 ** 27          # N*R elements of int64 drawn on the host in "auto" mode
+MAX_COUNT_BYTES = 4 << 30             # multiplicity buffer per batch
+_ALGO = {"auto": 0, "generic": 1, "tile8": 2, "first_order": 3}
+
+
+def _nacc(Dg, c2):
+    return 5 + 2 * Dg + (Dg * (Dg - 1) // 2 if c2 else 0)
+
+
+def _nest(Dg, c2):
+    return 2 * Dg + (Dg * (Dg - 1) // 2 if c2 else 0)
+
+
+class _Resampler:
+    """Produces the multiplicity rows w[c][:] for resamples [c0, c0+count) on the device."""
+
+    def __init__(self, N, R, seed, mode):
+        self.N, self.R = N, R
+        if mode == "auto":
+            mode = "numpy" if N * R <= NUMPY_RESAMPLE_MAX else "philox"
+        if mode not in ("numpy", "philox"):
+            raise ValueError(f"unknown resample mode {mode!r}")
+        self.mode = mode
+        self.flag = rt.zeros((1,), torch.int32)
+        if mode == "numpy":
+            # analyze/sobol.py:113-117,144 -- identical draw, C order [N, R]
+            rng = np.random.default_rng(seed).integers if seed else np.random.randint
+            r = rng(N, size=(N, R))
+            self.r = rt.to_device(np.ascontiguousarray(r, dtype=np.int64), torch.int64)
+        else:
+            if seed:
+                self.key = int(np.random.default_rng(seed).integers(0, 2 ** 63))
+            else:
+                self.key = int(np.random.randint(0, 2 ** 62))
+
+    @classmethod
+    def from_indices(cls, r):
+        self = cls.__new__(cls)
+        r = np.asarray(r)
+        self.N, self.R = r.shape
+        self.mode = "numpy"
+        self.flag = rt.zeros((1,), torch.int32)
+        self.r = rt.to_device(np.ascontiguousarray(r, dtype=np.int64), torch.int64)
+        return self
+
+    def counts(self, c0, count, w):
+        if self.mode == "numpy":
+            _lib.call("sa_counts_from_indices", rt.stream_ptr(), rt.ptr(self.r), self.N, self.R, int(c0),
+                      int(count), rt.ptr(w), rt.ptr(self.flag))
+        else:
+            _lib.call("sa_counts_philox", rt.stream_ptr(), self.key, self.N, int(c0), int(count), rt.ptr(w),
+                      rt.ptr(self.flag))
+
+    def check(self):
+        f = int(self.flag.item())
+        if f & 2:
+            raise ValueError("resample indices out of range [0, N)")
+        if f & 1:
+            raise OverflowError("a row was drawn more than 255 times in one resample")
+
+
+class SobolAnalyzer:
+    """Device state of one ``analyze`` call; also usable directly with a device-resident Y."""
+
+    def __init__(self, Dg, N, calc_second_order, algo="auto"):
+        rt.require_cuda()
+        self.Dg, self.N, self.c2 = int(Dg), int(N), bool(calc_second_order)
+        self.step = 2 * Dg + 2 if self.c2 else Dg + 2
+        self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
+        self.algo = _ALGO[algo]
+        kind = self.algo or (2 if (self.c2 and Dg <= 64) else (1 if self.c2 else 3))
+        self.kind = kind
+        self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
+        L = _lib.lib()
+        self.stride = L.sa_row_stride(self.Dg, int(self.c2))
+        self.Npad = int(L.sa_pad_rows(self.N))
+        self.stats = rt.zeros((8,), torch.float64)
+        self.Yn = None
+        self.Yt = None
+
+    # -- normalisation ---------------------------------------------------------------------
+    def load(self, Yd):
+        """Yd: device float64 [N*step] in the reference order -> stats, Yn (and Yt)."""
+        L = _lib.lib()
+        work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)
+        _lib.call("sa_moments_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.step, rt.ptr(self.stats),
+                  rt.ptr(work), int(work.numel()))
+        need_rows = self.kind in (1, 2)
+        need_cols = self.kind == 3
+        if need_rows:
+            self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
+        if need_cols:
+            self.Yt = rt.empty(((self.Dg + 2) * self.Npad,), torch.float64)
+        _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
+                  rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
+
+    # -- work decomposition ----------------------------------------------------------------
+    def _nsplit(self, count):
+        """Row splits so that `count` resamples fill the machine (at least 32 rows per split)."""
+        max_split = max(1, min(4096, self.N // 32))
+        if self.kind == 2:      # one warp per resample, 8 per block, one block per SM
+            blocks = -(-count // 8)
+        elif self.kind == 3:    # 4 resamples per warp, 8 warps per block, ~2 blocks per SM
+            blocks = -(-count // 32) * -(-self.Dg // 8)
+            return max(1, min(max_split, (2 * self.sms) // blocks))
+        else:                   # one block per resample
+            blocks = count
+        return max(1, min(max_split, self.sms // blocks if blocks <= self.sms else 1))
+
+    def _accumulate(self, w, count, est_out):
+        """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
+        nsplit = self._nsplit(count)
+        psum = rt.empty((nsplit * count * self.nacc,), torch.float64)
+        _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(self.Yn), rt.ptr(self.Yt), self.N,
+                  self.Dg, int(self.c2), rt.ptr(w), int(count), int(nsplit), rt.ptr(psum), self.kind)
+        _lib.call("sa_sobol_finalize_f64", rt.stream_ptr(), rt.ptr(psum), self.N, self.Dg, int(self.c2),
+                  int(count), int(nsplit), rt.ptr(self.stats), rt.ptr(est_out))
+
+    def point(self):
+        est = rt.empty((1, self.nest), torch.float64)
+        self._accumulate(None, 1, est)
+        return est
+
+    def _batches(self, lo, hi):
+        """Resample batches [c0, c1): bounded by the multiplicity buffer; for the one-warp-per-resample
+        kernel sized in whole waves (8 * SMs) with the remainder as its own, row-split, launch."""
+        cap = max(1, MAX_COUNT_BYTES // self.Npad)
+        wave = 8 * self.sms if self.kind == 2 else 32 * self.sms
+        c = lo
+        while c < hi:
+            left = hi - c
+            if left >= wave:
+                n = min((cap // wave) * wave, (left // wave) * wave) or min(cap, left)
+            else:
+                n = min(cap, left)
+            yield c, c + n
+            c += n
+
+    def bootstrap(self, resampler, lo, hi):
+        """Estimates of resamples [lo, hi) -> device [hi-lo, nest]."""
+        est = rt.empty((hi - lo, self.nest), torch.float64)
+        w = None
+        for c0, c1 in self._batches(lo, hi):
+            n = c1 - c0
+            if w is None or w.numel() < n * self.Npad:
+                w = rt.empty((n * self.Npad,), torch.uint8)
+            resampler.counts(c0, n, w)
+            self._accumulate(w, n, est[c0 - lo:c1 - lo])
+        return est
+
+    def conf(self, est, z):
+        out = rt.empty((self.nest,), torch.float64)
+        _lib.call("sa_sobol_conf_f64", rt.stream_ptr(), rt.ptr(est), int(est.shape[0]), self.nest, float(z),
+                  rt.ptr(out))
+        return out
+
+
+def allgather_estimates(est_local, R, rank, world):
+    """All-gather the per-rank [R_g, nest] estimate blocks (contiguous shares of resample ids, see
+    ``_runtime.shard_range``) into the full [R, nest] tensor on every rank."""
+    import torch.distributed as dist
+
+    nest = est_local.shape[1]
+    per = -(-R // world)
+    pad = torch.zeros((per, nest), dtype=est_local.dtype, device=est_local.device)
+    pad[: est_local.shape[0]] = est_local
+    full = torch.empty((world * per, nest), dtype=est_local.dtype, device=est_local.device)
+    dist.all_gather_into_tensor(full, pad)
+    parts = []
+    for g in range(world):
+        lo, hi = rt.shard_range(R, g, world)
+        parts.append(full[g * per: g * per + (hi - lo)])
+    return torch.cat(parts, dim=0)
+
+
+def _assemble(Dg, c2, keep, point, conf, est_all, const_y):
+    S = ResultDict((k, np.zeros(Dg)) for k in ("S1", "S1_conf", "ST", "ST_conf"))
+    R = 0 if est_all is None else est_all.shape[0]
+    if keep:
+        S["S1_conf_all"] = np.zeros((R, Dg))
+        S["ST_conf_all"] = np.zeros((R, Dg))
+    if c2:
+        S["S2"] = np.full((Dg, Dg), np.nan)
+        S["S2_conf"] = np.full((Dg, Dg), np.nan)
+    iu = np.triu_indices(Dg, 1)
+    if const_y:
+        # analyze/sobol.py:214-217 et al.: every estimator returns 0.0; the CI of a scalar 0.0 is
+        # 0 for S1/ST (:157-161) and NaN for S2 (std(ddof=1) of one value, :180-182)
+        if c2:
+            S["S2"][iu] = 0.0
+        return S
+    S["S1"][:] = point[:Dg]
+    S["ST"][:] = point[Dg:2 * Dg]
+    S["S1_conf"][:] = conf[:Dg]
+    S["ST_conf"][:] = conf[Dg:2 * Dg]
+    if keep:
+        S["S1_conf_all"][:] = est_all[:, :Dg]
+        S["ST_conf_all"][:] = est_all[:, Dg:2 * Dg]
+    if c2:
+        S["S2"][iu] = point[2 * Dg:]
+        S["S2_conf"][iu] = conf[2 * Dg:]
+    return S
+
+
+def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
+                   keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True):
+    """``analyze`` with the device knobs exposed.
+
+    Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
+    ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
+    ``algo``: force an accumulate kernel ("generic" | "tile8" | "first_order"); ``distributed``: shard the
+    resamples over the initialised torch.distributed job.
+    """
+    _, Dg = extract_group_names(problem)
+    size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+    if calc_second_order and size % (2 * Dg + 2) == 0:
+        N = size // (2 * Dg + 2)
+    elif not calc_second_order and size % (Dg + 2) == 0:
+        N = size // (Dg + 2)
+    else:
+        raise RuntimeError(
+            """
+        Incorrect number of samples in model output file.
+        Confirm that calc_second_order matches option used during sampling."""
+        )
+    if not 0 < conf_level < 1:
+        raise RuntimeError("Confidence level must be between 0-1.")
+
+    rt.require_cuda()
+    Yd = rt.to_device(Y, torch.float64).reshape(-1)
+    eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
+    eng.load(Yd)
+    Z = norm.ppf(0.5 + conf_level / 2)
+
+    if r is not None:
+        rs = _Resampler.from_indices(r)
+        if rs.N != N:
+            raise ValueError(f"`r` must have {N} rows")
+        R = rs.R
+    else:
+        R = int(num_resamples)
+        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
+
+    point = eng.point()
+    rank, world = rt.world() if distributed else (0, 1)
+    est = None
+    if R > 0:
+        lo, hi = rt.shard_range(R, rank, world)
+        est = eng.bootstrap(rs, lo, hi)
+        if world > 1:
+            est = allgather_estimates(est, R, rank, world)
+        conf = eng.conf(est, Z)
+    else:
+        conf = torch.full((eng.nest,), float("nan"), dtype=torch.float64, device=point.device)
+
+    stats = eng.stats.cpu().numpy()
+    if rs is not None:
+        rs.check()
+    # ptp([A;B]) == 0 -- or a constant Y, whose normalisation is 0/0 (the tested outcome is zeros)
+    const_y = not (stats[4] < stats[5])
+    if const_y:
+        warn(CONST_RESULT_MSG)
+    keep = bool(keep_resamples)
+    S = _assemble(Dg, bool(calc_second_order), keep, point[0].cpu().numpy(), conf.cpu().numpy(),
+                  est[:, :2 * Dg].cpu().numpy() if (keep and est is not None) else (np.zeros((0, 2 * Dg)) if keep else None),
+                  const_y)
+    S.problem = problem
+    S.to_df = MethodType(to_df, S)
+    return S
+
+
+def analyze(
+    problem,
+    Y,
+    calc_second_order=True,
+    num_resamples=100,
+    conf_level=0.95,
+    print_to_console=False,
+    parallel=False,
+    n_processors=None,
+    keep_resamples=False,
+    seed=None,
+):
+    """Sobol' first, second and total-order indices with bootstrap confidence intervals.
+
+    Same contract as ``SALib.analyze.sobol.analyze``.  ``parallel`` / ``n_processors`` (the reference's
+    CPU process pool, analyze/sobol.py:183-194) are accepted and ignored: the GPU path is always the
+    serial path's arithmetic, sharded over GPUs when torch.distributed is initialised.
+    """
+    S = analyze_device(problem, Y, calc_second_order=calc_second_order, num_resamples=num_resamples,
+                       conf_level=conf_level, keep_resamples=keep_resamples, seed=seed)
+    if print_to_console:
+        for df in S.to_df():
+            print(df)
+    return S
+
+
+def Si_to_pandas_dict(S_dict):
+    """(total, first, (index, second)) dicts ready for DataFrames (reference :365-415)."""
+    total = {"ST": S_dict["ST"], "ST_conf": S_dict["ST_conf"]}
+    first = {"S1": S_dict["S1"], "S1_conf": S_dict["S1_conf"]}
+    idx, second = None, None
+    if "S2" in S_dict:
+        names, _ = extract_group_names(S_dict.problem)
+        idx = list(combinations(names, 2)) if len(names) > 2 else (names,)
+        pos = {n: i for i, n in enumerate(names)}
+        second = {
+            "S2": [S_dict["S2"][pos[i[0]], pos[i[1]]] for i in idx],
+            "S2_conf": [S_dict["S2_conf"][pos[i[0]], pos[i[1]]] for i in idx],
+        }
+    return total, first, (idx, second)
+
+
+def to_df(self):
+    """[total, first(, second)] DataFrames; bound to the ResultDict by ``analyze`` (reference :418-439)."""
+    total, first, (idx, second) = Si_to_pandas_dict(self)
+    names, _ = extract_group_names(self.problem)
+    ret = [pd.DataFrame(total, index=names), pd.DataFrame(first, index=names)]
+    if second:
+        ret.append(pd.DataFrame(second, index=idx))
+    return ret

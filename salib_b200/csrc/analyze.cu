@@ -1,0 +1,803 @@
+// sobol.analyze on the device: normalisation, resample multiplicities, the weighted
+// first/total/second-order sums, estimator algebra and bootstrap confidence intervals.
+//
+// Reference behaviour replaced: src/SALib/analyze/sobol.py:141-182,209-246,267-279.
+//
+// Core idea: a bootstrap resample c is the multiset of rows r[:, c]; every sum the
+// reference takes over the gathered arrays A[r], AB[r, j], BA[r, j], B[r] equals the same sum over
+// ALL rows weighted by the multiplicity w_c[i] = #{t : r[t, c] == i}.  So the kernels stream the
+// normalised output matrix in row order (coalesced, shared by all resamples in flight, L1/L2
+// resident) instead of gathering N*R random 1 KB rows, and rows with w == 0 (36.8 %) are skipped.
+//
+//   second-order kernel  (s2_accum_tile8_kernel): one warp per resample; the D(D-1)/2 pair sums
+//     sum_i w*BA_j*AB_k live in registers as one 8x8 (j,k) tile per lane (28 off-diagonal tiles
+//     + the 8 diagonal triangles folded 7 pairs per lane), i.e. a register-tiled FP64 rank-1
+//     update per row: 16 operand loads feed 64 DFMAs.  FP64-pipe bound.
+//   first-order kernel   (fo_accum_kernel): lanes <-> rows over a column-major copy (coalesced),
+//     C resamples per warp share each row read.  L2-bandwidth bound.
+//   generic kernel       (accum_generic_kernel): any shape, one accumulator per thread; fallback
+//     for Dg > 64 with second order and an independent cross-check of the two fast kernels.
+#include "common.cuh"
+
+namespace sa {
+
+__host__ __device__ inline int round_up8(int x) { return (x + 7) & ~7; }
+__host__ __device__ inline int row_stride(int Dg, int second_order) {
+  return (second_order ? 2 : 1) * round_up8(Dg) + 8;
+}
+__host__ __device__ inline uint64_t pad_rows(uint64_t N) { return (N + 127) & ~(uint64_t)127; }
+__host__ __device__ inline int pair_index(int j, int k, int Dg) {
+  return j * Dg - (j * (j + 1)) / 2 + (k - j - 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// moments: mean, population std, min/max (all values and A/B columns only)
+// ------------------------------------------------------------------------------------------
+constexpr int kMomBlocks = 1024;
+constexpr int kMomThreads = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], const int (&op)[NV], double *dst) {
+  // op: 0 sum, 1 min, 2 max
+  __shared__ double sh[NV][kMomThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double x = v[q];
+    x = (op[q] == 0) ? warp_sum(x) : (op[q] == 1 ? warp_min(x) : warp_max(x));
+    if (lane == 0) sh[q][warp] = x;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double x;
+      if (lane < kMomThreads / 32) x = sh[q][lane];
+      else x = (op[q] == 0) ? 0.0 : (op[q] == 1 ? INFINITY : -INFINITY);
+      x = (op[q] == 0) ? warp_sum(x) : (op[q] == 1 ? warp_min(x) : warp_max(x));
+      if (lane == 0) dst[q] = x;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMomThreads)
+moments_pass1_kernel(const double *__restrict__ Y, uint64_t total, int step, double *__restrict__ part) {
+  const uint64_t S = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int col = (int)(idx % (uint64_t)step);
+  const int colstep = (int)(S % (uint64_t)step);
+  double v[5] = {0.0, INFINITY, -INFINITY, INFINITY, -INFINITY};
+  for (; idx < total; idx += S) {
+    const double y = Y[idx];
+    v[0] += y;
+    v[1] = fmin(v[1], y);
+    v[2] = fmax(v[2], y);
+    if (col == 0 || col == step - 1) {
+      v[3] = fmin(v[3], y);
+      v[4] = fmax(v[4], y);
+    }
+    col += colstep;
+    if (col >= step) col -= step;
+  }
+  const int op[5] = {0, 1, 2, 1, 2};
+  block_reduce_store<5>(v, op, part + (size_t)blockIdx.x * 5);
+}
+
+__global__ void __launch_bounds__(kMomThreads)
+moments_final1_kernel(const double *__restrict__ part, int nblocks, uint64_t total, double *__restrict__ stats) {
+  double v[5] = {0.0, INFINITY, -INFINITY, INFINITY, -INFINITY};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    const double *p = part + (size_t)b * 5;
+    v[0] += p[0];
+    v[1] = fmin(v[1], p[1]);
+    v[2] = fmax(v[2], p[2]);
+    v[3] = fmin(v[3], p[3]);
+    v[4] = fmax(v[4], p[4]);
+  }
+  const int op[5] = {0, 1, 2, 1, 2};
+  __shared__ double out[5];
+  block_reduce_store<5>(v, op, out);
+  if (threadIdx.x == 0) {
+    stats[0] = out[0] / (double)total;
+    stats[2] = out[1];
+    stats[3] = out[2];
+    stats[4] = out[3];
+    stats[5] = out[4];
+    stats[6] = 0.0;
+    stats[7] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(kMomThreads)
+moments_pass2_kernel(const double *__restrict__ Y, uint64_t total, const double *__restrict__ stats,
+                     double *__restrict__ part) {
+  const double mean = stats[0];
+  const uint64_t S = (uint64_t)gridDim.x * blockDim.x;
+  double v[1] = {0.0};
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += S) {
+    const double d = Y[idx] - mean;
+    v[0] = fma(d, d, v[0]);
+  }
+  const int op[1] = {0};
+  block_reduce_store<1>(v, op, part + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kMomThreads)
+moments_final2_kernel(const double *__restrict__ part, int nblocks, uint64_t total, double *__restrict__ stats) {
+  double v[1] = {0.0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v[0] += part[b];
+  const int op[1] = {0};
+  __shared__ double out[1];
+  block_reduce_store<1>(v, op, out);
+  if (threadIdx.x == 0) stats[1] = sqrt(out[0] / (double)total);
+}
+
+// ------------------------------------------------------------------------------------------
+// normalise + re-layout
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step, int second_order,
+                      const double *__restrict__ stats, double *__restrict__ Yn) {
+  const double mean = stats[0], sd = stats[1];
+  const int Dp = round_up8(Dg);
+  const int stride = row_stride(Dg, second_order);
+  const uint64_t total = N * (uint64_t)stride;
+  const uint64_t S = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = idx / (uint64_t)stride;
+  int p = (int)(idx - i * (uint64_t)stride);
+  const uint64_t di = S / (uint64_t)stride;
+  const int dp = (int)(S - di * (uint64_t)stride);
+  for (; idx < total; idx += S) {
+    int src = -1;
+    if (p < Dp) {
+      if (p < Dg) src = 1 + p;
+    } else if (second_order && p < 2 * Dp) {
+      if (p - Dp < Dg) src = 1 + Dg + (p - Dp);
+    } else {
+      const int q = p - (second_order ? 2 : 1) * Dp;
+      if (q == 0) src = 0;
+      else if (q == 1) src = step - 1;
+    }
+    double v = 0.0;
+    if (src >= 0) v = __ddiv_rn(__dsub_rn(Y[i * (uint64_t)step + src], mean), sd);
+    Yn[idx] = v;
+    i += di;
+    p += dp;
+    if (p >= stride) {
+      p -= stride;
+      ++i;
+    }
+  }
+}
+
+// Column-major copy: Yt[col][Npad], cols = A, B, AB_0..AB_{Dg-1}; rows >= N are zero.
+__global__ void __launch_bounds__(256)
+normalize_cols_kernel(const double *__restrict__ Y, uint64_t N, uint64_t Npad, int Dg, int step,
+                      const double *__restrict__ stats, double *__restrict__ Yt) {
+  const double mean = stats[0], sd = stats[1];
+  const int col = blockIdx.y;
+  const int src = (col == 0) ? 0 : (col == 1 ? step - 1 : col - 1);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Npad;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (i < N) v = __ddiv_rn(__dsub_rn(Y[i * (uint64_t)step + src], mean), sd);
+    Yt[(uint64_t)col * Npad + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// resample multiplicities
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+counts_from_indices_kernel(const int64_t *__restrict__ r, uint64_t N, uint64_t R, uint64_t c0,
+                           uint64_t count, uint64_t Npad, uint32_t *__restrict__ w32, int32_t *overflow) {
+  const uint64_t total = N * count;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = t / count;
+    const uint64_t cl = t - i * count;
+    const int64_t idx = r[i * R + c0 + cl];
+    if (idx < 0 || (uint64_t)idx >= N) {
+      if (overflow) atomicOr(overflow, 2);
+      continue;
+    }
+    const uint64_t pos = cl * Npad + (uint64_t)idx;
+    const unsigned sh = 8u * (unsigned)(pos & 3);
+    const uint32_t old = atomicAdd(w32 + (pos >> 2), 1u << sh);
+    if (((old >> sh) & 0xffu) == 0xffu && overflow) atomicOr(overflow, 1);
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: 128-bit counter, 64-bit key.
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// Draw t of resample c: u64 = philox(counter = (t/2, c), key = seed) word pair (t & 1);
+// index = floor(u64 * N / 2^64).
+__global__ void __launch_bounds__(256)
+counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint32_t *__restrict__ w32) {
+  const uint64_t c = c0 + blockIdx.y;
+  uint32_t *wrow = w32 + ((uint64_t)blockIdx.y * Npad >> 2);
+  const uint64_t npairs = (N + 1) >> 1;
+  for (uint64_t t2 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t2 < npairs;
+       t2 += (uint64_t)gridDim.x * blockDim.x) {
+    const Philox4 p = philox4x32_10((uint32_t)t2, (uint32_t)(t2 >> 32), (uint32_t)c, (uint32_t)(c >> 32),
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t u0 = ((uint64_t)p.y << 32) | p.x;
+    const uint64_t u1 = ((uint64_t)p.w << 32) | p.z;
+    const uint64_t i0 = __umul64hi(u0, N);
+    atomicAdd(wrow + (i0 >> 2), 1u << (8u * (unsigned)(i0 & 3)));
+    if (2 * t2 + 1 < N) {
+      const uint64_t i1 = __umul64hi(u1, N);
+      atomicAdd(wrow + (i1 >> 2), 1u << (8u * (unsigned)(i1 & 3)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// second-order accumulate: warp <-> resample, lane <-> 8x8 (j,k) register tile
+// ------------------------------------------------------------------------------------------
+constexpr int kS2Warps = 8;
+
+__device__ __forceinline__ void load8(const double *__restrict__ p, double (&v)[8]) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double2 d = __ldg(q + t);
+    v[2 * t] = d.x;
+    v[2 * t + 1] = d.y;
+  }
+}
+
+__global__ void __launch_bounds__(kS2Warps * 32, 1)
+s2_accum_tile8_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
+                      const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
+                      uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t c = (uint64_t)blockIdx.x * kS2Warps + warp;
+  if (c >= count) return;
+  const int sp = blockIdx.y;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+  const int TB = Dp >> 3;
+
+  // phase A: off-diagonal tile (tj < tk) of this lane
+  int tj = 0, tk = 0;
+  bool actA = false;
+  {
+    int idx = lane;
+    for (int t = 0; t < TB; ++t) {
+      const int cnt = TB - 1 - t;
+      if (idx < cnt) {
+        tj = t;
+        tk = t + 1 + idx;
+        actA = true;
+        break;
+      }
+      idx -= cnt;
+    }
+  }
+  const int offAx = actA ? Dp + 8 * tj : 0;  // BA_{8tj..}
+  const int offAy = actA ? 8 * tk : 0;       // AB_{8tk..}
+  // phase B: diagonal tile d, rows q and 7-q of its strict upper triangle (7 pairs)
+  const int dB = lane >> 2, qB = lane & 3;
+  const bool actB = dB < TB;
+  const int offBx0 = actB ? Dp + 8 * dB + qB : 0;
+  const int offBx1 = actB ? Dp + 8 * dB + 7 - qB : 0;
+  int offBy[7];
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+    const int kk = (s + 1 > qB) ? (s + 1) : (7 - qB + s + 1);
+    offBy[s] = actB ? 8 * dB + kk : 0;
+  }
+  // phase C: first/total order for columns lane, lane+32
+  const int offC0 = (lane < Dp) ? lane : 0;
+  const int offC1 = (lane + 32 < Dp) ? lane + 32 : 0;
+  const int offAB = 2 * Dp;  // A, B
+
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+  double accB[7];
+#pragma unroll
+  for (int s = 0; s < 7; ++s) accB[s] = 0.0;
+  double s1_0 = 0.0, s1_1 = 0.0, st_0 = 0.0, st_1 = 0.0;
+  double sA = 0.0, sB = 0.0, sAA = 0.0, sBB = 0.0, sAB = 0.0;
+
+  const uint8_t *wrow = w ? w + c * Npad : nullptr;
+  for (uint64_t i0 = row0; i0 < row1; i0 += 32) {
+    const uint64_t i = i0 + lane;
+    unsigned wl = 0;
+    if (i < row1) wl = wrow ? (unsigned)wrow[i] : 1u;
+    unsigned mask = __ballot_sync(kFull, wl != 0);
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double wv = (double)__shfl_sync(kFull, wl, b);
+      const double *__restrict__ row = Yn + (i0 + b) * (uint64_t)stride;
+      {  // phase A
+        double X[8], Yv[8];
+        load8(row + offAx, X);
+        load8(row + offAy, Yv);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const double wx = wv * X[a];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Yv[k], acc[a][k]);
+        }
+      }
+      {  // phase B
+        const double x0 = wv * __ldg(row + offBx0);
+        const double x1 = wv * __ldg(row + offBx1);
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const double y = __ldg(row + offBy[s]);
+          accB[s] = fma((s + 1 > qB) ? x0 : x1, y, accB[s]);
+        }
+      }
+      {  // phase C
+        const double2 ab = __ldg(reinterpret_cast<const double2 *>(row + offAB));
+        const double a = ab.x, bb = ab.y;
+        const double wa = wv * a, wb = wv * bb;
+        sA += wa;
+        sB += wb;
+        sAA = fma(wa, a, sAA);
+        sBB = fma(wb, bb, sBB);
+        sAB = fma(wb, a, sAB);
+        const double t0 = __ldg(row + offC0) - a;
+        const double t1 = __ldg(row + offC1) - a;
+        s1_0 = fma(wb, t0, s1_0);
+        s1_1 = fma(wb, t1, s1_1);
+        st_0 = fma(wv * t0, t0, st_0);
+        st_1 = fma(wv * t1, t1, st_1);
+      }
+    }
+  }
+
+  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+  if (lane == 0) {
+    out[0] = sA;
+    out[1] = sB;
+    out[2] = sAA;
+    out[3] = sBB;
+    out[4] = sAB;
+  }
+  if (lane < Dg) {
+    out[5 + lane] = s1_0;
+    out[5 + Dg + lane] = st_0;
+  }
+  if (lane + 32 < Dg) {
+    out[5 + lane + 32] = s1_1;
+    out[5 + Dg + lane + 32] = st_1;
+  }
+  double *o2 = out + 5 + 2 * Dg;
+  if (actA) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = 8 * tj + a, kk = 8 * tk + k;
+        if (j < Dg && kk < Dg) o2[pair_index(j, kk, Dg)] = acc[a][k];
+      }
+  }
+  if (actB) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const int jj = (s + 1 > qB) ? qB : 7 - qB;
+      const int kk = (s + 1 > qB) ? (s + 1) : (7 - qB + s + 1);
+      const int j = 8 * dB + jj, k = 8 * dB + kk;
+      if (k < Dg) o2[pair_index(j, k, Dg)] = accB[s];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// first/total-order accumulate: lanes <-> rows (column-major Yt), C resamples per warp
+// ------------------------------------------------------------------------------------------
+constexpr int kFoWarps = 8;
+constexpr int kFoJC = 8;
+constexpr int kFoC = 4;
+
+__global__ void __launch_bounds__(kFoWarps * 32)
+fo_accum_kernel(const double *__restrict__ Yt, uint64_t Npad, uint64_t N, int Dg,
+                const uint8_t *__restrict__ w, uint64_t count, uint64_t rows_per_split,
+                double *__restrict__ psum, int nacc) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t cbase = ((uint64_t)blockIdx.x * kFoWarps + warp) * kFoC;
+  if (cbase >= count) return;
+  const int sp = blockIdx.y;
+  const int j0 = blockIdx.z * kFoJC;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+
+  double s1[kFoC][kFoJC], st[kFoC][kFoJC], sc[kFoC][5];
+#pragma unroll
+  for (int c = 0; c < kFoC; ++c) {
+#pragma unroll
+    for (int j = 0; j < kFoJC; ++j) s1[c][j] = st[c][j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) sc[c][q] = 0.0;
+  }
+  const double *colA = Yt;
+  const double *colB = Yt + Npad;
+  const double *colAB = Yt + (uint64_t)(2 + j0) * Npad;
+  int nj = Dg - j0;
+  if (nj > kFoJC) nj = kFoJC;
+
+  for (uint64_t i = row0 + lane; i < row1; i += 32) {
+    const double a = colA[i], b = colB[i];
+    double t[kFoJC];
+#pragma unroll
+    for (int j = 0; j < kFoJC; ++j) t[j] = (j < nj) ? colAB[(uint64_t)j * Npad + i] - a : 0.0;
+#pragma unroll
+    for (int c = 0; c < kFoC; ++c) {
+      if (cbase + c < count) {  // warp-uniform
+        const double wv = w ? (double)w[(cbase + c) * Npad + i] : 1.0;
+        const double wa = wv * a, wb = wv * b;
+        sc[c][0] += wa;
+        sc[c][1] += wb;
+        sc[c][2] = fma(wa, a, sc[c][2]);
+        sc[c][3] = fma(wb, b, sc[c][3]);
+        sc[c][4] = fma(wb, a, sc[c][4]);
+#pragma unroll
+        for (int j = 0; j < kFoJC; ++j) {
+          s1[c][j] = fma(wb, t[j], s1[c][j]);
+          st[c][j] = fma(wv * t[j], t[j], st[c][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kFoC; ++c) {
+    if (cbase + c >= count) continue;
+    double *out = psum + ((uint64_t)sp * count + cbase + c) * (uint64_t)nacc;
+    if (blockIdx.z == 0) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const double v = warp_sum(sc[c][q]);
+        if (lane == 0) out[q] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kFoJC; ++j) {
+      const double v1 = warp_sum(s1[c][j]);
+      const double vt = warp_sum(st[c][j]);
+      if (lane == 0 && j < nj) {
+        out[5 + j0 + j] = v1;
+        out[5 + Dg + j0 + j] = vt;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic accumulate: block <-> (resample, split), thread <-> accumulator
+// ------------------------------------------------------------------------------------------
+constexpr int kGenThreads = 256;
+constexpr int kGenRows = 32;
+
+__global__ void __launch_bounds__(kGenThreads)
+accum_generic_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
+                     int second_order, const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
+                     uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  const uint64_t c = blockIdx.x;
+  const int sp = blockIdx.y;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+  const uint8_t *wrow = w ? w + c * Npad : nullptr;
+  const int offA = (second_order ? 2 : 1) * Dp, offB = offA + 1;
+  __shared__ double sw[kGenRows];
+  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+
+  for (int a0 = 0; a0 < nacc; a0 += kGenThreads) {
+    const int a = a0 + threadIdx.x;
+    // decode accumulator a -> kind, operand columns
+    int kind = -1, cx = 0, cy = 0;
+    if (a < nacc) {
+      if (a < 5) kind = a;
+      else if (a < 5 + Dg) { kind = 5; cx = a - 5; }
+      else if (a < 5 + 2 * Dg) { kind = 6; cx = a - 5 - Dg; }
+      else {
+        kind = 7;
+        int p = a - 5 - 2 * Dg, j = 0;
+        while (p >= Dg - 1 - j) { p -= Dg - 1 - j; ++j; }
+        cx = Dp + j;           // BA_j
+        cy = j + 1 + p;        // AB_k
+      }
+    }
+    double accv = 0.0;
+    for (uint64_t i0 = row0; i0 < row1; i0 += kGenRows) {
+      __syncthreads();
+      if (threadIdx.x < kGenRows) {
+        const uint64_t i = i0 + threadIdx.x;
+        sw[threadIdx.x] = (i < row1) ? (wrow ? (double)wrow[i] : 1.0) : 0.0;
+      }
+      __syncthreads();
+      if (kind < 0) continue;
+      for (int r = 0; r < kGenRows; ++r) {
+        const double wv = sw[r];
+        if (wv == 0.0) continue;
+        const double *row = Yn + (i0 + r) * (uint64_t)stride;
+        const double A = row[offA], B = row[offB];
+        double term;
+        switch (kind) {
+          case 0: term = A; break;
+          case 1: term = B; break;
+          case 2: term = A * A; break;
+          case 3: term = B * B; break;
+          case 4: term = A * B; break;
+          case 5: term = B * (row[cx] - A); break;
+          case 6: { const double t = A - row[cx]; term = t * t; break; }
+          default: term = row[cx] * row[cy]; break;
+        }
+        accv = fma(wv, term, accv);
+      }
+    }
+    if (a < nacc) out[a] = accv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: sums -> S1, ST, S2 per resample
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+finalize_kernel(const double *__restrict__ psum, uint64_t N, int Dg, int second_order, uint64_t count,
+                int nsplit, const double *__restrict__ stats, double *__restrict__ est, int nacc, int nest) {
+  const uint64_t c = blockIdx.x;
+  __shared__ double sc[5];
+  extern __shared__ double s1sh[];  // [Dg]
+  auto total = [&](int a) {
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
+    return v;
+  };
+  const bool constant = !(stats[4] < stats[5]);  // ptp([A;B]) == 0 (or NaN)
+  if (threadIdx.x < 5) sc[threadIdx.x] = total(threadIdx.x);
+  __syncthreads();
+  const double n = (double)N;
+  const double m = (sc[0] + sc[1]) / (2.0 * n);
+  const double V = (sc[2] + sc[3]) / (2.0 * n) - m * m;
+  double *o = est + c * (uint64_t)nest;
+  for (int j = threadIdx.x; j < Dg; j += blockDim.x) {
+    const double s1 = constant ? 0.0 : (total(5 + j) / n) / V;
+    const double st = constant ? 0.0 : 0.5 * (total(5 + Dg + j) / n) / V;
+    s1sh[j] = s1;
+    o[j] = s1;
+    o[Dg + j] = st;
+  }
+  __syncthreads();
+  if (second_order) {
+    const int npairs = Dg * (Dg - 1) / 2;
+    const double mab = sc[4] / n;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+      int q = p, j = 0;
+      while (q >= Dg - 1 - j) { q -= Dg - 1 - j; ++j; }
+      const int k = j + 1 + q;
+      const double vjk = (total(5 + 2 * Dg + p) / n - mab) / V;
+      o[2 * Dg + p] = constant ? 0.0 : vjk - s1sh[j] - s1sh[k];
+    }
+  }
+}
+
+// conf[col] = z * std(est[:, col], ddof=1): two passes (mean, then squared deviations)
+__global__ void __launch_bounds__(512)
+conf_kernel(const double *__restrict__ est, uint64_t R, int ncols, double z, double *__restrict__ conf) {
+  __shared__ double sh[16][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int ty = threadIdx.y;
+  double s = 0.0;
+  if (col < ncols)
+    for (uint64_t c = ty; c < R; c += 16) s += est[c * (uint64_t)ncols + col];
+  sh[ty][threadIdx.x] = s;
+  __syncthreads();
+  double mean = 0.0;
+  for (int q = 0; q < 16; ++q) mean += sh[q][threadIdx.x];
+  mean /= (double)R;
+  __syncthreads();
+  double ss = 0.0;
+  if (col < ncols)
+    for (uint64_t c = ty; c < R; c += 16) {
+      const double d = est[c * (uint64_t)ncols + col] - mean;
+      ss = fma(d, d, ss);
+    }
+  sh[ty][threadIdx.x] = ss;
+  __syncthreads();
+  if (ty == 0 && col < ncols) {
+    double t = 0.0;
+    for (int q = 0; q < 16; ++q) t += sh[q][threadIdx.x];
+    conf[col] = z * sqrt(t / (double)(R - 1));  // R == 1 -> NaN like numpy's ddof=1
+  }
+}
+
+}  // namespace sa
+
+using namespace sa;
+
+extern "C" int sa_row_stride(int Dg, int second_order) { return row_stride(Dg, second_order); }
+extern "C" uint64_t sa_pad_rows(uint64_t N) { return pad_rows(N); }
+extern "C" size_t sa_moments_workspace_bytes(void) { return (size_t)kMomBlocks * 6 * sizeof(double); }
+
+extern "C" int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double *d_stats,
+                              void *d_work, size_t work_bytes) {
+  SA_REQUIRE(d_Y && d_stats && d_work, SA_ERR_ARG, "sa_moments_f64: null pointer");
+  SA_REQUIRE(N >= 1 && step >= 2, SA_ERR_ARG, "sa_moments_f64: bad N/step");
+  SA_REQUIRE(work_bytes >= sa_moments_workspace_bytes(), SA_ERR_WORKSPACE, "sa_moments_f64: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t total = N * (uint64_t)step;
+  int blocks = (int)ceil_div_u64(total, kMomThreads * 4);
+  if (blocks > kMomBlocks) blocks = kMomBlocks;
+  if (blocks < 1) blocks = 1;
+  double *part = (double *)d_work;
+  moments_pass1_kernel<<<blocks, kMomThreads, 0, st>>>(d_Y, total, step, part);
+  moments_final1_kernel<<<1, kMomThreads, 0, st>>>(part, blocks, total, d_stats);
+  moments_pass2_kernel<<<blocks, kMomThreads, 0, st>>>(d_Y, total, d_stats, part + (size_t)kMomBlocks * 5);
+  moments_final2_kernel<<<1, kMomThreads, 0, st>>>(part + (size_t)kMomBlocks * 5, blocks, total, d_stats);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                                const double *d_stats, double *d_Yn, double *d_Yt) {
+  SA_REQUIRE(d_Y && d_stats && (d_Yn || d_Yt), SA_ERR_ARG, "sa_normalize_f64: null pointer");
+  SA_REQUIRE(N >= 1 && Dg >= 1, SA_ERR_ARG, "sa_normalize_f64: bad N/Dg");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  const int sms = sm_count();
+  if (d_Yn) {
+    const uint64_t total = N * (uint64_t)row_stride(Dg, second_order);
+    uint64_t blocks = ceil_div_u64(total, 256);
+    if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
+    normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, second_order, d_stats, d_Yn);
+  }
+  if (d_Yt) {
+    SA_REQUIRE(Dg + 2 <= 65535, SA_ERR_UNSUPPORTED, "sa_normalize_f64: too many groups for the column copy");
+    const uint64_t Npad = pad_rows(N);
+    uint64_t bx = ceil_div_u64(Npad, 256);
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)(Dg + 2));
+    normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
+  }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
+                                      uint64_t count, uint8_t *d_w, int32_t *d_overflow) {
+  SA_REQUIRE(d_r && d_w, SA_ERR_ARG, "sa_counts_from_indices: null pointer");
+  SA_REQUIRE(N >= 1 && c0 + count <= R, SA_ERR_ARG, "sa_counts_from_indices: resample range out of bounds");
+  SA_REQUIRE(((uintptr_t)d_w & 3) == 0, SA_ERR_ARG, "sa_counts_from_indices: d_w not 4-byte aligned");
+  if (count == 0) return SA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t Npad = pad_rows(N);
+  SA_CUDA(cudaMemsetAsync(d_w, 0, count * Npad, st));
+  uint64_t blocks = ceil_div_u64(N * count, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  counts_from_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_r, N, R, c0, count, Npad, (uint32_t *)d_w,
+                                                              d_overflow);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                uint8_t *d_w, int32_t *d_overflow) {
+  (void)d_overflow;  // P(multiplicity > 255) < 1e-500 for N iid uniform draws over N rows, N >= 256
+  SA_REQUIRE(d_w, SA_ERR_ARG, "sa_counts_philox: null pointer");
+  SA_REQUIRE(N >= 1, SA_ERR_ARG, "sa_counts_philox: bad N");
+  SA_REQUIRE(((uintptr_t)d_w & 3) == 0, SA_ERR_ARG, "sa_counts_philox: d_w not 4-byte aligned");
+  if (count == 0) return SA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t Npad = pad_rows(N);
+  SA_CUDA(cudaMemsetAsync(d_w, 0, count * Npad, st));
+  const uint64_t npairs = (N + 1) / 2;
+  uint64_t bx = ceil_div_u64(npairs, 256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  for (uint64_t done = 0; done < count; done += 65535) {
+    const uint64_t nb = (count - done < 65535) ? count - done : 65535;
+    dim3 grid((unsigned)bx, (unsigned)nb);
+    counts_philox_kernel<<<grid, 256, 0, st>>>(seed, N, c0 + done, Npad, (uint32_t *)(d_w + done * Npad));
+  }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// algo: 0 auto, 1 generic, 2 second-order tile8, 3 first-order
+extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
+                                          int Dg, int second_order, const uint8_t *d_w, uint64_t count,
+                                          int nsplit, double *d_psum, int algo) {
+  SA_REQUIRE(d_psum, SA_ERR_ARG, "sa_sobol_accumulate_f64: null pointer");
+  SA_REQUIRE(N >= 1 && Dg >= 1 && count >= 1 && nsplit >= 1, SA_ERR_ARG, "sa_sobol_accumulate_f64: bad shape");
+  SA_REQUIRE(d_w != nullptr || count == 1, SA_ERR_ARG, "sa_sobol_accumulate_f64: point estimate needs count == 1");
+  SA_REQUIRE(nsplit <= 65535, SA_ERR_ARG, "sa_sobol_accumulate_f64: nsplit too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Dp = round_up8(Dg);
+  const int stride = row_stride(Dg, second_order);
+  const uint64_t Npad = pad_rows(N);
+  const int nacc = SA_NACC(Dg, second_order);
+  uint64_t rps = ceil_div_u64(N, nsplit);
+  rps = (rps + 31) & ~(uint64_t)31;
+  if (algo == 0) algo = second_order ? (Dg <= 64 ? 2 : 1) : 3;
+  if (algo == 2) {
+    SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
+    SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
+    SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
+    const uint64_t bx = ceil_div_u64(count, kS2Warps);
+    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
+    dim3 grid((unsigned)bx, (unsigned)nsplit);
+    s2_accum_tile8_kernel<<<grid, kS2Warps * 32, 0, st>>>(d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum,
+                                                         nacc);
+  } else if (algo == 3) {
+    SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
+    SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt is null");
+    const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * kFoC);
+    const int nz = (Dg + kFoJC - 1) / kFoJC;
+    SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the first-order kernel");
+    dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
+    fo_accum_kernel<<<grid, kFoWarps * 32, 0, st>>>(d_Yt, Npad, N, Dg, d_w, count, rps, d_psum, nacc);
+  } else if (algo == 1) {
+    SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
+    SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
+    dim3 grid((unsigned)count, (unsigned)nsplit);
+    accum_generic_kernel<<<grid, kGenThreads, 0, st>>>(d_Yn, stride, Dp, N, Dg, second_order, d_w, Npad, count,
+                                                      rps, d_psum, nacc);
+  } else {
+    SA_REQUIRE(false, SA_ERR_ARG, "sa_sobol_accumulate_f64: unknown algo %d", algo);
+  }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N, int Dg,
+                                       int second_order, const uint8_t *d_w, uint64_t count, int nsplit,
+                                       double *d_psum) {
+  return sa_sobol_accumulate_ex_f64(stream, d_Yn, d_Yt, N, Dg, second_order, d_w, count, nsplit, d_psum, 0);
+}
+
+extern "C" int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg, int second_order,
+                                     uint64_t count, int nsplit, const double *d_stats, double *d_est) {
+  SA_REQUIRE(d_psum && d_stats && d_est, SA_ERR_ARG, "sa_sobol_finalize_f64: null pointer");
+  SA_REQUIRE(N >= 1 && Dg >= 1 && count >= 1 && nsplit >= 1, SA_ERR_ARG, "sa_sobol_finalize_f64: bad shape");
+  SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
+  finalize_kernel<<<(unsigned)count, 128, (size_t)Dg * sizeof(double), (cudaStream_t)stream>>>(
+      d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
+      SA_NEST(Dg, second_order));
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
+                                 double *d_conf) {
+  SA_REQUIRE(d_est && d_conf, SA_ERR_ARG, "sa_sobol_conf_f64: null pointer");
+  SA_REQUIRE(R >= 1 && ncols >= 1, SA_ERR_ARG, "sa_sobol_conf_f64: bad shape");
+  dim3 block(32, 16);
+  conf_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, z, d_conf);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

@@ -1,0 +1,501 @@
+// Saltelli sample generation: Sobol' draw (Joe-Kuo direction vectors, Gray-code skip-ahead)
+// fused with the A/AB/BA/B cross-matrix build and the uniform bounds scaling.
+//
+// Reference behaviour replaced: src/SALib/sample/sobol.py:107-188 (and saltelli.py:147-203).
+//   point k:   x_k[d] = shift[d] ^ XOR_{b in gray(k)} sv[d][b];  value = double(x) * 2^-30
+//   step k->k+1: x ^= sv[d][ctz(k+1)]                           (sobol_sequence.py:86-89)
+//   scaling:   round(round(v * span) + lb)                       (util/__init__.py:49-53)
+//   layout:    base row i -> rows i*step + {0: A, 1+k: AB_k, 1+Dg+k: BA_k, step-1: B}
+//
+// The kernel is bound by HBM writes (step*D*8 bytes per base row, nothing read but a
+// [2D][30] u32 table), so the design is about issuing 16-byte, fully coalesced, streaming
+// stores with as little integer work per store as possible:
+//   * "register path" (D even and D/2 | 32 or 32 | D/2): a warp owns a run of consecutive base
+//     rows; each lane owns one column pair, keeps the four Sobol' states (a0,a1,b0,b1) in
+//     registers, advances them with one XOR per row and writes every slot with st.global.cs.v2.f64.
+//   * "generic path" (any D): the block stages the scaled A/B rows of a chunk in shared memory and
+//     writes the chunk's contiguous output region flat, decoding (row, slot, col) with a
+//     multiply-shift division.
+#include "common.cuh"
+
+namespace sa {
+
+constexpr double kTwoPowMinus30 = 1.0 / 1073741824.0;
+
+// Closed form for point k in dimension d.
+__device__ __forceinline__ uint32_t sobol_point(const uint32_t *__restrict__ sv, uint32_t shift,
+                                                int d, uint64_t k) {
+  uint32_t g = (uint32_t)(k ^ (k >> 1));
+  uint32_t x = shift;
+  const uint32_t *v = sv + (size_t)d * SA_SOBOL_BITS;
+#pragma unroll
+  for (int b = 0; b < SA_SOBOL_BITS; ++b) {
+    if ((g >> b) & 1u) x ^= __ldg(v + b);
+  }
+  return x;
+}
+
+__device__ __forceinline__ double scale_value(uint32_t x, double span, double lb) {
+  // two roundings, never an FMA
+  return __dadd_rn(__dmul_rn((double)x * kTwoPowMinus30, span), lb);
+}
+
+// Does slot s take column (with group g) from B?  sample/sobol.py:149-186
+__device__ __forceinline__ bool slot_uses_b(int s, int g, int Dg, int step, int second_order) {
+  const int k1 = s - 1;
+  const int k2 = s - 1 - Dg;
+  const bool in_ab = (unsigned)k1 < (unsigned)Dg;
+  const bool in_ba = second_order && ((unsigned)k2 < (unsigned)Dg);
+  const bool last = (s == step - 1);
+  return last | (in_ab & (g == k1)) | (in_ba & (g != k2));
+}
+
+// ------------------------------------------------------------------------------------------
+// Register path
+// ------------------------------------------------------------------------------------------
+template <bool GROUPED>
+__global__ void __launch_bounds__(256)
+saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
+                    uint64_t first_index, uint64_t n, int D, int Dg,
+                    const int32_t *__restrict__ gcol, int step, int second_order,
+                    const double *__restrict__ lb, const double *__restrict__ span,
+                    double *__restrict__ out, int rows_per_warp) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t r0 = gw * (uint64_t)rows_per_warp;
+  if (r0 >= n) return;
+  const uint64_t r1 = (r0 + rows_per_warp < n) ? r0 + rows_per_warp : n;
+
+  const int halfD = D >> 1;
+  int ncb, nsub, sub, jp_lane;
+  if (halfD >= 32) {
+    ncb = halfD >> 5;
+    nsub = 1;
+    sub = 0;
+    jp_lane = lane;
+  } else {
+    ncb = 1;
+    nsub = 32 / halfD;
+    sub = lane / halfD;
+    jp_lane = lane - sub * halfD;
+  }
+
+  for (int cb = 0; cb < ncb; ++cb) {
+    const int j0 = 2 * (cb * 32 + jp_lane);
+    const int j1 = j0 + 1;
+    const int g0 = GROUPED ? gcol[j0] : j0;
+    const int g1 = GROUPED ? gcol[j1] : j1;
+    const double lb0 = lb[j0], lb1 = lb[j1], sp0 = span[j0], sp1 = span[j1];
+    const uint32_t *va0 = sv + (size_t)j0 * SA_SOBOL_BITS;
+    const uint32_t *va1 = sv + (size_t)j1 * SA_SOBOL_BITS;
+    const uint32_t *vb0 = sv + (size_t)(D + j0) * SA_SOBOL_BITS;
+    const uint32_t *vb1 = sv + (size_t)(D + j1) * SA_SOBOL_BITS;
+    uint64_t k = first_index + r0;
+    uint32_t xa0 = sobol_point(sv, shift ? shift[j0] : 0u, j0, k);
+    uint32_t xa1 = sobol_point(sv, shift ? shift[j1] : 0u, j1, k);
+    uint32_t xb0 = sobol_point(sv, shift ? shift[D + j0] : 0u, D + j0, k);
+    uint32_t xb1 = sobol_point(sv, shift ? shift[D + j1] : 0u, D + j1, k);
+
+    for (uint64_t r = r0; r < r1; ++r) {
+      const double a0 = scale_value(xa0, sp0, lb0);
+      const double a1 = scale_value(xa1, sp1, lb1);
+      const double b0 = scale_value(xb0, sp0, lb0);
+      const double b1 = scale_value(xb1, sp1, lb1);
+      double *row = out + (r * (uint64_t)step) * (uint64_t)D + j0;
+#pragma unroll 4
+      for (int s = sub; s < step; s += nsub) {
+        const bool u0 = slot_uses_b(s, g0, Dg, step, second_order);
+        const bool u1 = slot_uses_b(s, g1, Dg, step, second_order);
+        double2 v = make_double2(u0 ? b0 : a0, u1 ? b1 : a1);
+        __stcs(reinterpret_cast<double2 *>(row + (size_t)s * D), v);
+      }
+      // advance to point k+1: flip direction number ctz(k+1)
+      ++k;
+      const int c = __ffsll((long long)k) - 1;
+      if (c < SA_SOBOL_BITS) {
+        xa0 ^= __ldg(va0 + c);
+        xa1 ^= __ldg(va1 + c);
+        xb0 ^= __ldg(vb0 + c);
+        xb1 ^= __ldg(vb1 + c);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic path
+// ------------------------------------------------------------------------------------------
+// Stage the scaled A/B values of base rows [base, base+nv) in shared memory: sa/sb [BR][D].
+__device__ __forceinline__ void stage_rows(const uint32_t *__restrict__ sv,
+                                           const uint32_t *__restrict__ shift, uint64_t k0, int nv,
+                                           int D, const double *__restrict__ lb,
+                                           const double *__restrict__ span, double *sa, double *sb) {
+  const int dims = 2 * D;
+  int nseg = blockDim.x / dims;
+  if (nseg < 1) nseg = 1;
+  if (nseg > nv) nseg = nv;
+  const int seglen = (nv + nseg - 1) / nseg;
+  for (int item = threadIdx.x; item < dims * nseg; item += blockDim.x) {
+    const int seg = item / dims;
+    const int d = item - seg * dims;
+    const int rs = seg * seglen;
+    const int re = (rs + seglen < nv) ? rs + seglen : nv;
+    if (rs >= re) continue;
+    const int col = (d < D) ? d : d - D;
+    double *dst = (d < D) ? sa : sb;
+    const double l = lb[col], sp = span[col];
+    const uint32_t *v = sv + (size_t)d * SA_SOBOL_BITS;
+    uint64_t k = k0 + rs;
+    uint32_t x = sobol_point(sv, shift ? shift[d] : 0u, d, k);
+    for (int r = rs; r < re; ++r) {
+      dst[(size_t)r * D + col] = scale_value(x, sp, l);
+      ++k;
+      const int c = __ffsll((long long)k) - 1;
+      if (c < SA_SOBOL_BITS) x ^= __ldg(v + c);
+    }
+  }
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(256)
+saltelli_generic_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
+                        uint64_t first_index, uint64_t n, int D, int Dg,
+                        const int32_t *__restrict__ gcol, int step, int second_order,
+                        const double *__restrict__ lb, const double *__restrict__ span,
+                        double *__restrict__ out, int BR, uint32_t magic_rowlen, uint32_t magic_D) {
+  extern __shared__ double smem[];
+  double *sa = smem;
+  double *sb = smem + (size_t)BR * D;
+  const uint32_t rowlen = (uint32_t)step * (uint32_t)D;
+  const uint64_t nchunks = ceil_div_u64(n, BR);
+  for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const uint64_t base = chunk * (uint64_t)BR;
+    const int nv = (int)((n - base < (uint64_t)BR) ? (n - base) : BR);
+    stage_rows(sv, shift, first_index + base, nv, D, lb, span, sa, sb);
+    __syncthreads();
+    const uint32_t total = (uint32_t)nv * rowlen;
+    double *dst = out + base * (uint64_t)rowlen;
+    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+      const uint32_t r = fastdiv(e, rowlen, magic_rowlen);
+      const uint32_t q = e - r * rowlen;
+      const uint32_t s = fastdiv(q, (uint32_t)D, magic_D);
+      const uint32_t j = q - s * (uint32_t)D;
+      const int g = GROUPED ? gcol[j] : (int)j;
+      const bool ub = slot_uses_b((int)s, g, Dg, step, second_order);
+      const double v = ub ? sb[(size_t)r * D + j] : sa[(size_t)r * D + j];
+      __stcs(dst + e, v);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Test functions (X -> Y)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ishigami_value(double x0, double x1, double x2, double A, double B) {
+  // Ishigami.py:55-59: sin(x0) + A*sin(x1)^2 + B*x2^4*sin(x0), evaluated left to right
+  const double s0 = sin(x0);
+  const double s1 = sin(x1);
+  const double x2sq = __dmul_rn(x2, x2);
+  const double t1 = __dmul_rn(A, __dmul_rn(s1, s1));
+  const double t2 = __dmul_rn(__dmul_rn(B, __dmul_rn(x2sq, x2sq)), s0);
+  return __dadd_rn(__dadd_rn(s0, t1), t2);
+}
+
+__global__ void eval_ishigami_kernel(const double *__restrict__ X, uint64_t rows, double A, double B,
+                                     double *__restrict__ Y) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double *x = X + 3 * i;
+    Y[i] = ishigami_value(x[0], x[1], x[2], A, B);
+  }
+}
+
+// One factor of the G function, Sobol_G.py:79-83:
+//   ((1+alpha) * |2*frac(x+delta) - 1|^alpha + a) / (1 + a)
+__device__ __forceinline__ double g_factor(double x, double a, double delta, double alpha) {
+  const double sx = __dadd_rn(x, delta);
+  const double fx = __dsub_rn(sx, trunc(sx));
+  double t = fabs(__dsub_rn(__dmul_rn(2.0, fx), 1.0));
+  if (alpha != 1.0) t = pow(t, alpha);
+  return __ddiv_rn(__dadd_rn(__dmul_rn(__dadd_rn(1.0, alpha), t), a), __dadd_rn(1.0, a));
+}
+
+// LPR lanes cooperate on one row; the product is taken in column order within a lane and
+// combined across lanes by a shuffle tree (rounding differs from the reference's strictly
+// sequential product by a few ulp; the fused kernel below is strictly sequential).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+eval_sobol_g_kernel(const double *__restrict__ X, uint64_t rows, int D, const double *__restrict__ a,
+                    const double *__restrict__ delta, const double *__restrict__ alpha,
+                    double *__restrict__ Y, int32_t *flag) {
+  const int sub = threadIdx.x % LPR;
+  const uint64_t rows_per_block = blockDim.x / LPR;
+  int bad = 0;
+  for (uint64_t row = (uint64_t)blockIdx.x * rows_per_block + threadIdx.x / LPR;
+       row < ceil_div_u64(rows, rows_per_block) * rows_per_block;
+       row += (uint64_t)gridDim.x * rows_per_block) {
+    double p = 1.0;
+    if (row < rows) {
+      const double *x = X + row * (uint64_t)D;
+      for (int j = sub; j < D; j += LPR) {
+        const double v = x[j];
+        bad |= (v < 0.0) ? 1 : 0;
+        bad |= (v > 1.0) ? 2 : 0;
+        p = __dmul_rn(p, g_factor(v, a[j], delta ? delta[j] : 0.0, alpha ? alpha[j] : 1.0));
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) p = __dmul_rn(p, __shfl_xor_sync(kFull, p, o));
+    if (sub == 0 && row < rows) Y[row] = p;
+  }
+  if (flag && bad) atomicOr(flag, bad);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused: Sobol' indices -> Y (X never written)
+// ------------------------------------------------------------------------------------------
+// Block stages BR base rows (scaled a/b), converts them in place to G factors fa/fb, then each
+// thread owns one (base row, slot) output and multiplies D factors in column order -- the
+// same order as the reference's row.prod().
+template <bool GROUPED>
+__global__ void __launch_bounds__(256)
+saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
+                       uint64_t first_index, uint64_t n, int D, int Dg,
+                       const int32_t *__restrict__ gcol, int step, int second_order,
+                       const double *__restrict__ lb, const double *__restrict__ span,
+                       const double *__restrict__ a, const double *__restrict__ delta,
+                       const double *__restrict__ alpha, double *__restrict__ Y, int32_t *flag,
+                       int BR) {
+  extern __shared__ double smem[];
+  double *sa = smem;
+  double *sb = smem + (size_t)BR * D;
+  int *sg = reinterpret_cast<int *>(smem + 2 * (size_t)BR * D);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) sg[j] = GROUPED ? gcol[j] : j;
+  const uint64_t nchunks = ceil_div_u64(n, BR);
+  int bad = 0;
+  for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const uint64_t base = chunk * (uint64_t)BR;
+    const int nv = (int)((n - base < (uint64_t)BR) ? (n - base) : BR);
+    stage_rows(sv, shift, first_index + base, nv, D, lb, span, sa, sb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nv * D; e += blockDim.x) {
+      const int j = e % D;
+      const double aj = a[j], dj = delta ? delta[j] : 0.0, al = alpha ? alpha[j] : 1.0;
+      const double va = sa[e], vb = sb[e];
+      bad |= (va < 0.0 || vb < 0.0) ? 1 : 0;
+      bad |= (va > 1.0 || vb > 1.0) ? 2 : 0;
+      sa[e] = g_factor(va, aj, dj, al);
+      sb[e] = g_factor(vb, aj, dj, al);
+    }
+    __syncthreads();
+    const int total = nv * step;
+    for (int o = threadIdx.x; o < total; o += blockDim.x) {
+      const int r = o / step;
+      const int s = o - r * step;
+      const double *fa = sa + (size_t)r * D;
+      const double *fb = sb + (size_t)r * D;
+      double p = 1.0;
+      for (int j = 0; j < D; ++j) {
+        const bool ub = slot_uses_b(s, sg[j], Dg, step, second_order);
+        p = __dmul_rn(p, ub ? fb[j] : fa[j]);
+      }
+      __stcs(Y + base * (uint64_t)step + o, p);
+    }
+    __syncthreads();
+  }
+  if (flag && bad) atomicOr(flag, bad);
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(256)
+saltelli_eval_ishigami_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
+                              uint64_t first_index, uint64_t n, int Dg,
+                              const int32_t *__restrict__ gcol, int step, int second_order,
+                              const double *__restrict__ lb, const double *__restrict__ span,
+                              double A, double B, double *__restrict__ Y) {
+  // one thread per base row: 6 Sobol' values, `step` outputs
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double xa[3], xb[3];
+    int g[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      xa[j] = scale_value(sobol_point(sv, shift ? shift[j] : 0u, j, first_index + i), span[j], lb[j]);
+      xb[j] = scale_value(sobol_point(sv, shift ? shift[3 + j] : 0u, 3 + j, first_index + i), span[j], lb[j]);
+      g[j] = GROUPED ? gcol[j] : j;
+    }
+    for (int s = 0; s < step; ++s) {
+      double x[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) x[j] = slot_uses_b(s, g[j], Dg, step, second_order) ? xb[j] : xa[j];
+      Y[i * (uint64_t)step + s] = ishigami_value(x[0], x[1], x[2], A, B);
+    }
+  }
+}
+
+static bool reg_path_ok(int D) {
+  if (D < 2 || (D & 1)) return false;
+  const int h = D / 2;
+  return (h >= 32) ? (h % 32 == 0) : (32 % h == 0);
+}
+
+static int check_sample_args(const char *fn, const uint32_t *d_sv, uint64_t first_index, uint64_t n,
+                             int D, int Dg, const int32_t *gcol, const double *lb, const double *span,
+                             const void *out) {
+  SA_REQUIRE(d_sv && lb && span && out, SA_ERR_ARG, "%s: null pointer", fn);
+  SA_REQUIRE(D >= 1 && Dg >= 1 && Dg <= D, SA_ERR_ARG, "%s: bad D=%d Dg=%d", fn, D, Dg);
+  SA_REQUIRE(gcol != nullptr || Dg == D, SA_ERR_ARG, "%s: Dg != D needs group_of_col", fn);
+  SA_REQUIRE(2 * (int64_t)D <= SA_SOBOL_MAXDIM, SA_ERR_RANGE, "%s: 2*D=%d exceeds %d Sobol' dimensions",
+             fn, 2 * D, SA_SOBOL_MAXDIM);
+  SA_REQUIRE(first_index + n <= (1ull << SA_SOBOL_BITS) && first_index + n >= first_index, SA_ERR_RANGE,
+             "%s: index range [%llu, %llu) exceeds 2^30 points", fn, (unsigned long long)first_index,
+             (unsigned long long)(first_index + n));
+  return SA_OK;
+}
+
+}  // namespace sa
+
+using namespace sa;
+
+extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                      uint64_t first_index, uint64_t n, int D, int Dg,
+                                      const int32_t *d_group_of_col, int second_order,
+                                      const double *d_lb, const double *d_span, double *d_out) {
+  int rc = check_sample_args("sa_saltelli_sample_f64", d_sv, first_index, n, D, Dg, d_group_of_col, d_lb,
+                             d_span, d_out);
+  if (rc) return rc;
+  if (n == 0) return SA_OK;
+  SA_REQUIRE(((uintptr_t)d_out & 15) == 0, SA_ERR_ARG, "sa_saltelli_sample_f64: d_out not 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  const bool grouped = d_group_of_col != nullptr;
+  const int sms = sm_count();
+  if (reg_path_ok(D)) {
+    // enough warps to fill the machine, long enough row runs to amortise the closed form
+    uint64_t rpw = n / ((uint64_t)sms * 8 * 8);
+    if (rpw < 1) rpw = 1;
+    if (rpw > 16) rpw = 16;
+    const uint64_t warps = ceil_div_u64(n, rpw);
+    const uint64_t blocks = ceil_div_u64(warps, 8);
+    SA_REQUIRE(blocks < (1ull << 31), SA_ERR_UNSUPPORTED, "sa_saltelli_sample_f64: grid too large");
+    if (grouped)
+      saltelli_reg_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg,
+                                                                 d_group_of_col, step, second_order, d_lb,
+                                                                 d_span, d_out, (int)rpw);
+    else
+      saltelli_reg_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg,
+                                                                  nullptr, step, second_order, d_lb, d_span,
+                                                                  d_out, (int)rpw);
+  } else {
+    const size_t row_bytes = 2 * (size_t)D * sizeof(double);
+    SA_REQUIRE(row_bytes <= 200 * 1024, SA_ERR_UNSUPPORTED,
+               "sa_saltelli_sample_f64: D=%d needs %zu B of shared memory per base row", D, row_bytes);
+    int BR = (int)((48 * 1024) / row_bytes);
+    if (BR < 1) BR = 1;
+    if (BR > 32) BR = 32;
+    const uint64_t rowlen = (uint64_t)step * D;
+    while (BR > 1 && (uint64_t)BR * rowlen >= (1ull << 31)) BR >>= 1;
+    SA_REQUIRE((uint64_t)BR * rowlen < (1ull << 31), SA_ERR_UNSUPPORTED,
+               "sa_saltelli_sample_f64: row of %llu values too long", (unsigned long long)rowlen);
+    const size_t smem = (size_t)BR * row_bytes;
+    const uint32_t m_rowlen = fastdiv_magic((uint64_t)BR * rowlen, (uint32_t)rowlen);
+    const uint32_t m_D = fastdiv_magic(rowlen, (uint32_t)D);
+    uint64_t blocks = ceil_div_u64(n, BR);
+    if (blocks > (uint64_t)sms * 16) blocks = (uint64_t)sms * 16;
+    auto kern = grouped ? saltelli_generic_kernel<true> : saltelli_generic_kernel<false>;
+    if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, 256, smem, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
+                                             second_order, d_lb, d_span, d_out, BR, m_rowlen, m_D);
+  }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_eval_ishigami_f64(void *stream, const double *d_X, uint64_t rows, double A, double B,
+                                    double *d_Y) {
+  SA_REQUIRE(d_X && d_Y, SA_ERR_ARG, "sa_eval_ishigami_f64: null pointer");
+  if (rows == 0) return SA_OK;
+  uint64_t blocks = ceil_div_u64(rows, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  eval_ishigami_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_X, rows, A, B, d_Y);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_eval_sobol_g_f64(void *stream, const double *d_X, uint64_t rows, int D, const double *d_a,
+                                   const double *d_delta, const double *d_alpha, double *d_Y,
+                                   int32_t *d_flag) {
+  SA_REQUIRE(d_X && d_Y && d_a, SA_ERR_ARG, "sa_eval_sobol_g_f64: null pointer");
+  SA_REQUIRE(D >= 1, SA_ERR_ARG, "sa_eval_sobol_g_f64: bad D=%d", D);
+  if (rows == 0) return SA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int lpr = 1;
+  while (lpr < 32 && lpr < D) lpr <<= 1;
+  const uint64_t rows_per_block = 256 / lpr;
+  uint64_t blocks = ceil_div_u64(rows, rows_per_block);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+#define SA_G_CASE(L)                                                                                   \
+  case L:                                                                                              \
+    eval_sobol_g_kernel<L><<<(unsigned)blocks, 256, 0, st>>>(d_X, rows, D, d_a, d_delta, d_alpha, d_Y, \
+                                                            d_flag);                                   \
+    break;
+  switch (lpr) {
+    SA_G_CASE(1) SA_G_CASE(2) SA_G_CASE(4) SA_G_CASE(8) SA_G_CASE(16) SA_G_CASE(32)
+  }
+#undef SA_G_CASE
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                            uint64_t first_index, uint64_t n, int D, int Dg,
+                                            const int32_t *d_group_of_col, int second_order,
+                                            const double *d_lb, const double *d_span, const double *d_a,
+                                            const double *d_delta, const double *d_alpha, double *d_Y,
+                                            int32_t *d_flag) {
+  int rc = check_sample_args("sa_saltelli_eval_sobol_g_f64", d_sv, first_index, n, D, Dg, d_group_of_col,
+                             d_lb, d_span, d_Y);
+  if (rc) return rc;
+  SA_REQUIRE(d_a != nullptr, SA_ERR_ARG, "sa_saltelli_eval_sobol_g_f64: null a");
+  if (n == 0) return SA_OK;
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  const size_t row_bytes = 2 * (size_t)D * sizeof(double);
+  SA_REQUIRE(row_bytes + D * sizeof(int) <= 200 * 1024, SA_ERR_UNSUPPORTED,
+             "sa_saltelli_eval_sobol_g_f64: D=%d too large", D);
+  int BR = (int)((32 * 1024) / row_bytes);
+  if (BR < 1) BR = 1;
+  if (BR > 64) BR = 64;
+  const size_t smem = (size_t)BR * row_bytes + (size_t)D * sizeof(int);
+  uint64_t blocks = ceil_div_u64(n, BR);
+  if (blocks > (uint64_t)sm_count() * 16) blocks = (uint64_t)sm_count() * 16;
+  auto kern = d_group_of_col ? saltelli_eval_g_kernel<true> : saltelli_eval_g_kernel<false>;
+  if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, D, Dg,
+                                                             d_group_of_col, step, second_order, d_lb, d_span,
+                                                             d_a, d_delta, d_alpha, d_Y, d_flag, BR);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                             uint64_t first_index, uint64_t n, int Dg,
+                                             const int32_t *d_group_of_col, int second_order,
+                                             const double *d_lb, const double *d_span, double A, double B,
+                                             double *d_Y) {
+  int rc = check_sample_args("sa_saltelli_eval_ishigami_f64", d_sv, first_index, n, 3, Dg, d_group_of_col,
+                             d_lb, d_span, d_Y);
+  if (rc) return rc;
+  if (n == 0) return SA_OK;
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  uint64_t blocks = ceil_div_u64(n, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  if (d_group_of_col)
+    saltelli_eval_ishigami_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_sv, d_shift, first_index, n, Dg, d_group_of_col, step, second_order, d_lb, d_span, A, B, d_Y);
+  else
+    saltelli_eval_ishigami_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_sv, d_shift, first_index, n, Dg, nullptr, step, second_order, d_lb, d_span, A, B, d_Y);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

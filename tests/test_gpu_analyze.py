@@ -1,0 +1,209 @@
+"""GPU parity: sobol.analyze vs the frozen reference outputs and the oracle.
+
+Tolerances (float64): rtol 1e-10 as BASELINE north_star states, plus atol 1e-13 for indices that are
+differences of O(1) quantities (S2 ~ 5e-4, S1[x3] ~ -0.013)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden, problem_from
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-10, 1e-13
+ANALYZE_CASES = ["ishigami_n1024_r100", "ishigami_n256_c1_r50", "g8_n512_r64", "g8_n512_c1_r64",
+                 "g16_n256_r32", "grp3_n512_r40", "g64_n128_r16"]
+ISHI = {"num_vars": 3, "names": ["x1", "x2", "x3"], "bounds": [[-np.pi, np.pi]] * 3}
+
+
+def _cmp(S, ref, D, c2, keep=True, rtol=RTOL, atol=ATOL):
+    keys = ["S1", "S1_conf", "ST", "ST_conf"] + (["S1_conf_all", "ST_conf_all"] if keep else [])
+    for k in keys:
+        np.testing.assert_allclose(S[k], ref[k], rtol=rtol, atol=atol, err_msg=k)
+    if c2:
+        iu, il = np.triu_indices(D, 1), np.tril_indices(D)
+        for k in ("S2", "S2_conf"):
+            np.testing.assert_allclose(S[k][iu], np.asarray(ref[k])[iu], rtol=rtol, atol=atol, err_msg=k)
+            assert np.isnan(S[k][il]).all()
+
+
+@pytest.mark.parametrize("name", ANALYZE_CASES)
+def test_matches_frozen_reference(name):
+    """Drop-in call, numpy resample indices from the same seed -> same dict as the reference."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_" + name)
+    p = problem_from(z)
+    D = z["S1"].shape[0]
+    S = sobol.analyze(p, z["Y"], calc_second_order=bool(z["c2"]), num_resamples=int(z["R"]),
+                      conf_level=float(z["conf"]), keep_resamples=True, seed=int(z["seed"]))
+    _cmp(S, z, D, bool(z["c2"]))
+    assert S.problem is p
+    dfs = S.to_df()
+    assert len(dfs) == (3 if bool(z["c2"]) else 2)
+
+
+@pytest.mark.parametrize("name,algo", [("g8_n512_r64", "generic"), ("g16_n256_r32", "generic"),
+                                       ("g8_n512_c1_r64", "generic"), ("g64_n128_r16", "generic"),
+                                       ("grp3_n512_r40", "generic")])
+def test_generic_kernel_matches_frozen_reference(name, algo):
+    """The fallback kernel is an independent implementation of the same sums."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_" + name)
+    D = z["S1"].shape[0]
+    S = sobol.analyze_device(problem_from(z), z["Y"], calc_second_order=bool(z["c2"]), conf_level=float(z["conf"]),
+                             keep_resamples=True, r=z["r"].astype(np.int64), algo=algo)
+    _cmp(S, z, D, bool(z["c2"]))
+
+
+def test_cli_golden_table():
+    """reference tests/test_cli_analyze.py:250-275 -- the printed table, 6 decimals, R=1000, seed=100."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_cli_golden")
+    S = sobol.analyze(dict(ISHI), z["Y"], calc_second_order=True, num_resamples=1000, conf_level=0.95, seed=100)
+    fmt = lambda v: ["%.6f" % x for x in np.asarray(v).ravel()]  # noqa: E731
+    assert fmt(S["ST"]) == ["0.557947", "0.442189", "0.241402"]
+    assert fmt(S["ST_conf"]) == ["0.085851", "0.041396", "0.028607"]
+    assert fmt(S["S1"]) == ["0.310576", "0.443653", "-0.012962"]
+    assert fmt(S["S1_conf"]) == ["0.059615", "0.053436", "0.053891"]
+    iu = np.triu_indices(3, 1)
+    assert fmt(S["S2"][iu]) == ["-0.014397", "0.246231", "0.000539"]
+    assert fmt(S["S2_conf"][iu]) == ["0.083679", "0.103117", "0.064169"]
+    _cmp(S, z, 3, True, keep=False)
+
+
+@pytest.mark.parametrize("D,N,c2,R", [(3, 100, True, 10), (5, 1000, False, 37), (9, 333, True, 20),
+                                      (24, 200, True, 12), (40, 96, True, 9), (64, 300, True, 40),
+                                      (70, 64, True, 6), (70, 64, False, 6), (20, 5000, False, 50),
+                                      (8, 20000, True, 8)])
+def test_matches_oracle_over_shapes(D, N, c2, R):
+    """Ragged N (not a multiple of 32), Dg not a multiple of 8, Dg > 64 (generic fallback), row splits."""
+    from oracle import analyze as o_analyze
+    from salib_b200.analyze import sobol
+
+    rng = np.random.default_rng(D * 7 + N)
+    step = 2 * D + 2 if c2 else D + 2
+    base = rng.normal(size=(N, 1))
+    Y = (base + 0.5 * rng.normal(size=(N, step)) * rng.uniform(0.2, 2.0, size=(1, step))).ravel() * 3.0 + 11.0
+    r = rng.integers(N, size=(N, R))
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0, 1]] * D}
+    S = sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r)
+    So = o_analyze.analyze(D, Y, c2, R, keep_resamples=True, r=r)
+    _cmp(S, So, D, c2, rtol=1e-9, atol=1e-12)
+
+
+def test_device_resident_input_and_seed_zero():
+    """Y may already live on the GPU; seed=0 is falsy -> legacy global RNG like the reference (:113)."""
+    import torch
+
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_g8_n512_r64")
+    p = problem_from(z)
+    Yd = torch.from_numpy(z["Y"]).cuda()
+    S = sobol.analyze(p, Yd, num_resamples=64, keep_resamples=True, seed=int(z["seed"]))
+    _cmp(S, z, 8, True)
+    np.random.seed(123)
+    S0 = sobol.analyze(p, z["Y"], num_resamples=16, seed=0)
+    np.random.seed(123)
+    r = np.random.randint(512, size=(512, 16))
+    S1 = sobol.analyze_device(p, z["Y"], r=r)
+    assert np.array_equal(S0["S1_conf"], S1["S1_conf"])
+
+
+def test_constant_output():
+    """reference tests/test_sobol.py:170-224: constant Y -> all indices and CIs exactly 0, with a warning."""
+    from salib_b200.analyze import sobol
+
+    for p in (dict(ISHI), {**ISHI, "groups": ["A", "B", "A"]}):
+        Dg = 2 if "groups" in p else 3
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            S = sobol.analyze(p, np.full(1024 * (2 * Dg + 2), 0.4), num_resamples=10, seed=1)
+        assert any("Constant values" in str(x.message) for x in w)
+        for k in ("S1", "S1_conf", "ST", "ST_conf"):
+            assert S[k].shape == (Dg,) and not S[k].any()
+        assert S["S2"][0, 1] == 0.0 and np.isnan(S["S2_conf"][0, 1])
+
+
+def test_philox_resampling_is_statistically_equivalent():
+    """Device Philox indices: not the same stream as NumPy, so compare the CI widths within the
+    bootstrap's own sampling error (~ conf / sqrt(2(R-1))) and the point estimates exactly."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_cli_golden")
+    R = 2000
+    Sn = sobol.analyze_device(dict(ISHI), z["Y"], num_resamples=R, seed=100, resample="numpy")
+    Sp = sobol.analyze_device(dict(ISHI), z["Y"], num_resamples=R, seed=100, resample="philox", keep_resamples=True)
+    Sp2 = sobol.analyze_device(dict(ISHI), z["Y"], num_resamples=R, seed=100, resample="philox")
+    Sq = sobol.analyze_device(dict(ISHI), z["Y"], num_resamples=R, seed=101, resample="philox")
+    for k in ("S1", "ST"):
+        assert np.array_equal(Sn[k], Sp[k])
+    tol = 5.0 / np.sqrt(2 * (R - 1))
+    for k in ("S1_conf", "ST_conf"):
+        np.testing.assert_allclose(Sp[k], Sn[k], rtol=tol)
+        assert np.array_equal(Sp[k], Sp2[k])          # same seed -> same stream
+        assert not np.array_equal(Sp[k], Sq[k])       # different seed -> different stream
+    iu = np.triu_indices(3, 1)
+    np.testing.assert_allclose(Sp["S2_conf"][iu], Sn["S2_conf"][iu], rtol=tol)
+    # the resampled estimates are centred on the point estimate
+    se = Sp["S1_conf_all"].std(axis=0, ddof=1) / np.sqrt(R)
+    assert np.all(np.abs(Sp["S1_conf_all"].mean(axis=0) - Sp["S1"]) < 6 * se + 5e-3)
+
+
+def test_multiplicities_sum_to_n():
+    """Every Philox resample draws exactly N rows; index-built multiplicities equal np.bincount."""
+    import torch
+
+    from salib_b200 import _lib, _runtime as rt
+
+    N, R = 1000, 7
+    Npad = int(_lib.lib().sa_pad_rows(N))
+    w = rt.empty((R * Npad,), torch.uint8)
+    _lib.call("sa_counts_philox", rt.stream_ptr(), 42, N, 3, R, rt.ptr(w), None)
+    wc = w.reshape(R, Npad).cpu().numpy()
+    assert (wc.sum(axis=1) == N).all() and not wc[:, N:].any()
+    assert len({tuple(row) for row in wc}) == R
+    # global resample id keys the stream: resample 5 is the same whether it is drawn first or third
+    w1 = rt.empty((Npad,), torch.uint8)
+    _lib.call("sa_counts_philox", rt.stream_ptr(), 42, N, 5, 1, rt.ptr(w1), None)
+    assert np.array_equal(w1.cpu().numpy(), wc[2])
+    r = np.random.default_rng(0).integers(N, size=(N, R))
+    rd = rt.to_device(r, torch.int64)
+    flag = rt.zeros((1,), torch.int32)
+    _lib.call("sa_counts_from_indices", rt.stream_ptr(), rt.ptr(rd), N, R, 2, 4, rt.ptr(w), rt.ptr(flag))
+    wc = w.reshape(R, Npad)[:4].cpu().numpy()
+    for c in range(4):
+        assert np.array_equal(wc[c, :N], np.bincount(r[:, 2 + c], minlength=N))
+    assert int(flag.item()) == 0
+
+
+def test_problem_spec_chain_on_device():
+    """ProblemSpec.sample_sobol -> evaluate -> analyze_sobol (reference examples/Problem/problem_spec.py)."""
+    from oracle import analyze as o_analyze
+    from oracle import saltelli as o_saltelli
+    from oracle import test_functions as o_tf
+    from salib_b200.test_functions import Ishigami
+    from salib_b200.util import ProblemSpec
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp = ProblemSpec({"names": ["x1", "x2", "x3"], "bounds": [[-np.pi, np.pi]] * 3, "outputs": ["Y"]})
+        sp.sample_sobol(512, scramble=False, skip_values=512).evaluate(Ishigami.evaluate).analyze_sobol(
+            num_resamples=50, seed=101)
+        Xo = o_saltelli.sample(dict(ISHI), 512, True, skip_values=512, closed_form=True)
+        assert np.array_equal(sp.samples, Xo)
+        So = o_analyze.analyze(3, o_tf.ishigami(Xo), True, 50, seed=101)
+        _cmp(sp.analysis, So, 3, True, keep=False, rtol=1e-9, atol=1e-12)
+        total, first, second = sp.to_df()
+        assert list(first.index) == ["x1", "x2", "x3"] and "Analysis" in str(sp)
+        # device-resident chain and two outputs
+        sp2 = ProblemSpec({"names": ["x1", "x2", "x3"], "bounds": [[-np.pi, np.pi]] * 3})
+        sp2.sample_sobol(256, scramble=False, device=True)
+        assert sp2.samples.is_cuda
+        sp2.evaluate(lambda X: __import__("torch").stack([Ishigami.evaluate(X), 2 * Ishigami.evaluate(X) + 1], dim=1))
+        sp2.analyze_sobol(num_resamples=20, seed=3)
+        assert set(sp2.analysis) == {"Y1", "Y2"}
+        np.testing.assert_allclose(sp2.analysis["Y1"]["S1"], sp2.analysis["Y2"]["S1"], rtol=1e-9, atol=1e-12)

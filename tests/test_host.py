@@ -1,0 +1,255 @@
+"""Host-side logic that runs without a GPU: the C-ABI library loads and exports every declared symbol,
+direction vectors, argument validation / warnings of the drop-ins, ProblemSpec bookkeeping, sharding."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import sobol_seq
+
+
+def test_library_exports_every_declared_symbol():
+    from salib_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "salib_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.lib().sa_version() >= 100
+    assert _lib.lib().sa_row_stride(64, 1) == 136 and _lib.lib().sa_row_stride(3, 0) == 16
+    assert _lib.lib().sa_pad_rows(1000) == 1024
+
+
+def test_direction_vectors_match_oracle_and_scipy():
+    from salib_b200.sample.directions import direction_vectors
+    from scipy.stats import qmc
+
+    sv = direction_vectors(300)
+    assert sv.dtype == np.uint32 and sv.shape == (300, 30)
+    assert np.array_equal(sv, sobol_seq.direction_vectors(300).astype(np.uint32))
+    assert np.array_equal(sv, qmc.Sobol(300, scramble=False)._sv)
+    with pytest.raises(ValueError):
+        direction_vectors(21202)
+
+
+def test_direction_vectors_argument_errors():
+    from salib_b200 import _lib
+
+    L = _lib.lib()
+    assert L.sa_direction_vectors(None, None, None, 4, None) == -1
+    assert b"sa_direction_vectors" in L.sa_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from salib_b200.analyze import sobol as an
+    from salib_b200.sample import sobol as sm
+
+    p = {"num_vars": 3, "names": ["a", "b", "c"], "bounds": [[0, 1]] * 3}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sm.sample(p, 8, scramble=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        an.analyze(p, np.zeros(64))
+
+
+def test_sample_validation_matches_reference():
+    # reference sample/sobol.py:110-133 and tests/test_cli_sample.py:57-90 (warnings), util bounds errors
+    from salib_b200.sample import sobol as sm
+
+    p = {"num_vars": 2, "names": ["a", "b"], "bounds": [[0, 1], [0, 1]]}
+    with pytest.raises(ValueError, match="positive integer"):
+        sm.sample(p, 8, skip_values=-1)
+    with pytest.raises(ValueError, match="positive integer"):
+        sm.sample(p, 8, skip_values=2.0)
+    bad = {"num_vars": 2, "names": ["a", "b"], "bounds": [[0, 1], [1, 0]]}
+    with pytest.raises(ValueError, match="Bounds are not legal"):
+        sm.sample(bad, 8, scramble=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        for kw in (dict(skip_values=1025), dict(skip_values=4)):
+            try:
+                sm.sample(p, 16, scramble=False, **kw)
+            except RuntimeError:
+                pass  # no GPU here: validation already ran
+        msgs = " | ".join(str(x.message) for x in w)
+    assert "is a power of 2" in msgs and "Convergence may not be valid" in msgs
+    with pytest.raises(ValueError, match="At most 2\\*\\*30"):
+        sm.sample(p, 2 ** 30, scramble=False, skip_values=2)
+
+
+def test_saltelli_validation_matches_reference():
+    from salib_b200.sample import saltelli
+
+    p = {"num_vars": 2, "names": ["a", "b"], "bounds": [[0, 1], [0, 1]]}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        for kw in (dict(), dict(skip_values=0), dict(skip_values=3)):
+            try:
+                saltelli.sample(p, 511, **kw)
+            except RuntimeError:
+                pass
+    cats = [x.category for x in w]
+    msgs = " | ".join(str(x.message) for x in w)
+    assert DeprecationWarning in cats
+    assert "is equal to `2^n`" in msgs and "Duplicate samples" in msgs and "is a power of 2" in msgs
+
+
+def test_analyze_validation_matches_reference():
+    # reference tests/test_sobol.py:53-85
+    from salib_b200.analyze import sobol as an
+
+    p = {"num_vars": 3, "names": ["a", "b", "c"], "bounds": [[0, 1]] * 3}
+    with pytest.raises(RuntimeError, match="Incorrect number of samples"):
+        an.analyze(p, np.ones(7))
+    with pytest.raises(RuntimeError, match="Incorrect number of samples"):
+        an.analyze(p, np.ones(5 * 4 + 1), calc_second_order=False)
+    with pytest.raises(RuntimeError, match="Confidence level"):
+        an.analyze(p, np.ones(16), conf_level=1.0)
+    # must stay a plain function without a parameter called X (util/problem.py:354)
+    assert "X" not in an.analyze.__code__.co_varnames
+
+
+def test_group_helpers():
+    from salib_b200.util import _check_groups, compute_groups_matrix, extract_group_names, group_columns
+
+    p = {"num_vars": 5, "names": list("vwxyz"), "groups": ["a", "b", "a", "c", "b"], "bounds": [[0, 1]] * 5}
+    assert _check_groups(p) == p["groups"]
+    assert _check_groups({"names": ["a"], "groups": None}) is False
+    assert _check_groups({"names": ["a", "b"], "groups": ["g", "g"]}) is False
+    assert _check_groups({"names": ["a", "b"], "groups": ["a", "b"]}) is False
+    G, names = compute_groups_matrix(p["groups"])
+    assert list(names) == ["a", "b", "c"]
+    assert G.tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0]]
+    assert extract_group_names(p) == (["a", "b", "c"], 3)
+    assert extract_group_names({"names": ["q", "r"]}) == (["q", "r"], 2)
+    gcol, Dg = group_columns(p)
+    assert gcol.tolist() == [0, 1, 0, 2, 1] and Dg == 3
+    assert group_columns({"num_vars": 2, "names": ["a", "b"]}) == (None, 2)
+
+
+def test_problem_spec_bookkeeping():
+    # reference tests/test_problem_spec.py:30-96
+    from salib_b200.util import ProblemSpec, ResultDict
+
+    sp = ProblemSpec({"names": ["x1", "x2", "x3"], "bounds": [[-np.pi, np.pi]] * 3, "outputs": ["Y"]})
+    assert sp["num_vars"] == 3 and sp["groups"] == sp["names"]
+    assert "does not currently contain" in str(sp)
+    sp.sample(lambda prob, n: np.zeros((n, prob["num_vars"])), 10)
+    assert sp.samples.shape == (10, 3)
+    with pytest.raises(ValueError, match="Mismatched sample size"):
+        sp.samples = np.zeros((4, 2))
+    sp.evaluate(lambda X, k: X.sum(axis=1) + k, 2.0)
+    assert np.all(sp.results == 2.0)
+    sp.set_samples(np.ones((10, 3)))
+    assert sp.results is None  # setter clears results
+    with pytest.raises(RuntimeError, match="Model not yet evaluated"):
+        sp.analyze(lambda prob, Y: None)
+    with pytest.raises(AssertionError):
+        sp.set_results(np.zeros(11))
+    sp.set_results(np.arange(10.0))
+
+    def fake_analyze(problem, Y, scale=1.0):
+        S = ResultDict(S1=np.full(problem["num_vars"], Y.mean() * scale), names=problem["names"])
+        return S
+
+    sp.analyze(fake_analyze, scale=2.0)
+    assert np.allclose(sp.analysis["S1"], 9.0)
+    assert sp.to_df().shape == (3, 1)
+    sp2 = ProblemSpec({"names": ["a", "b"], "bounds": [[0, 1]] * 2})
+    sp2.set_samples(np.zeros((4, 2))).set_results(np.arange(8.0).reshape(4, 2))
+    assert sp2["outputs"] == ["Y1", "Y2"]
+    sp2.analyze(fake_analyze)
+    assert set(sp2.analysis) == {"Y1", "Y2"} and len(sp2.to_df()) == 2
+    with pytest.raises(ValueError, match="single parameter"):
+        ProblemSpec({"names": ["a"], "bounds": [[0, 1]]}).set_samples(np.zeros((2, 1))).set_results(
+            np.zeros(2)).analyze(fake_analyze)
+    with pytest.raises(AssertionError):
+        ProblemSpec({"names": ["a", "b"], "bounds": [[0, 1]]})
+
+
+def test_result_assembly_and_to_df():
+    # reference tests/test_to_df.py:59-83, analyze/sobol.py:249-264
+    from types import MethodType
+
+    from salib_b200.analyze import sobol as an
+
+    D = 3
+    point = np.arange(1.0, 1.0 + 2 * D + 3)
+    conf = point / 10
+    est = np.arange(4.0 * (2 * D)).reshape(4, 2 * D)
+    S = an._assemble(D, True, True, point, conf, est, False)
+    assert list(S) == ["S1", "S1_conf", "ST", "ST_conf", "S1_conf_all", "ST_conf_all", "S2", "S2_conf"]
+    assert S["S2"].shape == (3, 3) and np.isnan(S["S2"][1, 0]) and np.isnan(S["S2"][0, 0])
+    assert S["S2"][0, 1] == 7.0 and S["S2"][0, 2] == 8.0 and S["S2"][1, 2] == 9.0
+    assert S["S1_conf_all"].shape == (4, 3) and S["ST_conf_all"][2, 1] == est[2, 4]
+    S.problem = {"names": ["x1", "x2", "x3"], "num_vars": 3}
+    S.to_df = MethodType(an.to_df, S)
+    total, first, second = S.to_df()
+    assert list(total.columns) == ["ST", "ST_conf"] and list(first.index) == ["x1", "x2", "x3"]
+    assert list(second.index) == [("x1", "x2"), ("x1", "x3"), ("x2", "x3")]
+    # constant output: zeros, S2 = 0, S2_conf = NaN (reference tests/test_sobol.py:170-196)
+    C = an._assemble(D, True, False, point, conf, est, True)
+    assert not C["S1"].any() and not C["ST_conf"].any() and C["S2"][0, 1] == 0.0 and np.isnan(C["S2_conf"][0, 1])
+    F = an._assemble(D, False, False, point[:2 * D], conf[:2 * D], None, False)
+    assert "S2" not in F and F["ST"].tolist() == [4.0, 5.0, 6.0]
+
+
+def test_shard_range_covers_everything():
+    from salib_b200._runtime import shard_range
+
+    for total in (0, 1, 7, 100, 10000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, R, nest, q):
+    import torch
+    import torch.distributed as dist
+
+    from salib_b200._runtime import shard_range
+    from salib_b200.analyze.sobol import allgather_estimates
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(R * nest, dtype=torch.float64).reshape(R, nest)
+    lo, hi = shard_range(R, rank, world)
+    out = allgather_estimates(full[lo:hi].clone(), R, rank, world)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("R", [7, 16])
+def test_allgather_estimates_gloo_world2(R):
+    """N>1 host logic of analyze (resample sharding + all-gather) on the CPU with gloo, world_size 2."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, R, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
