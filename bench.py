@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark of the Sobol' hot path (BASELINE.json): bootstrapped ``sobol.analyze`` and Saltelli
+sample generation on the Sobol' G function, D=64, N=2^20, second order, R=10^4 (configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
+    python bench.py --impl reference ...                     # reference CPU algorithm (oracle port)
+
+One JSON line on stdout (rank 0).  A *step* is one full ``sobol.analyze`` of the resident model output Y
+(moments, normalise, point estimates, R bootstrap resamples sharded over the ranks, all-gather, CIs).
+``value`` = N*R / step time (resample-rows/s, the unit BASELINE.md section 3 defines for both arms);
+``analyze_s`` is the same number as seconds.  Sample generation is timed in its own loop and reported under
+``sample`` (Grows/s) with its HBM roofline.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+G_A8 = [0, 1, 4.5, 9, 99, 99, 99, 99]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="salib_b200", choices=["salib_b200", "reference"])
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--resamples", type=int, default=10000)
+    ap.add_argument("--first-order-only", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sample", action="store_true", help="skip the 70 GB sample-generation leg")
+    ap.add_argument("--ref-log2n", type=int, default=10, help="bounded sample of the reference arm")
+    ap.add_argument("--ref-resamples", type=int, default=48)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    order = "first+total order" if a.first_order_only else "second order"
+    return f"Sobol' G-function D={a.dim}, N=2^{a.log2n}, {order}, num_resamples={a.resamples}"
+
+
+def g_problem(D):
+    return {"num_vars": D, "names": [f"x{i + 1}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+
+
+def g_a(D):
+    return np.resize(np.array(G_A8, dtype=np.float64), D)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's reference-form analyze on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(a, steps, warmup, processes):
+    """Times oracle.analyze.analyze_reference_form(_parallel) (a NumPy restatement of
+    analyze/sobol.py:147-194, same gathers and reductions) on D=a.dim, N=2^ref_log2n, R=ref_resamples.
+    Returns (resample_rows_per_s, seconds_per_step, description)."""
+    from oracle import analyze as o_analyze
+    from oracle import saltelli as o_saltelli
+    from oracle import test_functions as o_tf
+
+    D, N, R = a.dim, 1 << a.ref_log2n, a.ref_resamples
+    c2 = not a.first_order_only
+    X = o_saltelli.sample(g_problem(D), N, c2, skip_values=0, closed_form=True)
+    Y = o_tf.sobol_g(X, a=g_a(D))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if processes > 1:
+            o_analyze.analyze_reference_form_parallel(D, Y, c2, R, seed=100, n_processors=processes)
+        else:
+            o_analyze.analyze_reference_form(D, Y, c2, R, seed=100)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    desc = (f"oracle port of analyze/sobol.py on G-function D={D}, N=2^{a.ref_log2n}, R={R}, "
+            f"{'second' if c2 else 'first+total'} order, {processes} process(es); "
+            f"the headline itself needs 84 GB for r alone on the CPU (BASELINE.md)")
+    return N * R / sec, sec, desc
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    # keep the whole run within a few minutes: warm-up is capped at 1 for the CPU arm
+    val, sec, desc = cpu_reference_run(a, max(1, a.steps), min(a.warmup, 1), procs)
+    line = {
+        "metric": "sobol.analyze resample-rows/s (N*R/s)", "value": val, "unit": "resample-rows/s",
+        "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "resample-rows/s", "cores": procs, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "resample-rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from salib_b200 import _lib, _runtime as rt
+    from salib_b200.analyze import sobol as analyze_sobol
+    from salib_b200.sample import sobol as sample_sobol
+    from salib_b200.test_functions import Sobol_G
+
+    D, N, R = a.dim, 1 << a.log2n, a.resamples
+    c2 = not a.first_order_only
+    step_rows = 2 * D + 2 if c2 else D + 2
+    problem = g_problem(D)
+    avec = g_a(D)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        """W untimed calls, then K calls between CUDA events with barrier+sync on both sides; max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / 1e3)
+
+    import warnings
+
+    warnings.simplefilter("ignore")
+    plan, first = sample_sobol._plan(problem, N, c2, False, 0, None)
+    lo, hi = rt.shard_range(N, rank, world)
+    hbm_peak, hbm_src = measured_peaks()
+
+    # ---- leg 1: Saltelli sample generation into HBM (sharded by Sobol' index range, no communication)
+    sample = None
+    if not a.no_sample:
+        X = rt.empty((step_rows * (hi - lo), D), torch.float64)
+        L.sa_launch_count(1)
+        t = timed(lambda: plan.generate(first + lo, hi - lo, out=X), a.steps, a.warmup)
+        launches = L.sa_launch_count(1)
+        rows = step_rows * N
+        sample_bytes_rank = step_rows * (hi - lo) * D * 8
+        gbs = sample_bytes_rank * a.steps / t / 1e9  # per GPU
+        sample = {"value": rows * a.steps / t / 1e9, "unit": "Grows/s", "ms_per_pass": t / a.steps * 1e3,
+                  "rows": rows, "bytes_per_gpu": sample_bytes_rank, "launches": int(launches),
+                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                               "kernel": "saltelli_reg_kernel" if D % 2 == 0 else "saltelli_generic_kernel"}}
+        del X
+        torch.cuda.empty_cache()
+
+    # ---- model output: fused Sobol' -> G evaluation of this rank's index range, all-gathered
+    Ypart = rt.empty((step_rows * (hi - lo),), torch.float64)
+    t_eval = timed(lambda: Sobol_G.evaluate_sample(plan, first + lo, hi - lo, a=avec, out=Ypart, check=False),
+                   a.steps, a.warmup)
+    if world > 1:
+        sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0]) for g in range(world)]
+        parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
+        dist.all_gather(parts, Ypart)
+        Yd = torch.cat(parts)
+    else:
+        Yd = Ypart
+    fused = {"value": step_rows * N * a.steps / t_eval / 1e9, "unit": "Grows/s", "ms_per_pass": t_eval / a.steps * 1e3}
+
+    # ---- leg 2 (the metric): sobol.analyze on resident Y
+    events = []
+
+    def analyze_step():
+        return analyze_sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100,
+                                            resample="philox", kernel_events=events)
+
+    for _ in range(a.warmup):
+        analyze_step()
+    events.clear()
+    L.sa_launch_count(1)
+    with ClockSampler(local_rank) as clocks:
+        t_an = timed(analyze_step, a.steps, 0)
+    launches = int(L.sa_launch_count(1))
+    S = analyze_step()
+    # dominant kernel: the accumulate launches of the timed steps
+    timed_events = events[: len(events) * a.steps // (a.steps + 1)] if events else []
+    k_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in timed_events)
+    k_rows = sum(c for c, _, _ in timed_events) * N
+    k_ms = max_over_ranks(k_ms)
+
+    # roofline denominator: FP64 FMA pipe, measured here
+    out = rt.zeros((1,), torch.float64)
+    import ctypes
+
+    nthreads = ctypes.c_uint64(0)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("sa_microbench_fp64", rt.stream_ptr(), 40000, rt.ptr(out), ctypes.addressof(nthreads))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 32.0 * 40000 * nthreads.value / (e0.elapsed_time(e1) / 1e3) / 1e12)
+    fp64_peak = best
+    if c2:
+        flop_per_row = 2 * (D * (D - 1) // 2) + 6 * D + 6
+        kernel = "s2_accum_tile8_kernel" if D <= 64 else "accum_generic_kernel"
+    else:
+        flop_per_row = 6 * D + 6
+        kernel = "fo_accum_kernel"
+    achieved = flop_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": (achieved / fp64_peak) if achieved else None, "traffic": None, "kernel": kernel,
+                "kernel_ms_per_step": k_ms / a.steps, "kernel_share_of_step": (k_ms / 1e3) / t_an,
+                "algorithmic_flop_per_resample_row": flop_per_row,
+                "peak_source": "measured here: sa_microbench_fp64 (16 independent DFMA chains/thread)",
+                "note": "FP64-FMA-pipe bound (no tensor cores by design); rows with multiplicity 0 are skipped, "
+                        "so achieved counts algorithmic flop of all N*R resample-rows"}
+
+    # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region
+    Yh = torch.empty(Yd.shape, dtype=torch.float64, pin_memory=True)
+    Yh.copy_(Yd)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        return analyze_sobol.analyze_device(problem, Yh, calc_second_order=c2, num_resamples=R, seed=100,
+                                            resample="philox")
+
+    t_e2e = timed(e2e_step, a.steps, 1)
+    nest = analyze_sobol._nest(D, c2)
+    e2e = {"value": N * R * a.steps / t_e2e, "unit": "resample-rows/s", "analyze_s": t_e2e / a.steps,
+           "h2d_bytes_per_step": int(Yh.numel() * 8), "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        val, sec, desc = cpu_reference_run(a, 1, 0, 1)
+        cpu = {"value": val, "unit": "resample-rows/s", "cores": 1, "kind": "port", "sample": desc,
+               "seconds": sec}
+
+    if rank == 0:
+        line = {
+            "metric": "sobol.analyze resample-rows/s (N*R/s)", "value": N * R * a.steps / t_an,
+            "unit": "resample-rows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t_an / a.steps * 1e3, "analyze_s": t_an / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
+                       "skip_values": 0, "resample": "philox seed 100", "parallelism": f"resample-id x{world}",
+                       "l2": f"Y is {Yd.numel() * 8 / 1e6:.0f} MB (> 126 MB L2), no explicit flush"
+                       if Yd.numel() * 8 > 126e6 else "Y fits L2 (resident by design)"},
+            "sample": sample, "fused_sample_eval": fused, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "result_check": {"S1_0": float(S["S1"][0]), "ST_0": float(S["ST"][0]), "S1_conf_0": float(S["S1_conf"][0])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

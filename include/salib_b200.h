@@ -143,7 +143,9 @@ int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt
                             int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                             int nsplit, double *d_psum);
 /* Same, with an explicit kernel choice for tests: algo 0 = auto, 1 = generic (any shape),
- * 2 = second-order 8x8 register-tile kernel (Dg <= 64), 3 = first/total-order kernel.        */
+ * 2 = second-order 8x8 register-tile kernel reading rows through the L1 (Dg <= 64),
+ * 3 = first/total-order kernel, 4 = second-order 8x8 register-tile kernel with rows staged in
+ * shared memory by cp.async.bulk (Dg <= 64; what "auto" picks).                              */
 int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                                int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                                int nsplit, double *d_psum, int algo);
@@ -156,6 +158,14 @@ int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg
  * d_conf[SA_NEST].                                                                            */
 int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
                       double *d_conf);
+
+/* ---- measurement helpers (bench.py only) ----------------------------------------------------
+ * sa_launch_count: kernels enqueued by this library since the last reset (bench.py "gpu_launches").
+ * sa_microbench_fp64 / sa_microbench_l2_read: the FP64-FMA and L2-read roofline denominators that
+ * MEASURED_PEAKS.json lacks.  fp64: flop = 32 * iters * (*h_threads).                */
+long long sa_launch_count(int reset);
+int sa_microbench_fp64(void *stream, int iters, double *d_out, uint64_t *h_threads);
+int sa_microbench_l2_read(void *stream, const void *d_buf, uint64_t bytes, int reps, double *d_out);
 
 #ifdef __cplusplus
 }

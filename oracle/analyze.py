@@ -174,3 +174,52 @@ def analyze(D, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
         if calc_second_order:
             S["S2_conf"][iu] = Z * s2_all.std(ddof=1, axis=0)
     return S
+
+
+# ---- process-pool variant (reference: analyze/sobol.py:183-194,282-362) --------------------------
+_POOL_STATE = {}
+
+
+def _pool_task(task):
+    """One (kind, j, k) unit of sobol_parallel (:282-299), on arrays inherited by fork."""
+    A, B, AB, BA, r, Z = (_POOL_STATE[k] for k in ("A", "B", "AB", "BA", "r", "Z"))
+    kind, j, k = task
+    with np.errstate(all="ignore"):
+        if kind == "S1":
+            return task, first_order(A, AB[:, j], B)
+        if kind == "S1_conf":
+            return task, Z * first_order(A[r], AB[r, j], B[r]).std(ddof=1)
+        if kind == "ST":
+            return task, total_order(A, AB[:, j], B)
+        if kind == "ST_conf":
+            return task, Z * total_order(A[r], AB[r, j], B[r]).std(ddof=1)
+        if kind == "S2":
+            return task, second_order(A, AB[:, j], AB[:, k], BA[:, j], B)
+        return task, Z * second_order(A[r], AB[r, j], AB[r, k], BA[r, j], B[r]).std(ddof=1)
+
+
+def analyze_reference_form_parallel(D, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
+                                    seed=None, r=None, n_processors=None):
+    """parallel=True path of the reference: a task list of (index-kind, j, k) mapped over a process pool."""
+    import multiprocessing as mp
+
+    Y = np.asarray(Y, dtype=np.float64)
+    N = _n_from_size(Y.size, D, calc_second_order)
+    Yn = (Y - Y.mean()) / Y.std()
+    A, B, AB, BA = split(Yn, D, N, calc_second_order)
+    if r is None:
+        r = resample_indices(N, num_resamples, seed)
+    Z = norm.ppf(0.5 + conf_level / 2)
+    _POOL_STATE.update(A=np.ascontiguousarray(A), B=np.ascontiguousarray(B), AB=np.ascontiguousarray(AB),
+                       BA=None if BA is None else np.ascontiguousarray(BA), r=r, Z=Z)
+    tasks = [(kind, j, None) for j in range(D) for kind in ("S1", "S1_conf", "ST", "ST_conf")]
+    if calc_second_order:
+        tasks += [(kind, j, k) for j in range(D) for k in range(j + 1, D) for kind in ("S2", "S2_conf")]
+    S = _empty(D, r.shape[1], False, calc_second_order)
+    with mp.get_context("fork").Pool(n_processors) as pool:
+        for (kind, j, k), val in pool.imap_unordered(_pool_task, tasks, chunksize=8):
+            if k is None:
+                S[kind][j] = val
+            else:
+                S[kind][j, k] = val
+    return S

@@ -35,6 +35,9 @@ SIGNATURES = {
     "sa_sobol_accumulate_ex_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp, _i32]),
     "sa_sobol_finalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _u64, _i32, _vp, _vp]),
     "sa_sobol_conf_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp]),
+    "sa_launch_count": (C.c_longlong, [_i32]),
+    "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "sa_microbench_l2_read": (C.c_int, [_vp, _vp, _u64, _i32, _vp]),
 }
 
 

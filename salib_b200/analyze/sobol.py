@@ -44,7 +44,7 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 27          # N*R elements of int64 drawn on the host in "auto" mode
 MAX_COUNT_BYTES = 4 << 30             # multiplicity buffer per batch
-_ALGO = {"auto": 0, "generic": 1, "tile8": 2, "first_order": 3}
+_ALGO = {"auto": 0, "generic": 1, "tile8_l1": 2, "first_order": 3, "tile8": 4}
 
 
 def _nacc(Dg, c2):
@@ -112,7 +112,7 @@ class SobolAnalyzer:
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[algo]
-        kind = self.algo or (2 if (self.c2 and Dg <= 64) else (1 if self.c2 else 3))
+        kind = self.algo or (4 if (self.c2 and Dg <= 64) else (1 if self.c2 else 3))
         self.kind = kind
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
         L = _lib.lib()
@@ -121,6 +121,7 @@ class SobolAnalyzer:
         self.stats = rt.zeros((8,), torch.float64)
         self.Yn = None
         self.Yt = None
+        self.kernel_events = None   # bench.py sets this to a list to time the accumulate launches
 
     # -- normalisation ---------------------------------------------------------------------
     def load(self, Yd):
@@ -129,7 +130,7 @@ class SobolAnalyzer:
         work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)
         _lib.call("sa_moments_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.step, rt.ptr(self.stats),
                   rt.ptr(work), int(work.numel()))
-        need_rows = self.kind in (1, 2)
+        need_rows = self.kind in (1, 2, 4)
         need_cols = self.kind == 3
         if need_rows:
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
@@ -142,7 +143,7 @@ class SobolAnalyzer:
     def _nsplit(self, count):
         """Row splits so that `count` resamples fill the machine (at least 32 rows per split)."""
         max_split = max(1, min(4096, self.N // 32))
-        if self.kind == 2:      # one warp per resample, 8 per block, one block per SM
+        if self.kind in (2, 4):  # one warp per resample, 8 per block, one block per SM
             blocks = -(-count // 8)
         elif self.kind == 3:    # 4 resamples per warp, 8 warps per block, ~2 blocks per SM
             blocks = -(-count // 32) * -(-self.Dg // 8)
@@ -155,8 +156,15 @@ class SobolAnalyzer:
         """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
         nsplit = self._nsplit(count)
         psum = rt.empty((nsplit * count * self.nacc,), torch.float64)
+        ev = None
+        if self.kernel_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(self.Yn), rt.ptr(self.Yt), self.N,
                   self.Dg, int(self.c2), rt.ptr(w), int(count), int(nsplit), rt.ptr(psum), self.kind)
+        if ev is not None:
+            ev[1].record()
+            self.kernel_events.append((int(count), ev[0], ev[1]))
         _lib.call("sa_sobol_finalize_f64", rt.stream_ptr(), rt.ptr(psum), self.N, self.Dg, int(self.c2),
                   int(count), int(nsplit), rt.ptr(self.stats), rt.ptr(est_out))
 
@@ -169,7 +177,7 @@ class SobolAnalyzer:
         """Resample batches [c0, c1): bounded by the multiplicity buffer; for the one-warp-per-resample
         kernel sized in whole waves (8 * SMs) with the remainder as its own, row-split, launch."""
         cap = max(1, MAX_COUNT_BYTES // self.Npad)
-        wave = 8 * self.sms if self.kind == 2 else 32 * self.sms
+        wave = 8 * self.sms if self.kind in (2, 4) else 32 * self.sms
         c = lo
         while c < hi:
             left = hi - c
@@ -247,7 +255,8 @@ def _assemble(Dg, c2, keep, point, conf, est_all, const_y):
 
 
 def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
-                   keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True):
+                   keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
+                   kernel_events=None):
     """``analyze`` with the device knobs exposed.
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
@@ -273,6 +282,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
     rt.require_cuda()
     Yd = rt.to_device(Y, torch.float64).reshape(-1)
     eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
+    eng.kernel_events = kernel_events
     eng.load(Yd)
     Z = norm.ppf(0.5 + conf_level / 2)
 

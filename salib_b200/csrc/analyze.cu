@@ -416,6 +416,297 @@ s2_accum_tile8_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_
 }
 
 // ------------------------------------------------------------------------------------------
+// second-order accumulate, shared-memory staged (the production kernel for Dg <= 64)
+// ------------------------------------------------------------------------------------------
+// Same decomposition as s2_accum_tile8_kernel (warp <-> resample, lane <-> 8x8 register tile) but
+// the rows are streamed through shared memory instead of the L1: ncu on the L1 version showed the
+// L1 data pipe at 91 % (118 wavefronts per row) and the FP64 pipe at 38 %.
+//   * tiles of 32 contiguous rows (32*stride*8 B, contiguous in HBM) are brought in with one
+//     cp.async.bulk each into a 4-stage ring; an mbarrier per stage carries the byte count;
+//   * the 8 warps of a block (8 resamples) consume the same tiles at their own pace; the last warp
+//     to leave a stage (shared counter) re-arms its barrier and issues the copy of tile t+4, so
+//     there is no block-wide barrier in the loop;
+//   * operand loads are 128-bit and bank-conflict free: lane tiles whose 64-byte blocks share banks
+//     read their four 16-byte chunks in an XOR-permuted order (free: the permutation only renames
+//     accumulators);
+//   * the 4 lanes left over by the 28 off-diagonal tiles take 4 of the 8 diagonal tiles as full
+//     tiles; the other 4 diagonal triangles (112 pairs) are spread 4 per lane.
+constexpr int kTileRows = 32;
+constexpr int kStages = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// The 28 pairs (jj < kk) of an 8x8 strict upper triangle in 7 groups of 4; each group touches at
+// most two columns.  Packed per group: rows x[0..3] (3 bits each), columns y0, y1 (3 bits each),
+// selector bits (slot s uses y1 if bit s).
+__device__ __forceinline__ void diag_group(int g, int (&xr)[4], int &y0, int &y1, int &sel) {
+  // g0..g3: column 7-g, rows 0..3
+  // g4: (4,7)(5,7)(6,7)(0,1)   g5: (4,6)(5,6)(0,2)(1,2)   g6: (4,5)(0,3)(1,3)(2,3)
+  if (g < 4) {
+    xr[0] = 0; xr[1] = 1; xr[2] = 2; xr[3] = 3;
+    y0 = 7 - g; y1 = 7 - g; sel = 0;
+  } else if (g == 4) {
+    xr[0] = 4; xr[1] = 5; xr[2] = 6; xr[3] = 0;
+    y0 = 7; y1 = 1; sel = 0x8;
+  } else if (g == 5) {
+    xr[0] = 4; xr[1] = 5; xr[2] = 0; xr[3] = 1;
+    y0 = 6; y1 = 2; sel = 0xC;
+  } else {
+    xr[0] = 4; xr[1] = 0; xr[2] = 1; xr[3] = 2;
+    y0 = 5; y1 = 3; sel = 0xE;
+  }
+}
+
+__global__ void __launch_bounds__(kS2Warps * 32, 1)
+s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
+                     const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
+                     uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t c = (uint64_t)blockIdx.x * kS2Warps + warp;
+  const bool live = c < count;
+  const int sp = blockIdx.y;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+  const int ntiles = (row1 > row0) ? (int)((row1 - row0 + kTileRows - 1) / kTileRows) : 0;
+  const int TB = Dp >> 3;
+  const uint32_t row_bytes = (uint32_t)stride * 8u;
+  const uint32_t stage_bytes = kTileRows * row_bytes;
+  const uint32_t sm_base = smem_u32(smraw);
+  const uint32_t bar_base = sm_base + kStages * stage_bytes;   // kStages x u64
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(smraw + kStages * stage_bytes + kStages * 8);
+
+  auto issue = [&](int t) {  // one elected thread: arm the barrier and start the bulk copy of tile t
+    const int s = t % kStages;
+    const uint64_t r = row0 + (uint64_t)t * kTileRows;
+    const uint32_t rows = (uint32_t)((row1 - r < (uint64_t)kTileRows) ? (row1 - r) : kTileRows);
+    const uint32_t bytes = rows * row_bytes;
+    mbar_arrive_expect_tx(bar_base + 8u * s, bytes);
+    bulk_g2s(sm_base + s * stage_bytes, Yn + r * (uint64_t)stride, bytes, bar_base + 8u * s);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_base + 8u * s, 1);
+      cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+  }
+
+  // ---- lane roles ------------------------------------------------------------------------
+  // full 8x8 tile: off-diagonal (tj < tk) first, then diagonal tiles while lanes remain
+  const int ntOff = TB * (TB - 1) / 2;
+  int tj = 0, tk = 0;
+  bool actA = false;
+  if (lane < ntOff) {
+    int idx = lane;
+    for (int t = 0; t < TB; ++t) {
+      const int n = TB - 1 - t;
+      if (idx < n) {
+        tj = t;
+        tk = t + 1 + idx;
+        actA = true;
+        break;
+      }
+      idx -= n;
+    }
+  } else if (lane - ntOff < TB) {
+    tj = tk = lane - ntOff;
+    actA = true;
+  }
+  const int ndiag_full = (32 - ntOff < TB) ? (32 - ntOff) : TB;   // diagonal tiles done as full tiles
+  const int rx = (tj >> 1) & 3, ry = (tk >> 1) & 3;
+  uint32_t offX[4], offY[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    offX[t] = actA ? (uint32_t)(Dp + 8 * tj + 2 * (t ^ rx)) * 8u : 0u;
+    offY[t] = actA ? (uint32_t)(8 * tk + 2 * (t ^ ry)) * 8u : 0u;
+  }
+  // remaining diagonal tiles (only when TB == 8: tiles 4..7), 4 pairs per lane on lanes 0..27
+  const bool hasB = ndiag_full < TB;
+  const int dB = ndiag_full + (lane & 3);
+  const int gB = lane >> 2;
+  const bool actB = hasB && gB < 7 && dB < TB;
+  int xr[4], yb0, yb1, selB;
+  diag_group(gB < 7 ? gB : 0, xr, yb0, yb1, selB);
+  const int swz = (dB >> 1) & 1;  // de-conflict lanes whose tiles are 128 B apart
+  uint32_t offBx[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) offBx[s] = actB ? (uint32_t)(Dp + 8 * dB + xr[s ^ swz]) * 8u : 0u;
+  const uint32_t offBy0 = actB ? (uint32_t)(8 * dB + yb0) * 8u : 0u;
+  const uint32_t offBy1 = actB ? (uint32_t)(8 * dB + yb1) * 8u : 0u;
+  // first/total order: columns lane, lane+32
+  const uint32_t offC0 = (lane < Dp) ? lane * 8u : 0u;
+  const uint32_t offC1 = (lane + 32 < Dp) ? (lane + 32) * 8u : 0u;
+  const uint32_t offAB = 2u * Dp * 8u;
+
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+  double accB[4] = {0.0, 0.0, 0.0, 0.0};
+  double s1_0 = 0.0, s1_1 = 0.0, st_0 = 0.0, st_1 = 0.0;
+  double sA = 0.0, sB = 0.0, sAA = 0.0, sBB = 0.0, sAB = 0.0;
+
+  const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
+  auto load_w = [&](int t) -> unsigned {
+    const uint64_t i = row0 + (uint64_t)t * kTileRows + lane;
+    if (!live || t >= ntiles || i >= row1) return 0u;
+    return wrow ? (unsigned)__ldg(wrow + i) : 1u;
+  };
+  unsigned wl_next = load_w(0);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kStages;
+    const uint32_t parity = (uint32_t)(t / kStages) & 1u;
+    const unsigned wl = wl_next;
+    wl_next = load_w(t + 1);
+    unsigned mask = __ballot_sync(kFull, wl != 0);
+    const uint32_t bar = bar_base + 8u * s;
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    const uint32_t tile = sm_base + s * stage_bytes;
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double wv = (double)__shfl_sync(kFull, wl, b);
+      const uint32_t row = tile + (uint32_t)b * row_bytes;
+      {  // full 8x8 tile
+        double X[8], Yv[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 vx = lds_f64x2(row + offX[q]);
+          const double2 vy = lds_f64x2(row + offY[q]);
+          X[2 * q] = vx.x;
+          X[2 * q + 1] = vx.y;
+          Yv[2 * q] = vy.x;
+          Yv[2 * q + 1] = vy.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const double wx = wv * X[a];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Yv[k], acc[a][k]);
+        }
+      }
+      if (hasB) {  // warp-uniform
+        const double y0 = wv * lds_f64(row + offBy0);
+        const double y1 = wv * lds_f64(row + offBy1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double x = lds_f64(row + offBx[q]);
+          accB[q] = fma(x, ((selB >> (q ^ swz)) & 1) ? y1 : y0, accB[q]);
+        }
+      }
+      {  // first / total order + scalars
+        const double2 ab = lds_f64x2(row + offAB);
+        const double a = ab.x, bb = ab.y;
+        const double wa = wv * a, wb = wv * bb;
+        sA += wa;
+        sB += wb;
+        sAA = fma(wa, a, sAA);
+        sBB = fma(wb, bb, sBB);
+        sAB = fma(wb, a, sAB);
+        const double t0 = lds_f64(row + offC0) - a;
+        const double t1 = lds_f64(row + offC1) - a;
+        s1_0 = fma(wb, t0, s1_0);
+        s1_1 = fma(wb, t1, s1_1);
+        st_0 = fma(wv * t0, t0, st_0);
+        st_1 = fma(wv * t1, t1, st_1);
+      }
+    }
+    // release the stage; the last warp out refills it with tile t + kStages
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "r"(smem_u32(cnt + s))
+                   : "memory");
+      if (old == kS2Warps - 1) {
+        cnt[s] = 0;
+        if (t + kStages < ntiles) issue(t + kStages);
+      }
+    }
+  }
+
+  if (!live) return;
+  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+  if (lane == 0) {
+    out[0] = sA;
+    out[1] = sB;
+    out[2] = sAA;
+    out[3] = sBB;
+    out[4] = sAB;
+  }
+  if (lane < Dg) {
+    out[5 + lane] = s1_0;
+    out[5 + Dg + lane] = st_0;
+  }
+  if (lane + 32 < Dg) {
+    out[5 + lane + 32] = s1_1;
+    out[5 + Dg + lane + 32] = st_1;
+  }
+  double *o2 = out + 5 + 2 * Dg;
+  if (actA) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = 8 * tj + 2 * ((a >> 1) ^ rx) + (a & 1);
+        const int kk = 8 * tk + 2 * ((k >> 1) ^ ry) + (k & 1);
+        if (j < kk && kk < Dg) o2[pair_index(j, kk, Dg)] = acc[a][k];
+      }
+  }
+  if (actB) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sl = q ^ swz;
+      const int j = 8 * dB + xr[sl];
+      const int k = 8 * dB + (((selB >> sl) & 1) ? yb1 : yb0);
+      if (k < Dg) o2[pair_index(j, k, Dg)] = accB[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // first/total-order accumulate: lanes <-> rows (column-major Yt), C resamples per warp
 // ------------------------------------------------------------------------------------------
 constexpr int kFoWarps = 8;
@@ -659,6 +950,7 @@ extern "C" int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int s
   moments_final1_kernel<<<1, kMomThreads, 0, st>>>(part, blocks, total, d_stats);
   moments_pass2_kernel<<<blocks, kMomThreads, 0, st>>>(d_Y, total, d_stats, part + (size_t)kMomBlocks * 5);
   moments_final2_kernel<<<1, kMomThreads, 0, st>>>(part + (size_t)kMomBlocks * 5, blocks, total, d_stats);
+  note_launches(4);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -675,6 +967,7 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
     uint64_t blocks = ceil_div_u64(total, 256);
     if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
     normalize_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, second_order, d_stats, d_Yn);
+    note_launches(1);
   }
   if (d_Yt) {
     SA_REQUIRE(Dg + 2 <= 65535, SA_ERR_UNSUPPORTED, "sa_normalize_f64: too many groups for the column copy");
@@ -683,6 +976,7 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)(Dg + 2));
     normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
+    note_launches(1);
   }
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -701,6 +995,7 @@ extern "C" int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t
   if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
   counts_from_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_r, N, R, c0, count, Npad, (uint32_t *)d_w,
                                                               d_overflow);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -723,12 +1018,13 @@ extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_
     const uint64_t nb = (count - done < 65535) ? count - done : 65535;
     dim3 grid((unsigned)bx, (unsigned)nb);
     counts_philox_kernel<<<grid, 256, 0, st>>>(seed, N, c0 + done, Npad, (uint32_t *)(d_w + done * Npad));
+    note_launches(1);
   }
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
 
-// algo: 0 auto, 1 generic, 2 second-order tile8, 3 first-order
+// algo: 0 auto, 1 generic, 2 second-order tile8 via L1, 3 first-order, 4 second-order tile8 via shared memory
 extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                                           int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                                           int nsplit, double *d_psum, int algo) {
@@ -743,8 +1039,23 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   const int nacc = SA_NACC(Dg, second_order);
   uint64_t rps = ceil_div_u64(N, nsplit);
   rps = (rps + 31) & ~(uint64_t)31;
-  if (algo == 0) algo = second_order ? (Dg <= 64 ? 2 : 1) : 3;
-  if (algo == 2) {
+  if (algo == 0) algo = second_order ? (Dg <= 64 ? 4 : 1) : 3;
+  if (algo == 4) {
+    SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
+    SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
+    SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
+    const uint64_t bx = ceil_div_u64(count, kS2Warps);
+    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
+    const size_t smem = (size_t)kStages * kTileRows * stride * 8 + kStages * 8 + kStages * 4 + 16;
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+      SA_CUDA(cudaFuncSetAttribute(s2_accum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    dim3 grid((unsigned)bx, (unsigned)nsplit);
+    s2_accum_smem_kernel<<<grid, kS2Warps * 32, smem, st>>>(d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum,
+                                                           nacc);
+  } else if (algo == 2) {
     SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
     SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
     SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
@@ -770,6 +1081,7 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   } else {
     SA_REQUIRE(false, SA_ERR_ARG, "sa_sobol_accumulate_f64: unknown algo %d", algo);
   }
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -788,6 +1100,7 @@ extern "C" int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_
   finalize_kernel<<<(unsigned)count, 128, (size_t)Dg * sizeof(double), (cudaStream_t)stream>>>(
       d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
       SA_NEST(Dg, second_order));
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -798,6 +1111,7 @@ extern "C" int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, 
   SA_REQUIRE(R >= 1 && ncols >= 1, SA_ERR_ARG, "sa_sobol_conf_f64: bad shape");
   dim3 block(32, 16);
   conf_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, z, d_conf);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -9,6 +9,8 @@
 namespace sa {
 
 void set_error(const char *fmt, ...);
+// Bookkeeping for bench.py's "gpu_launches": every entry point reports the kernels it enqueued.
+void note_launches(int n);
 
 #define SA_REQUIRE(cond, code, ...)    \
   do {                                 \

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace sa {
@@ -13,6 +15,12 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int sm_count() {
@@ -32,6 +40,8 @@ int sm_count() {
 }  // namespace sa
 
 extern "C" int sa_version(void) { return 100; }
+
+extern "C" long long sa_launch_count(int reset) { return sa::launches(reset); }
 
 extern "C" const char *sa_last_error(void) { return sa::g_err; }
 

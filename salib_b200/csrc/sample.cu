@@ -408,6 +408,7 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     kern<<<(unsigned)blocks, 256, smem, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
                                              second_order, d_lb, d_span, d_out, BR, m_rowlen, m_D);
   }
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -419,6 +420,7 @@ extern "C" int sa_eval_ishigami_f64(void *stream, const double *d_X, uint64_t ro
   uint64_t blocks = ceil_div_u64(rows, 256);
   if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
   eval_ishigami_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_X, rows, A, B, d_Y);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -444,6 +446,7 @@ extern "C" int sa_eval_sobol_g_f64(void *stream, const double *d_X, uint64_t row
     SA_G_CASE(1) SA_G_CASE(2) SA_G_CASE(4) SA_G_CASE(8) SA_G_CASE(16) SA_G_CASE(32)
   }
 #undef SA_G_CASE
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -474,6 +477,7 @@ extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, 
   kern<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, D, Dg,
                                                              d_group_of_col, step, second_order, d_lb, d_span,
                                                              d_a, d_delta, d_alpha, d_Y, d_flag, BR);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -496,6 +500,7 @@ extern "C" int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv,
   else
     saltelli_eval_ishigami_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         d_sv, d_shift, first_index, n, Dg, nullptr, step, second_order, d_lb, d_span, A, B, d_Y);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
