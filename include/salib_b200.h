@@ -101,14 +101,17 @@ int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double
 
 /* Layout of the normalised model output used by the accumulate kernels ("analysis layout"):
  * row i of length sa_row_stride(Dg, second_order) doubles =
- *   [ AB_0..AB_{Dg-1} 0.. | BA_0..BA_{Dg-1} 0.. | A B 0 0 0 0 0 0 ]   (second order)
- *   [ AB_0..AB_{Dg-1} 0.. | A B 0 0 0 0 0 0 ]                         (first/total only)
- * with each column block padded with zeros to a multiple of 8 doubles (64 B).                */
+ *   [ AB part | BA part | A B ]   (second order)        [ AB part | A B ]   (first/total only)
+ * A part holds its columns in blocks of 8 at a pitch of 10 doubles (80 B): column j sits at
+ * (j / 8) * 10 + j % 8, the 2 pad doubles of each block and the columns >= Dg are zero.  The pitch
+ * makes the tile kernel's 128-bit shared-memory loads bank-conflict free (5*b mod 8 is a bijection).
+ * sa_row_stride = parts * ceil(Dg / 8) * 10 + 2.                                                */
 int sa_row_stride(int Dg, int second_order);
 /* Replaces (Y - mean)/std and separate_output_values (analyze/sobol.py:141,267-279):
  * d_Y [N*step] reference order [A, AB_0.., (BA_0..,) B] -> d_Yn [N*stride (+8 doubles slack)]
- * in analysis layout; if d_Yt != NULL also writes the column-major copy d_Yt[col][Npad]
- * (cols: A, B, AB_0..AB_{Dg-1}), Npad = sa_pad_rows(N), used by the first-order kernel.      */
+ * in analysis layout; if d_Yt != NULL also writes the column-major copy d_Yt[col][Npad],
+ * Npad = sa_pad_rows(N): cols A, B, AB_0..AB_{Dg-1} when second_order == 0 (first-order kernel),
+ * cols A, B only when second_order != 0 (scalar sums of the tile kernel).                    */
 uint64_t sa_pad_rows(uint64_t N);
 int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
                      const double *d_stats, double *d_Yn, double *d_Yt);
@@ -138,12 +141,11 @@ int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint6
  *   [5+2Dg+p(j,k)] sum w*BA_j*AB_k, j<k, p = j*Dg - j*(j+1)/2 + (k-j-1)
  * into d_psum[nsplit][count][SA_NACC].  d_w == NULL means weight 1 for every row (the point
  * estimate; count must be 1).  nsplit row ranges of equal size let small `count` fill the GPU.
- * d_Yt is required when second_order == 0 (first-order kernel), ignored otherwise.            */
+ * d_Yt is required by the first-order kernel and by the tile kernel (its A/B columns).        */
 int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                             int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                             int nsplit, double *d_psum);
 /* Same, with an explicit kernel choice for tests: algo 0 = auto, 1 = generic (any shape),
- * 2 = second-order 8x8 register-tile kernel reading rows through the L1 (Dg <= 64),
  * 3 = first/total-order kernel, 4 = second-order 8x8 register-tile kernel with rows staged in
  * shared memory by cp.async.bulk (Dg <= 64; what "auto" picks).                              */
 int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,

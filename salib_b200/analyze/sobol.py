@@ -44,7 +44,7 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 27          # N*R elements of int64 drawn on the host in "auto" mode
 MAX_COUNT_BYTES = 4 << 30             # multiplicity buffer per batch
-_ALGO = {"auto": 0, "generic": 1, "tile8_l1": 2, "first_order": 3, "tile8": 4}
+_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "tile8": 4}
 
 
 def _nacc(Dg, c2):
@@ -130,12 +130,12 @@ class SobolAnalyzer:
         work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)
         _lib.call("sa_moments_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.step, rt.ptr(self.stats),
                   rt.ptr(work), int(work.numel()))
-        need_rows = self.kind in (1, 2, 4)
-        need_cols = self.kind == 3
+        need_rows = self.kind in (1, 4)
+        need_cols = self.kind in (3, 4)   # kind 4 only needs the A and B columns
         if need_rows:
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
         if need_cols:
-            self.Yt = rt.empty(((self.Dg + 2) * self.Npad,), torch.float64)
+            self.Yt = rt.empty(((2 if self.c2 else self.Dg + 2) * self.Npad,), torch.float64)
         _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
                   rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
 
@@ -143,7 +143,7 @@ class SobolAnalyzer:
     def _nsplit(self, count):
         """Row splits so that `count` resamples fill the machine (at least 32 rows per split)."""
         max_split = max(1, min(4096, self.N // 32))
-        if self.kind in (2, 4):  # one warp per resample, 8 per block, one block per SM
+        if self.kind == 4:       # one warp per resample, 8 per block, one block per SM
             blocks = -(-count // 8)
         elif self.kind == 3:    # 4 resamples per warp, 8 warps per block, ~2 blocks per SM
             blocks = -(-count // 32) * -(-self.Dg // 8)
@@ -177,7 +177,7 @@ class SobolAnalyzer:
         """Resample batches [c0, c1): bounded by the multiplicity buffer; for the one-warp-per-resample
         kernel sized in whole waves (8 * SMs) with the remainder as its own, row-split, launch."""
         cap = max(1, MAX_COUNT_BYTES // self.Npad)
-        wave = 8 * self.sms if self.kind in (2, 4) else 32 * self.sms
+        wave = 8 * self.sms if self.kind == 4 else 32 * self.sms
         c = lo
         while c < hi:
             left = hi - c

@@ -9,10 +9,10 @@
 // normalised output matrix in row order (coalesced, shared by all resamples in flight, L1/L2
 // resident) instead of gathering N*R random 1 KB rows, and rows with w == 0 (36.8 %) are skipped.
 //
-//   second-order kernel  (s2_accum_tile8_kernel): one warp per resample; the D(D-1)/2 pair sums
-//     sum_i w*BA_j*AB_k live in registers as one 8x8 (j,k) tile per lane (28 off-diagonal tiles
-//     + the 8 diagonal triangles folded 7 pairs per lane), i.e. a register-tiled FP64 rank-1
-//     update per row: 16 operand loads feed 64 DFMAs.  FP64-pipe bound.
+//   second-order kernel  (s2_accum_smem_kernel): one warp per resample; the D(D-1)/2 pair sums
+//     sum_i w*BA_j*AB_k live in registers as one 8x8 (j,k) tile per lane, i.e. a register-tiled
+//     FP64 rank-1 update per row (16 operand doubles feed 64 DFMAs); rows are staged through shared
+//     memory by cp.async.bulk.  FP64-pipe / shared-memory-bandwidth bound.
 //   first-order kernel   (fo_accum_kernel): lanes <-> rows over a column-major copy (coalesced),
 //     C resamples per warp share each row read.  L2-bandwidth bound.
 //   generic kernel       (accum_generic_kernel): any shape, one accumulator per thread; fallback
@@ -22,10 +22,17 @@
 namespace sa {
 
 __host__ __device__ inline int round_up8(int x) { return (x + 7) & ~7; }
+// Analysis layout: every block of 8 columns sits at a pitch of 10 doubles (80 B): 5*b mod 8 is a
+// bijection, so the 16-byte chunks of 8 different blocks read with the same instruction offset fall
+// into 8 different bank groups -- the tile kernel's LDS.128 are conflict free with plain offsets.
+constexpr int kBlockPitch = 10;
+__host__ __device__ inline int part_len(int Dg) { return (round_up8(Dg) >> 3) * kBlockPitch; }
 __host__ __device__ inline int row_stride(int Dg, int second_order) {
-  return (second_order ? 2 : 1) * round_up8(Dg) + 8;
+  return (second_order ? 2 : 1) * part_len(Dg) + 2;
 }
 __host__ __device__ inline uint64_t pad_rows(uint64_t N) { return (N + 127) & ~(uint64_t)127; }
+// Position of logical column j inside the AB / BA part of an analysis-layout row.
+__host__ __device__ inline int col_pos(int j) { return (j >> 3) * kBlockPitch + (j & 7); }
 __host__ __device__ inline int pair_index(int j, int k, int Dg) {
   return j * Dg - (j * (j + 1)) / 2 + (k - j - 1);
 }
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step, int second_order,
                       const double *__restrict__ stats, double *__restrict__ Yn) {
   const double mean = stats[0], sd = stats[1];
-  const int Dp = round_up8(Dg);
+  const int PL = part_len(Dg);
   const int stride = row_stride(Dg, second_order);
   const uint64_t total = N * (uint64_t)stride;
   const uint64_t S = (uint64_t)gridDim.x * blockDim.x;
@@ -151,12 +158,15 @@ normalize_rows_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step
   const int dp = (int)(S - di * (uint64_t)stride);
   for (; idx < total; idx += S) {
     int src = -1;
-    if (p < Dp) {
-      if (p < Dg) src = 1 + p;
-    } else if (second_order && p < 2 * Dp) {
-      if (p - Dp < Dg) src = 1 + Dg + (p - Dp);
+    const int nparts = second_order ? 2 : 1;
+    if (p < nparts * PL) {
+      const int part = (p >= PL) ? 1 : 0;
+      const int q = p - part * PL;
+      const int blk = q / kBlockPitch, e = q - blk * kBlockPitch;
+      const int j = 8 * blk + e;
+      if (e < 8 && j < Dg) src = 1 + part * Dg + j;
     } else {
-      const int q = p - (second_order ? 2 : 1) * Dp;
+      const int q = p - nparts * PL;
       if (q == 0) src = 0;
       else if (q == 1) src = step - 1;
     }
@@ -255,182 +265,30 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// second-order accumulate: warp <-> resample, lane <-> 8x8 (j,k) register tile
+// second-order accumulate (production kernel for Dg <= 64): warp <-> resample,
+// lane <-> 8x8 (j,k) register tile, rows staged in shared memory
 // ------------------------------------------------------------------------------------------
+// For resample c the D(D-1)/2 sums  S_jk = sum_i w_i * BA_j[i] * AB_k[i]  (j < k) are a weighted
+// rank-1 update per row.  One warp owns one resample; the (j,k) triangle is cut into 8x8 tiles:
+// 28 off-diagonal tiles + 4 diagonal tiles are full register tiles on the 32 lanes (64 DFMA per row
+// fed by 16 operand doubles), the other 4 diagonal triangles (112 pairs) are spread 4 per lane.
+// First/total-order sums ride along (2 columns per lane).  Rows with multiplicity 0 are skipped.
+//
+// Data path: tiles of 32 contiguous rows (one cp.async.bulk each, 34 KB at Dg = 64) go through a
+// 4-stage shared-memory ring with one mbarrier per stage; the 8 warps of a block (8 resamples)
+// consume the same tiles at their own pace and the last warp to leave a stage re-arms it and issues
+// the copy of tile t+4 -- no block-wide barrier in the loop.  The analysis layout puts the 8-column
+// blocks at an 80-byte pitch (col_pos), so the chunks that different lanes read with the SAME
+// instruction offset fall into different bank groups: all operand loads are conflict-free LDS.128
+// from one base register per operand set.
+//
+// Software pipeline (no extra registers): two operand sets P (8 BA values) and Q (8 AB values) stay
+// in registers across rows and rows alternate between
+//   type 1: a-major order, P streamed in at the row start, Q already resident; each P chunk is
+//           refilled with the NEXT row's values as soon as its 16 DFMAs are issued;
+//   type 2: k-major order, Q streamed, P resident, Q chunks refilled for the next row.
+// ncu history of this kernel is in profiles/ (L1 version: 118 wavefronts/row, FP64 pipe 38 %).
 constexpr int kS2Warps = 8;
-
-__device__ __forceinline__ void load8(const double *__restrict__ p, double (&v)[8]) {
-  const double2 *q = reinterpret_cast<const double2 *>(p);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const double2 d = __ldg(q + t);
-    v[2 * t] = d.x;
-    v[2 * t + 1] = d.y;
-  }
-}
-
-__global__ void __launch_bounds__(kS2Warps * 32, 1)
-s2_accum_tile8_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
-                      const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
-                      uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const uint64_t c = (uint64_t)blockIdx.x * kS2Warps + warp;
-  if (c >= count) return;
-  const int sp = blockIdx.y;
-  const uint64_t row0 = (uint64_t)sp * rows_per_split;
-  uint64_t row1 = row0 + rows_per_split;
-  if (row1 > N) row1 = N;
-  const int TB = Dp >> 3;
-
-  // phase A: off-diagonal tile (tj < tk) of this lane
-  int tj = 0, tk = 0;
-  bool actA = false;
-  {
-    int idx = lane;
-    for (int t = 0; t < TB; ++t) {
-      const int cnt = TB - 1 - t;
-      if (idx < cnt) {
-        tj = t;
-        tk = t + 1 + idx;
-        actA = true;
-        break;
-      }
-      idx -= cnt;
-    }
-  }
-  const int offAx = actA ? Dp + 8 * tj : 0;  // BA_{8tj..}
-  const int offAy = actA ? 8 * tk : 0;       // AB_{8tk..}
-  // phase B: diagonal tile d, rows q and 7-q of its strict upper triangle (7 pairs)
-  const int dB = lane >> 2, qB = lane & 3;
-  const bool actB = dB < TB;
-  const int offBx0 = actB ? Dp + 8 * dB + qB : 0;
-  const int offBx1 = actB ? Dp + 8 * dB + 7 - qB : 0;
-  int offBy[7];
-#pragma unroll
-  for (int s = 0; s < 7; ++s) {
-    const int kk = (s + 1 > qB) ? (s + 1) : (7 - qB + s + 1);
-    offBy[s] = actB ? 8 * dB + kk : 0;
-  }
-  // phase C: first/total order for columns lane, lane+32
-  const int offC0 = (lane < Dp) ? lane : 0;
-  const int offC1 = (lane + 32 < Dp) ? lane + 32 : 0;
-  const int offAB = 2 * Dp;  // A, B
-
-  double acc[8][8];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-  double accB[7];
-#pragma unroll
-  for (int s = 0; s < 7; ++s) accB[s] = 0.0;
-  double s1_0 = 0.0, s1_1 = 0.0, st_0 = 0.0, st_1 = 0.0;
-  double sA = 0.0, sB = 0.0, sAA = 0.0, sBB = 0.0, sAB = 0.0;
-
-  const uint8_t *wrow = w ? w + c * Npad : nullptr;
-  for (uint64_t i0 = row0; i0 < row1; i0 += 32) {
-    const uint64_t i = i0 + lane;
-    unsigned wl = 0;
-    if (i < row1) wl = wrow ? (unsigned)wrow[i] : 1u;
-    unsigned mask = __ballot_sync(kFull, wl != 0);
-    while (mask) {
-      const int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const double wv = (double)__shfl_sync(kFull, wl, b);
-      const double *__restrict__ row = Yn + (i0 + b) * (uint64_t)stride;
-      {  // phase A
-        double X[8], Yv[8];
-        load8(row + offAx, X);
-        load8(row + offAy, Yv);
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const double wx = wv * X[a];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Yv[k], acc[a][k]);
-        }
-      }
-      {  // phase B
-        const double x0 = wv * __ldg(row + offBx0);
-        const double x1 = wv * __ldg(row + offBx1);
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const double y = __ldg(row + offBy[s]);
-          accB[s] = fma((s + 1 > qB) ? x0 : x1, y, accB[s]);
-        }
-      }
-      {  // phase C
-        const double2 ab = __ldg(reinterpret_cast<const double2 *>(row + offAB));
-        const double a = ab.x, bb = ab.y;
-        const double wa = wv * a, wb = wv * bb;
-        sA += wa;
-        sB += wb;
-        sAA = fma(wa, a, sAA);
-        sBB = fma(wb, bb, sBB);
-        sAB = fma(wb, a, sAB);
-        const double t0 = __ldg(row + offC0) - a;
-        const double t1 = __ldg(row + offC1) - a;
-        s1_0 = fma(wb, t0, s1_0);
-        s1_1 = fma(wb, t1, s1_1);
-        st_0 = fma(wv * t0, t0, st_0);
-        st_1 = fma(wv * t1, t1, st_1);
-      }
-    }
-  }
-
-  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
-  if (lane == 0) {
-    out[0] = sA;
-    out[1] = sB;
-    out[2] = sAA;
-    out[3] = sBB;
-    out[4] = sAB;
-  }
-  if (lane < Dg) {
-    out[5 + lane] = s1_0;
-    out[5 + Dg + lane] = st_0;
-  }
-  if (lane + 32 < Dg) {
-    out[5 + lane + 32] = s1_1;
-    out[5 + Dg + lane + 32] = st_1;
-  }
-  double *o2 = out + 5 + 2 * Dg;
-  if (actA) {
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int j = 8 * tj + a, kk = 8 * tk + k;
-        if (j < Dg && kk < Dg) o2[pair_index(j, kk, Dg)] = acc[a][k];
-      }
-  }
-  if (actB) {
-#pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const int jj = (s + 1 > qB) ? qB : 7 - qB;
-      const int kk = (s + 1 > qB) ? (s + 1) : (7 - qB + s + 1);
-      const int j = 8 * dB + jj, k = 8 * dB + kk;
-      if (k < Dg) o2[pair_index(j, k, Dg)] = accB[s];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// second-order accumulate, shared-memory staged (the production kernel for Dg <= 64)
-// ------------------------------------------------------------------------------------------
-// Same decomposition as s2_accum_tile8_kernel (warp <-> resample, lane <-> 8x8 register tile) but
-// the rows are streamed through shared memory instead of the L1: ncu on the L1 version showed the
-// L1 data pipe at 91 % (118 wavefronts per row) and the FP64 pipe at 38 %.
-//   * tiles of 32 contiguous rows (32*stride*8 B, contiguous in HBM) are brought in with one
-//     cp.async.bulk each into a 4-stage ring; an mbarrier per stage carries the byte count;
-//   * the 8 warps of a block (8 resamples) consume the same tiles at their own pace; the last warp
-//     to leave a stage (shared counter) re-arms its barrier and issues the copy of tile t+4, so
-//     there is no block-wide barrier in the loop;
-//   * operand loads are 128-bit and bank-conflict free: lane tiles whose 64-byte blocks share banks
-//     read their four 16-byte chunks in an XOR-permuted order (free: the permutation only renames
-//     accumulators);
-//   * the 4 lanes left over by the 28 off-diagonal tiles take 4 of the 8 diagonal tiles as full
-//     tiles; the other 4 diagonal triangles (112 pairs) are spread 4 per lane.
 constexpr int kTileRows = 32;
 constexpr int kStages = 4;
 
@@ -466,24 +324,79 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
-// The 28 pairs (jj < kk) of an 8x8 strict upper triangle in 7 groups of 4; each group touches at
-// most two columns.  Packed per group: rows x[0..3] (3 bits each), columns y0, y1 (3 bits each),
-// selector bits (slot s uses y1 if bit s).
-__device__ __forceinline__ void diag_group(int g, int (&xr)[4], int &y0, int &y1, int &sel) {
-  // g0..g3: column 7-g, rows 0..3
-  // g4: (4,7)(5,7)(6,7)(0,1)   g5: (4,6)(5,6)(0,2)(1,2)   g6: (4,5)(0,3)(1,3)(2,3)
-  if (g < 4) {
-    xr[0] = 0; xr[1] = 1; xr[2] = 2; xr[3] = 3;
-    y0 = 7 - g; y1 = 7 - g; sel = 0;
-  } else if (g == 4) {
-    xr[0] = 4; xr[1] = 5; xr[2] = 6; xr[3] = 0;
-    y0 = 7; y1 = 1; sel = 0x8;
-  } else if (g == 5) {
-    xr[0] = 4; xr[1] = 5; xr[2] = 0; xr[3] = 1;
-    y0 = 6; y1 = 2; sel = 0xC;
-  } else {
-    xr[0] = 4; xr[1] = 0; xr[2] = 1; xr[3] = 2;
-    y0 = 5; y1 = 3; sel = 0xE;
+// The 28 pairs (jj < kk) of an 8x8 strict upper triangle on 8 lanes, 4 slots per lane: slots 0,1 are
+// rows (ra, ra+1) of column ca, slots 2,3 rows (rb, rb+1) of column cb.  Lanes 0..5 carry two full
+// row pairs, lanes 6,7 carry the four left-over single pairs (their slots 1 and 3 are unused):
+//   g:      0        1        2        3        4        5        6          7
+//   ca/ra:  7/0      7/2      7/4      5/0      5/2      3/0      7/6 (one)  3/2 (one)
+//   cb/rb:  6/0      6/2      6/4      4/0      4/2      2/0      5/4 (one)  1/0 (one)
+// Every lane uses column ca for slots 0,1 and cb for slots 2,3: no per-slot operand selection, and
+// each row pair is one aligned LDS.128.
+__device__ __forceinline__ void diag_group(int g, int &ca, int &ra, int &cb, int &rb, bool &single) {
+  const int sh = 4 * g;  // one nibble per group, group 0 in the low nibble
+  ca = (0x37355777u >> sh) & 15;
+  ra = (0x26020420u >> sh) & 15;
+  cb = (0x15244666u >> sh) & 15;
+  rb = (0x04020420u >> sh) & 15;
+  single = g >= 6;
+}
+
+// sum_i w*A, w*B, w*A^2, w*B^2, w*A*B.  Kept out of the tile kernel (10 registers and 5 DFMA per row
+// there).  One block per 4 resamples and row split; its 256 threads stride over the rows of the
+// column-major A/B copy (coalesced, L2 resident), two rows in flight per thread; fixed-order
+// block reduction, so the result is deterministic.
+constexpr int kScC = 4;
+__global__ void __launch_bounds__(256)
+scalar_sums_kernel(const double *__restrict__ Yt, uint64_t Npad, uint64_t N, const uint8_t *__restrict__ w,
+                   uint64_t count, uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  __shared__ double red[8][kScC * 5];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t cbase = (uint64_t)blockIdx.x * kScC;
+  const int sp = blockIdx.y;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+  double sc[kScC][5];
+#pragma unroll
+  for (int c = 0; c < kScC; ++c)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) sc[c][q] = 0.0;
+  const double *colA = Yt, *colB = Yt + Npad;
+  auto add_row = [&](uint64_t i) {
+    const double a = colA[i], b = colB[i];
+    const double aa = a * a, bb = b * b, ab = a * b;
+#pragma unroll
+    for (int c = 0; c < kScC; ++c) {
+      double wv = 1.0;
+      if (w) wv = (cbase + c < count) ? (double)w[(cbase + c) * Npad + i] : 0.0;
+      sc[c][0] = fma(wv, a, sc[c][0]);
+      sc[c][1] = fma(wv, b, sc[c][1]);
+      sc[c][2] = fma(wv, aa, sc[c][2]);
+      sc[c][3] = fma(wv, bb, sc[c][3]);
+      sc[c][4] = fma(wv, ab, sc[c][4]);
+    }
+  };
+  uint64_t i = row0 + threadIdx.x;
+  for (; i + 256 < row1; i += 512) {
+    add_row(i);
+    add_row(i + 256);
+  }
+  if (i < row1) add_row(i);
+#pragma unroll
+  for (int c = 0; c < kScC; ++c)
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double v = warp_sum(sc[c][q]);
+      if (lane == 0) red[warp][c * 5 + q] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < kScC * 5) {
+    const int c = threadIdx.x / 5, q = threadIdx.x % 5;
+    if (cbase + c < count) {
+      double v = 0.0;
+      for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+      psum[((uint64_t)sp * count + cbase + c) * (uint64_t)nacc + q] = v;
+    }
   }
 }
 
@@ -505,7 +418,7 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   const uint32_t row_bytes = (uint32_t)stride * 8u;
   const uint32_t stage_bytes = kTileRows * row_bytes;
   const uint32_t sm_base = smem_u32(smraw);
-  const uint32_t bar_base = sm_base + kStages * stage_bytes;   // kStages x u64
+  const uint32_t bar_base = sm_base + kStages * stage_bytes;  // kStages x u64
   uint32_t *cnt = reinterpret_cast<uint32_t *>(smraw + kStages * stage_bytes + kStages * 8);
 
   auto issue = [&](int t) {  // one elected thread: arm the barrier and start the bulk copy of tile t
@@ -550,31 +463,29 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     tj = tk = lane - ntOff;
     actA = true;
   }
-  const int ndiag_full = (32 - ntOff < TB) ? (32 - ntOff) : TB;   // diagonal tiles done as full tiles
-  const int rx = (tj >> 1) & 3, ry = (tk >> 1) & 3;
-  uint32_t offX[4], offY[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    offX[t] = actA ? (uint32_t)(Dp + 8 * tj + 2 * (t ^ rx)) * 8u : 0u;
-    offY[t] = actA ? (uint32_t)(8 * tk + 2 * (t ^ ry)) * 8u : 0u;
-  }
-  // remaining diagonal tiles (only when TB == 8: tiles 4..7), 4 pairs per lane on lanes 0..27
+  const int ndiag_full = (32 - ntOff < TB) ? (32 - ntOff) : TB;  // diagonal tiles done as full tiles
+  const int PL = TB * kBlockPitch;                                              // doubles per AB / BA part
+  const uint32_t offX = actA ? (uint32_t)(PL + kBlockPitch * tj) * 8u : 0u;  // BA block tj
+  const uint32_t offY = actA ? (uint32_t)(kBlockPitch * tk) * 8u : 0u;       // AB block tk
+  // remaining diagonal tiles (only when TB == 8: tiles 4..7): 8 lanes per tile, see diag_group
   const bool hasB = ndiag_full < TB;
-  const int dB = ndiag_full + (lane & 3);
-  const int gB = lane >> 2;
-  const bool actB = hasB && gB < 7 && dB < TB;
-  int xr[4], yb0, yb1, selB;
-  diag_group(gB < 7 ? gB : 0, xr, yb0, yb1, selB);
-  const int swz = (dB >> 1) & 1;  // de-conflict lanes whose tiles are 128 B apart
-  uint32_t offBx[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) offBx[s] = actB ? (uint32_t)(Dp + 8 * dB + xr[s ^ swz]) * 8u : 0u;
-  const uint32_t offBy0 = actB ? (uint32_t)(8 * dB + yb0) * 8u : 0u;
-  const uint32_t offBy1 = actB ? (uint32_t)(8 * dB + yb1) * 8u : 0u;
-  // first/total order: columns lane, lane+32
-  const uint32_t offC0 = (lane < Dp) ? lane * 8u : 0u;
-  const uint32_t offC1 = (lane + 32 < Dp) ? (lane + 32) * 8u : 0u;
-  const uint32_t offAB = 2u * Dp * 8u;
+  const int dB = ndiag_full + (lane >> 3);
+  const int gB = lane & 7;
+  const bool actB = hasB && dB < TB;
+  int bca, bra, bcb, brb;
+  bool bsingle;
+  diag_group(gB, bca, bra, bcb, brb, bsingle);
+  const uint32_t offBxa = actB ? (uint32_t)(PL + col_pos(8 * dB + bra)) * 8u : 0u;  // rows ra, ra+1
+  const uint32_t offBxb = actB ? (uint32_t)(PL + col_pos(8 * dB + brb)) * 8u : 0u;  // rows rb, rb+1
+  const uint32_t offBya = actB ? (uint32_t)col_pos(8 * dB + bca) * 8u : 0u;
+  const uint32_t offByb = actB ? (uint32_t)col_pos(8 * dB + bcb) * 8u : 0u;
+  // first/total order: two columns per lane; block order {0,4,1,5} / {2,6,3,7} over the quarter-warps
+  // keeps the two blocks a half-warp reads with one LDS.64 in disjoint banks
+  const int cblk0 = ((lane >> 3) & 1) * 4 + (lane >> 4);
+  const int jC0 = 8 * cblk0 + (lane & 7), jC1 = jC0 + 16;
+  const uint32_t offC0 = (jC0 < Dp) ? (uint32_t)col_pos(jC0) * 8u : 0u;
+  const uint32_t offC1 = (jC1 < Dp) ? (uint32_t)col_pos(jC1) * 8u : 0u;
+  const uint32_t offAB = 2u * PL * 8u;
 
   double acc[8][8];
 #pragma unroll
@@ -583,7 +494,6 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
   double accB[4] = {0.0, 0.0, 0.0, 0.0};
   double s1_0 = 0.0, s1_1 = 0.0, st_0 = 0.0, st_1 = 0.0;
-  double sA = 0.0, sB = 0.0, sAA = 0.0, sBB = 0.0, sAB = 0.0;
 
   const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
   auto load_w = [&](int t) -> unsigned {
@@ -593,63 +503,101 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   };
   unsigned wl_next = load_w(0);
 
+  double P[8], Q[8];
+  auto ldP = [&](uint32_t row, int q) {
+    const double2 v = lds_f64x2(row + offX + 16u * q);
+    P[2 * q] = v.x;
+    P[2 * q + 1] = v.y;
+  };
+  auto ldQ = [&](uint32_t row, int q) {
+    const double2 v = lds_f64x2(row + offY + 16u * q);
+    Q[2 * q] = v.x;
+    Q[2 * q + 1] = v.y;
+  };
+  auto side_work = [&](uint32_t row, double wv) {  // diagonal leftovers + first/total order
+    if (hasB) {                                    // warp-uniform
+      const double ya = wv * lds_f64(row + offBya);
+      const double yb = wv * lds_f64(row + offByb);
+      const double2 xa = lds_f64x2(row + offBxa);
+      const double2 xb = lds_f64x2(row + offBxb);
+      accB[0] = fma(xa.x, ya, accB[0]);
+      accB[1] = fma(xa.y, ya, accB[1]);
+      accB[2] = fma(xb.x, yb, accB[2]);
+      accB[3] = fma(xb.y, yb, accB[3]);
+    }
+    const double2 ab = lds_f64x2(row + offAB);
+    const double wb = wv * ab.y;
+    const double t0 = lds_f64(row + offC0) - ab.x;
+    const double t1 = lds_f64(row + offC1) - ab.x;
+    s1_0 = fma(wb, t0, s1_0);
+    s1_1 = fma(wb, t1, s1_1);
+    st_0 = fma(wv * t0, t0, st_0);
+    st_1 = fma(wv * t1, t1, st_1);
+  };
+
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kStages;
     const uint32_t parity = (uint32_t)(t / kStages) & 1u;
     const unsigned wl = wl_next;
     wl_next = load_w(t + 1);
     unsigned mask = __ballot_sync(kFull, wl != 0);
+    // multiplicities are small integers: as doubles their low word is 0, so one 32-bit shuffle of
+    // the high word moves them between lanes and no int->double conversion sits in the row loop
+    const int whi = __double2hiint((double)wl);
     const uint32_t bar = bar_base + 8u * s;
     while (!mbar_try_wait(bar, parity)) {
     }
     const uint32_t tile = sm_base + s * stage_bytes;
+    bool pre = false;  // is the resident operand set of the upcoming row already loaded?
     while (mask) {
-      const int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const double wv = (double)__shfl_sync(kFull, wl, b);
-      const uint32_t row = tile + (uint32_t)b * row_bytes;
-      {  // full 8x8 tile
-        double X[8], Yv[8];
+      {  // ---- type 1 row: P streamed, Q resident
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
+        const uint32_t row = tile + (uint32_t)b * row_bytes;
+        const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
+        if (!pre) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ldQ(row, q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ldP(row, q);
+        side_work(row, wv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const double2 vx = lds_f64x2(row + offX[q]);
-          const double2 vy = lds_f64x2(row + offY[q]);
-          X[2 * q] = vx.x;
-          X[2 * q + 1] = vx.y;
-          Yv[2 * q] = vy.x;
-          Yv[2 * q + 1] = vy.y;
-        }
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const double wx = wv * X[a];
+          for (int e = 0; e < 2; ++e) {
+            const int a = 2 * q + e;
+            const double wx = wv * P[a];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Yv[k], acc[a][k]);
+            for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Q[k], acc[a][k]);
+          }
+          ldP(nrow, q);  // the next (type 2) row wants P resident
         }
+        pre = mask != 0;
       }
-      if (hasB) {  // warp-uniform
-        const double y0 = wv * lds_f64(row + offBy0);
-        const double y1 = wv * lds_f64(row + offBy1);
+      if (!mask) break;
+      {  // ---- type 2 row: Q streamed, P resident
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
+        const uint32_t row = tile + (uint32_t)b * row_bytes;
+        const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ldQ(row, q);
+        side_work(row, wv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const double x = lds_f64(row + offBx[q]);
-          accB[q] = fma(x, ((selB >> (q ^ swz)) & 1) ? y1 : y0, accB[q]);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * q + e;
+            const double wy = wv * Q[k];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) acc[a][k] = fma(P[a], wy, acc[a][k]);
+          }
+          ldQ(nrow, q);  // the next (type 1) row wants Q resident
         }
-      }
-      {  // first / total order + scalars
-        const double2 ab = lds_f64x2(row + offAB);
-        const double a = ab.x, bb = ab.y;
-        const double wa = wv * a, wb = wv * bb;
-        sA += wa;
-        sB += wb;
-        sAA = fma(wa, a, sAA);
-        sBB = fma(wb, bb, sBB);
-        sAB = fma(wb, a, sAB);
-        const double t0 = lds_f64(row + offC0) - a;
-        const double t1 = lds_f64(row + offC1) - a;
-        s1_0 = fma(wb, t0, s1_0);
-        s1_1 = fma(wb, t1, s1_1);
-        st_0 = fma(wv * t0, t0, st_0);
-        st_1 = fma(wv * t1, t1, st_1);
+        pre = mask != 0;
       }
     }
     // release the stage; the last warp out refills it with tile t + kStages
@@ -669,20 +617,13 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 
   if (!live) return;
   double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
-  if (lane == 0) {
-    out[0] = sA;
-    out[1] = sB;
-    out[2] = sAA;
-    out[3] = sBB;
-    out[4] = sAB;
+  if (jC0 < Dg) {
+    out[5 + jC0] = s1_0;
+    out[5 + Dg + jC0] = st_0;
   }
-  if (lane < Dg) {
-    out[5 + lane] = s1_0;
-    out[5 + Dg + lane] = st_0;
-  }
-  if (lane + 32 < Dg) {
-    out[5 + lane + 32] = s1_1;
-    out[5 + Dg + lane + 32] = st_1;
+  if (jC1 < Dg) {
+    out[5 + jC1] = s1_1;
+    out[5 + Dg + jC1] = st_1;
   }
   double *o2 = out + 5 + 2 * Dg;
   if (actA) {
@@ -690,18 +631,20 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int j = 8 * tj + 2 * ((a >> 1) ^ rx) + (a & 1);
-        const int kk = 8 * tk + 2 * ((k >> 1) ^ ry) + (k & 1);
+        const int j = 8 * tj + a;
+        const int kk = 8 * tk + k;
         if (j < kk && kk < Dg) o2[pair_index(j, kk, Dg)] = acc[a][k];
       }
   }
   if (actB) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int sl = q ^ swz;
-      const int j = 8 * dB + xr[sl];
-      const int k = 8 * dB + (((selB >> sl) & 1) ? yb1 : yb0);
-      if (k < Dg) o2[pair_index(j, k, Dg)] = accB[q];
+    const int base = 8 * dB;
+    if (base + bca < Dg) {
+      o2[pair_index(base + bra, base + bca, Dg)] = accB[0];
+      if (!bsingle) o2[pair_index(base + bra + 1, base + bca, Dg)] = accB[1];
+    }
+    if (base + bcb < Dg) {
+      o2[pair_index(base + brb, base + bcb, Dg)] = accB[2];
+      if (!bsingle) o2[pair_index(base + brb + 1, base + bcb, Dg)] = accB[3];
     }
   }
 }
@@ -799,11 +742,12 @@ accum_generic_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
                      uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
   const uint64_t c = blockIdx.x;
   const int sp = blockIdx.y;
+  const int PL = part_len(Dg);
   const uint64_t row0 = (uint64_t)sp * rows_per_split;
   uint64_t row1 = row0 + rows_per_split;
   if (row1 > N) row1 = N;
   const uint8_t *wrow = w ? w + c * Npad : nullptr;
-  const int offA = (second_order ? 2 : 1) * Dp, offB = offA + 1;
+  const int offA = (second_order ? 2 : 1) * PL, offB = offA + 1;
   __shared__ double sw[kGenRows];
   double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
 
@@ -813,14 +757,14 @@ accum_generic_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     int kind = -1, cx = 0, cy = 0;
     if (a < nacc) {
       if (a < 5) kind = a;
-      else if (a < 5 + Dg) { kind = 5; cx = a - 5; }
-      else if (a < 5 + 2 * Dg) { kind = 6; cx = a - 5 - Dg; }
+      else if (a < 5 + Dg) { kind = 5; cx = col_pos(a - 5); }
+      else if (a < 5 + 2 * Dg) { kind = 6; cx = col_pos(a - 5 - Dg); }
       else {
         kind = 7;
         int p = a - 5 - 2 * Dg, j = 0;
         while (p >= Dg - 1 - j) { p -= Dg - 1 - j; ++j; }
-        cx = Dp + j;           // BA_j
-        cy = j + 1 + p;        // AB_k
+        cx = PL + col_pos(j);       // BA_j
+        cy = col_pos(j + 1 + p);    // AB_k
       }
     }
     double accv = 0.0;
@@ -974,7 +918,7 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
     const uint64_t Npad = pad_rows(N);
     uint64_t bx = ceil_div_u64(Npad, 256);
     if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)(Dg + 2));
+    dim3 grid((unsigned)bx, (unsigned)(second_order ? 2 : Dg + 2));
     normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
     note_launches(1);
   }
@@ -1024,7 +968,7 @@ extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_
   return SA_OK;
 }
 
-// algo: 0 auto, 1 generic, 2 second-order tile8 via L1, 3 first-order, 4 second-order tile8 via shared memory
+// algo: 0 auto, 1 generic, 3 first/total order, 4 second-order 8x8 register tiles
 extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                                           int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                                           int nsplit, double *d_psum, int algo) {
@@ -1042,28 +986,18 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   if (algo == 0) algo = second_order ? (Dg <= 64 ? 4 : 1) : 3;
   if (algo == 4) {
     SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
-    SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
+    SA_REQUIRE(d_Yn && d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn / d_Yt is null");
     SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
     const uint64_t bx = ceil_div_u64(count, kS2Warps);
+    const uint64_t bsc = ceil_div_u64(count, kScC);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
     const size_t smem = (size_t)kStages * kTileRows * stride * 8 + kStages * 8 + kStages * 4 + 16;
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-      SA_CUDA(cudaFuncSetAttribute(s2_accum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    dim3 grid((unsigned)bx, (unsigned)nsplit);
-    s2_accum_smem_kernel<<<grid, kS2Warps * 32, smem, st>>>(d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum,
-                                                           nacc);
-  } else if (algo == 2) {
-    SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
-    SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
-    SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
-    const uint64_t bx = ceil_div_u64(count, kS2Warps);
-    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
-    dim3 grid((unsigned)bx, (unsigned)nsplit);
-    s2_accum_tile8_kernel<<<grid, kS2Warps * 32, 0, st>>>(d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum,
-                                                         nacc);
+    SA_CUDA(cudaFuncSetAttribute(s2_accum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scalar_sums_kernel<<<dim3((unsigned)bsc, (unsigned)nsplit), 256, 0, st>>>(d_Yt, Npad, N, d_w, count, rps, d_psum,
+                                                                               nacc);
+    s2_accum_smem_kernel<<<dim3((unsigned)bx, (unsigned)nsplit), kS2Warps * 32, smem, st>>>(
+        d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc);
+    note_launches(1);
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
     SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt is null");

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == declared
     assert _lib.lib().sa_version() >= 100
-    assert _lib.lib().sa_row_stride(64, 1) == 136 and _lib.lib().sa_row_stride(3, 0) == 16
+    assert _lib.lib().sa_row_stride(64, 1) == 162 and _lib.lib().sa_row_stride(3, 0) == 12
     assert _lib.lib().sa_pad_rows(1000) == 1024
 
 
