@@ -282,11 +282,9 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
 // instruction offset fall into different bank groups: all operand loads are conflict-free LDS.128
 // from one base register per operand set.
 //
-// Software pipeline (no extra registers): two operand sets P (8 BA values) and Q (8 AB values) stay
-// in registers across rows and rows alternate between
-//   type 1: a-major order, P streamed in at the row start, Q already resident; each P chunk is
-//           refilled with the NEXT row's values as soon as its 16 DFMAs are issued;
-//   type 2: k-major order, Q streamed, P resident, Q chunks refilled for the next row.
+// Software pipeline: the operands of row r+1 (8 LDS.128) are fetched while the 64 DFMAs of row r are
+// issued -- the BA chunks into the registers the update has just finished with, the AB values into
+// a second buffer -- so only the first row of a tile waits for shared memory.
 // ncu history of this kernel is in profiles/ (L1 version: 118 wavefronts/row, FP64 pipe 38 %).
 constexpr int kS2Warps = 8;
 constexpr int kTileRows = 32;
@@ -503,32 +501,60 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   };
   unsigned wl_next = load_w(0);
 
-  double P[8], Q[8];
+  // Operand registers: P = the 8 BA values of the lane's tile, Q0/Q1 = the 8 AB values of the current
+  // and of the next row (roles swap every row).  While the 64 DFMAs of row r are issued, the 8
+  // LDS.128 of row r+1 are already in flight: P chunks are refilled as soon as their 16 DFMAs are
+  // out, the other AB buffer is free.  Only the first row of a tile waits for its operands.
+  double P[8], Q0[8], Q1[8];
   auto ldP = [&](uint32_t row, int q) {
     const double2 v = lds_f64x2(row + offX + 16u * q);
     P[2 * q] = v.x;
     P[2 * q + 1] = v.y;
   };
-  auto ldQ = [&](uint32_t row, int q) {
+  auto ldQ = [&](double(&Q)[8], uint32_t row, int q) {
     const double2 v = lds_f64x2(row + offY + 16u * q);
     Q[2 * q] = v.x;
     Q[2 * q + 1] = v.y;
   };
-  auto side_work = [&](uint32_t row, double wv) {  // diagonal leftovers + first/total order
-    if (hasB) {                                    // warp-uniform
-      const double ya = wv * lds_f64(row + offBya);
-      const double yb = wv * lds_f64(row + offByb);
-      const double2 xa = lds_f64x2(row + offBxa);
-      const double2 xb = lds_f64x2(row + offBxb);
+  // one row: rank-1 update with (P, Qc); prefetch the next row into (P, Qn); diagonal leftovers and
+  // first/total order ("side work") are loaded after the second chunk and consumed at the end
+  auto do_row = [&](uint32_t row, uint32_t nrow, double wv, double(&Qc)[8], double(&Qn)[8]) {
+    double ya = 0.0, yb = 0.0, t0, t1;
+    double2 xa = make_double2(0.0, 0.0), xb = xa, ab;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int a = 2 * q + e;
+        const double wx = wv * P[a];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Qc[k], acc[a][k]);
+      }
+      ldP(nrow, q);
+      ldQ(Qn, nrow, q);
+      if (q == 1) {  // side loads for THIS row
+        if (hasB) {
+          ya = lds_f64(row + offBya);
+          yb = lds_f64(row + offByb);
+          xa = lds_f64x2(row + offBxa);
+          xb = lds_f64x2(row + offBxb);
+        }
+        ab = lds_f64x2(row + offAB);
+        t0 = lds_f64(row + offC0);
+        t1 = lds_f64(row + offC1);
+      }
+    }
+    if (hasB) {  // warp-uniform
+      ya *= wv;
+      yb *= wv;
       accB[0] = fma(xa.x, ya, accB[0]);
       accB[1] = fma(xa.y, ya, accB[1]);
       accB[2] = fma(xb.x, yb, accB[2]);
       accB[3] = fma(xb.y, yb, accB[3]);
     }
-    const double2 ab = lds_f64x2(row + offAB);
     const double wb = wv * ab.y;
-    const double t0 = lds_f64(row + offC0) - ab.x;
-    const double t1 = lds_f64(row + offC1) - ab.x;
+    t0 -= ab.x;
+    t1 -= ab.x;
     s1_0 = fma(wb, t0, s1_0);
     s1_1 = fma(wb, t1, s1_1);
     st_0 = fma(wv * t0, t0, st_0);
@@ -548,56 +574,31 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     while (!mbar_try_wait(bar, parity)) {
     }
     const uint32_t tile = sm_base + s * stage_bytes;
-    bool pre = false;  // is the resident operand set of the upcoming row already loaded?
+    if (mask) {  // cold start of the tile: operands of its first row
+      const uint32_t row = tile + (uint32_t)(__ffs(mask) - 1) * row_bytes;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ldP(row, q);
+        ldQ(Q0, row, q);
+      }
+    }
     while (mask) {
-      {  // ---- type 1 row: P streamed, Q resident
+      {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
         const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
         const uint32_t row = tile + (uint32_t)b * row_bytes;
         const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-        if (!pre) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ldQ(row, q);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ldP(row, q);
-        side_work(row, wv);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int a = 2 * q + e;
-            const double wx = wv * P[a];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Q[k], acc[a][k]);
-          }
-          ldP(nrow, q);  // the next (type 2) row wants P resident
-        }
-        pre = mask != 0;
+        do_row(row, nrow, wv, Q0, Q1);
       }
       if (!mask) break;
-      {  // ---- type 2 row: Q streamed, P resident
+      {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
         const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
         const uint32_t row = tile + (uint32_t)b * row_bytes;
         const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ldQ(row, q);
-        side_work(row, wv);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int k = 2 * q + e;
-            const double wy = wv * Q[k];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) acc[a][k] = fma(P[a], wy, acc[a][k]);
-          }
-          ldQ(nrow, q);  // the next (type 1) row wants Q resident
-        }
-        pre = mask != 0;
+        do_row(row, nrow, wv, Q1, Q0);
       }
     }
     // release the stage; the last warp out refills it with tile t + kStages
