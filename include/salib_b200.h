@@ -60,12 +60,20 @@ int sa_direction_vectors(const uint32_t *h_a, const uint8_t *h_s, const uint32_t
  *   d_shift  [2D] digital shift (zeros when unscrambled), may be NULL
  *   d_group_of_col [D] group index of each column (NULL = ungrouped, Dg must equal D)
  *   d_lb, d_span   [D] lower bound and (ub - lb), both already rounded to f64 on the host
+ *   d_dist_code, d_dist_par  NULL for uniform bounds; else [D] codes and [D][4] parameters of the
+ *            per-column inverse CDFs (replaces util/__init__.py:126-289; d_lb/d_span then unused):
+ *              0 unif      {lb, span}                 1 triang  {loc, scale, c}
+ *              2 logunif   {log a, log b - log a}     3 norm    {loc, scale}
+ *              4 truncnorm, a < 0   {Phi(a),  Phi(b)-Phi(a), loc, scale}
+ *              5 truncnorm, a >= 0  {Phi(-b), Phi(b)-Phi(a), loc, scale}
+ *              6 lognorm   {loc, scale}               7 weibull {1/c, scale, loc}
  *   d_out    [(step*n), D] row-major f64, step = 2*Dg+2 (second_order) or Dg+2; 16-byte aligned
- * Values are computed as round(round(x * span) + lb) -- no FMA contraction.      */
+ * Uniform values are computed as round(round(x * span) + lb) -- no FMA contraction.  */
 int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                            uint64_t first_index, uint64_t n, int D, int Dg,
                            const int32_t *d_group_of_col, int second_order, const double *d_lb,
-                           const double *d_span, double *d_out);
+                           const double *d_span, const int32_t *d_dist_code, const double *d_dist_par,
+                           double *d_out);
 
 /* ---- test functions on the path -----------------------------------------------------------
  * sa_eval_ishigami_f64 replaces test_functions/Ishigami.py:55-59, sa_eval_sobol_g_f64 replaces
@@ -81,14 +89,16 @@ int sa_eval_sobol_g_f64(void *stream, const double *d_X, uint64_t rows, int D, c
 int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                                  uint64_t first_index, uint64_t n, int D, int Dg,
                                  const int32_t *d_group_of_col, int second_order,
-                                 const double *d_lb, const double *d_span, const double *d_a,
-                                 const double *d_delta, const double *d_alpha, double *d_Y,
-                                 int32_t *d_flag);
+                                 const double *d_lb, const double *d_span,
+                                 const int32_t *d_dist_code, const double *d_dist_par,
+                                 const double *d_a, const double *d_delta, const double *d_alpha,
+                                 double *d_Y, int32_t *d_flag);
 int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                                   uint64_t first_index, uint64_t n, int Dg,
                                   const int32_t *d_group_of_col, int second_order,
-                                  const double *d_lb, const double *d_span, double A, double B,
-                                  double *d_Y);
+                                  const double *d_lb, const double *d_span,
+                                  const int32_t *d_dist_code, const double *d_dist_par, double A,
+                                  double B, double *d_Y);
 
 /* ---- analyze: normalisation ---------------------------------------------------------------
  * sa_moments_f64 replaces Y.mean() / Y.std() of analyze/sobol.py:141 (two-pass, population

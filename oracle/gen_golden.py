@@ -78,6 +78,21 @@ for name, D, N, seed, skip in [("scr_g6_n64_seed7", 6, 64, 7, 0), ("scr_g40_n32_
          bounds=np.array(p["bounds"], dtype=np.float64),
          sv=eng._sv.astype(np.uint32), shift=eng._shift.astype(np.uint32))
 
+# non-uniform `dists` (util/__init__.py:126-289): every distribution the reference supports, in one problem
+DIST_PROBLEM = {
+    "num_vars": 9, "names": [f"p{i}" for i in range(9)],
+    "dists": ["unif", "triang", "norm", "truncnorm", "lognorm", "logunif", "weibull", "triang", "truncnorm"],
+    "bounds": [[-2.0, 3.5], [1.0, 3.0, 0.25], [0.5, 2.0], [-1.0, 4.0, 1.0, 2.0], [0.1, 0.6], [1e-3, 10.0],
+               [1.7, 2.5, 0.3], [3.0, 0.5], [2.0, 6.0, 1.0, 1.5]],
+}
+for name, N, c2, skip, groups in [("dists_n64_c2_skip64", 64, True, 64, None), ("dists_n32_c1_skip0", 32, False, 0, None),
+                                  ("dists_grp_n32_c2_skip32", 32, True, 32, ["a", "b", "a", "c", "b", "c", "d", "d", "a"])]:
+    p = {k: (list(v) if isinstance(v, list) else v) for k, v in DIST_PROBLEM.items()}
+    if groups:
+        p["groups"] = groups
+    X = ref_sobol.sample(p, N, calc_second_order=c2, scramble=False, skip_values=skip)
+    save("sample_" + name, X=X, N=N, c2=c2, skip=skip, groups=np.array(groups or [], dtype="U8"))
+
 # first ten Joe-Kuo points (tests/test_sobol.py:24-35 checks these with atol 5e-2)
 save("joe_kuo_first10", pts=qmc.Sobol(d=3, scramble=False).random(16)[:10])
 

@@ -40,6 +40,45 @@ __device__ __forceinline__ double scale_value(uint32_t x, double span, double lb
   return __dadd_rn(__dmul_rn((double)x * kTwoPowMinus30, span), lb);
 }
 
+// Per-column scaling: uniform bounds (code == nullptr; util/__init__.py:49-53) or the inverse CDF of
+// the column's distribution (util/__init__.py:126-289, scipy.stats ppf restated).  Distribution
+// codes and the 4 parameters per column are prepared by the host (salib_b200/sample/sobol.py):
+//   0 unif      lb, span                        u*span + lb
+//   1 triang    loc, scale, c                   loc + scale * (u < c ? sqrt(c u) : 1 - sqrt((1-c)(1-u)))
+//   2 logunif   log a, log b - log a            exp(log a + u (log b - log a))
+//   3 norm      loc, scale                      loc + scale * ndtri(u)
+//   4 truncnorm (a < 0)  Phi(a),  mass, loc, scale    loc + scale * ndtri(Phi(a) + u mass)
+//   5 truncnorm (a >= 0) Phi(-b), mass, loc, scale    loc - scale * ndtri(Phi(-b) + (1-u) mass)
+//   6 lognorm   loc, scale                      exp(loc + scale * ndtri(u))
+//   7 weibull   1/c, scale, loc                 loc + scale * (-log1p(-u))^(1/c)
+struct ColScale {
+  const double *lb, *span;
+  const int32_t *code;  // nullptr: every column uniform
+  const double *par;    // [D][4]
+};
+
+__device__ __forceinline__ double dist_transform(double u, int code, const double *__restrict__ p) {
+  switch (code) {
+    case 1: {
+      const double c = p[2];
+      const double t = (u < c) ? sqrt(__dmul_rn(c, u)) : __dsub_rn(1.0, sqrt(__dmul_rn(__dsub_rn(1.0, c), __dsub_rn(1.0, u))));
+      return __dadd_rn(__dmul_rn(t, p[1]), p[0]);
+    }
+    case 2: return exp(__dadd_rn(p[0], __dmul_rn(u, p[1])));
+    case 3: return __dadd_rn(__dmul_rn(normcdfinv(u), p[1]), p[0]);
+    case 4: return __dadd_rn(__dmul_rn(normcdfinv(__dadd_rn(p[0], __dmul_rn(u, p[1]))), p[3]), p[2]);
+    case 5: return __dadd_rn(__dmul_rn(-normcdfinv(__dadd_rn(p[0], __dmul_rn(__dsub_rn(1.0, u), p[1]))), p[3]), p[2]);
+    case 6: return exp(__dadd_rn(__dmul_rn(normcdfinv(u), p[1]), p[0]));
+    case 7: return __dadd_rn(__dmul_rn(pow(-log1p(-u), p[0]), p[1]), p[2]);
+    default: return __dadd_rn(__dmul_rn(u, p[1]), p[0]);
+  }
+}
+
+__device__ __forceinline__ double scale_col(uint32_t x, int col, const ColScale &cs) {
+  if (cs.code == nullptr) return scale_value(x, cs.span[col], cs.lb[col]);
+  return dist_transform((double)x * kTwoPowMinus30, cs.code[col], cs.par + 4 * (size_t)col);
+}
+
 // Does slot s take column (with group g) from B?  sample/sobol.py:149-186
 __device__ __forceinline__ bool slot_uses_b(int s, int g, int Dg, int step, int second_order) {
   const int k1 = s - 1;
@@ -53,12 +92,11 @@ __device__ __forceinline__ bool slot_uses_b(int s, int g, int Dg, int step, int 
 // ------------------------------------------------------------------------------------------
 // Register path
 // ------------------------------------------------------------------------------------------
-template <bool GROUPED>
+template <bool GROUPED, bool DISTS>
 __global__ void __launch_bounds__(256)
 saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                     uint64_t first_index, uint64_t n, int D, int Dg,
-                    const int32_t *__restrict__ gcol, int step, int second_order,
-                    const double *__restrict__ lb, const double *__restrict__ span,
+                    const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
                     double *__restrict__ out, int rows_per_warp) {
   const int lane = threadIdx.x & 31;
   const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -85,7 +123,13 @@ saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
     const int j1 = j0 + 1;
     const int g0 = GROUPED ? gcol[j0] : j0;
     const int g1 = GROUPED ? gcol[j1] : j1;
-    const double lb0 = lb[j0], lb1 = lb[j1], sp0 = span[j0], sp1 = span[j1];
+    double lb0 = 0.0, lb1 = 0.0, sp0 = 0.0, sp1 = 0.0;
+    if (!DISTS) {
+      lb0 = cs.lb[j0];
+      lb1 = cs.lb[j1];
+      sp0 = cs.span[j0];
+      sp1 = cs.span[j1];
+    }
     const uint32_t *va0 = sv + (size_t)j0 * SA_SOBOL_BITS;
     const uint32_t *va1 = sv + (size_t)j1 * SA_SOBOL_BITS;
     const uint32_t *vb0 = sv + (size_t)(D + j0) * SA_SOBOL_BITS;
@@ -97,10 +141,10 @@ saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
     uint32_t xb1 = sobol_point(sv, shift ? shift[D + j1] : 0u, D + j1, k);
 
     for (uint64_t r = r0; r < r1; ++r) {
-      const double a0 = scale_value(xa0, sp0, lb0);
-      const double a1 = scale_value(xa1, sp1, lb1);
-      const double b0 = scale_value(xb0, sp0, lb0);
-      const double b1 = scale_value(xb1, sp1, lb1);
+      const double a0 = DISTS ? scale_col(xa0, j0, cs) : scale_value(xa0, sp0, lb0);
+      const double a1 = DISTS ? scale_col(xa1, j1, cs) : scale_value(xa1, sp1, lb1);
+      const double b0 = DISTS ? scale_col(xb0, j0, cs) : scale_value(xb0, sp0, lb0);
+      const double b1 = DISTS ? scale_col(xb1, j1, cs) : scale_value(xb1, sp1, lb1);
       double *row = out + (r * (uint64_t)step) * (uint64_t)D + j0;
 #pragma unroll 4
       for (int s = sub; s < step; s += nsub) {
@@ -128,8 +172,7 @@ saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
 // Stage the scaled A/B values of base rows [base, base+nv) in shared memory: sa/sb [BR][D].
 __device__ __forceinline__ void stage_rows(const uint32_t *__restrict__ sv,
                                            const uint32_t *__restrict__ shift, uint64_t k0, int nv,
-                                           int D, const double *__restrict__ lb,
-                                           const double *__restrict__ span, double *sa, double *sb) {
+                                           int D, const ColScale &cs, double *sa, double *sb) {
   const int dims = 2 * D;
   int nseg = blockDim.x / dims;
   if (nseg < 1) nseg = 1;
@@ -143,12 +186,11 @@ __device__ __forceinline__ void stage_rows(const uint32_t *__restrict__ sv,
     if (rs >= re) continue;
     const int col = (d < D) ? d : d - D;
     double *dst = (d < D) ? sa : sb;
-    const double l = lb[col], sp = span[col];
     const uint32_t *v = sv + (size_t)d * SA_SOBOL_BITS;
     uint64_t k = k0 + rs;
     uint32_t x = sobol_point(sv, shift ? shift[d] : 0u, d, k);
     for (int r = rs; r < re; ++r) {
-      dst[(size_t)r * D + col] = scale_value(x, sp, l);
+      dst[(size_t)r * D + col] = scale_col(x, col, cs);
       ++k;
       const int c = __ffsll((long long)k) - 1;
       if (c < SA_SOBOL_BITS) x ^= __ldg(v + c);
@@ -160,8 +202,7 @@ template <bool GROUPED>
 __global__ void __launch_bounds__(256)
 saltelli_generic_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                         uint64_t first_index, uint64_t n, int D, int Dg,
-                        const int32_t *__restrict__ gcol, int step, int second_order,
-                        const double *__restrict__ lb, const double *__restrict__ span,
+                        const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
                         double *__restrict__ out, int BR, uint32_t magic_rowlen, uint32_t magic_D) {
   extern __shared__ double smem[];
   double *sa = smem;
@@ -171,7 +212,7 @@ saltelli_generic_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restr
   for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const uint64_t base = chunk * (uint64_t)BR;
     const int nv = (int)((n - base < (uint64_t)BR) ? (n - base) : BR);
-    stage_rows(sv, shift, first_index + base, nv, D, lb, span, sa, sb);
+    stage_rows(sv, shift, first_index + base, nv, D, cs, sa, sb);
     __syncthreads();
     const uint32_t total = (uint32_t)nv * rowlen;
     double *dst = out + base * (uint64_t)rowlen;
@@ -262,8 +303,7 @@ template <bool GROUPED>
 __global__ void __launch_bounds__(256)
 saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                        uint64_t first_index, uint64_t n, int D, int Dg,
-                       const int32_t *__restrict__ gcol, int step, int second_order,
-                       const double *__restrict__ lb, const double *__restrict__ span,
+                       const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
                        const double *__restrict__ a, const double *__restrict__ delta,
                        const double *__restrict__ alpha, double *__restrict__ Y, int32_t *flag,
                        int BR) {
@@ -277,7 +317,7 @@ saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restri
   for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const uint64_t base = chunk * (uint64_t)BR;
     const int nv = (int)((n - base < (uint64_t)BR) ? (n - base) : BR);
-    stage_rows(sv, shift, first_index + base, nv, D, lb, span, sa, sb);
+    stage_rows(sv, shift, first_index + base, nv, D, cs, sa, sb);
     __syncthreads();
     for (int e = threadIdx.x; e < nv * D; e += blockDim.x) {
       const int j = e % D;
@@ -311,8 +351,7 @@ template <bool GROUPED>
 __global__ void __launch_bounds__(256)
 saltelli_eval_ishigami_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                               uint64_t first_index, uint64_t n, int Dg,
-                              const int32_t *__restrict__ gcol, int step, int second_order,
-                              const double *__restrict__ lb, const double *__restrict__ span,
+                              const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
                               double A, double B, double *__restrict__ Y) {
   // one thread per base row: 6 Sobol' values, `step` outputs
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -321,8 +360,8 @@ saltelli_eval_ishigami_kernel(const uint32_t *__restrict__ sv, const uint32_t *_
     int g[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      xa[j] = scale_value(sobol_point(sv, shift ? shift[j] : 0u, j, first_index + i), span[j], lb[j]);
-      xb[j] = scale_value(sobol_point(sv, shift ? shift[3 + j] : 0u, 3 + j, first_index + i), span[j], lb[j]);
+      xa[j] = scale_col(sobol_point(sv, shift ? shift[j] : 0u, j, first_index + i), j, cs);
+      xb[j] = scale_col(sobol_point(sv, shift ? shift[3 + j] : 0u, 3 + j, first_index + i), j, cs);
       g[j] = GROUPED ? gcol[j] : j;
     }
     for (int s = 0; s < step; ++s) {
@@ -342,8 +381,10 @@ static bool reg_path_ok(int D) {
 
 static int check_sample_args(const char *fn, const uint32_t *d_sv, uint64_t first_index, uint64_t n,
                              int D, int Dg, const int32_t *gcol, const double *lb, const double *span,
-                             const void *out) {
-  SA_REQUIRE(d_sv && lb && span && out, SA_ERR_ARG, "%s: null pointer", fn);
+                             const int32_t *code, const double *par, const void *out) {
+  SA_REQUIRE(d_sv && out, SA_ERR_ARG, "%s: null pointer", fn);
+  SA_REQUIRE((code && par) || (!code && lb && span), SA_ERR_ARG,
+             "%s: need either lb/span or dist_code/dist_par", fn);
   SA_REQUIRE(D >= 1 && Dg >= 1 && Dg <= D, SA_ERR_ARG, "%s: bad D=%d Dg=%d", fn, D, Dg);
   SA_REQUIRE(gcol != nullptr || Dg == D, SA_ERR_ARG, "%s: Dg != D needs group_of_col", fn);
   SA_REQUIRE(2 * (int64_t)D <= SA_SOBOL_MAXDIM, SA_ERR_RANGE, "%s: 2*D=%d exceeds %d Sobol' dimensions",
@@ -361,9 +402,11 @@ using namespace sa;
 extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                                       uint64_t first_index, uint64_t n, int D, int Dg,
                                       const int32_t *d_group_of_col, int second_order,
-                                      const double *d_lb, const double *d_span, double *d_out) {
+                                      const double *d_lb, const double *d_span, const int32_t *d_dist_code,
+                                      const double *d_dist_par, double *d_out) {
   int rc = check_sample_args("sa_saltelli_sample_f64", d_sv, first_index, n, D, Dg, d_group_of_col, d_lb,
-                             d_span, d_out);
+                             d_span, d_dist_code, d_dist_par, d_out);
+  const ColScale cs{d_lb, d_span, d_dist_code, d_dist_par};
   if (rc) return rc;
   if (n == 0) return SA_OK;
   SA_REQUIRE(((uintptr_t)d_out & 15) == 0, SA_ERR_ARG, "sa_saltelli_sample_f64: d_out not 16-byte aligned");
@@ -379,14 +422,10 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     const uint64_t warps = ceil_div_u64(n, rpw);
     const uint64_t blocks = ceil_div_u64(warps, 8);
     SA_REQUIRE(blocks < (1ull << 31), SA_ERR_UNSUPPORTED, "sa_saltelli_sample_f64: grid too large");
-    if (grouped)
-      saltelli_reg_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg,
-                                                                 d_group_of_col, step, second_order, d_lb,
-                                                                 d_span, d_out, (int)rpw);
-    else
-      saltelli_reg_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg,
-                                                                  nullptr, step, second_order, d_lb, d_span,
-                                                                  d_out, (int)rpw);
+    auto kern = grouped ? (d_dist_code ? saltelli_reg_kernel<true, true> : saltelli_reg_kernel<true, false>)
+                        : (d_dist_code ? saltelli_reg_kernel<false, true> : saltelli_reg_kernel<false, false>);
+    kern<<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
+                                          second_order, cs, d_out, (int)rpw);
   } else {
     const size_t row_bytes = 2 * (size_t)D * sizeof(double);
     SA_REQUIRE(row_bytes <= 200 * 1024, SA_ERR_UNSUPPORTED,
@@ -406,7 +445,7 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     auto kern = grouped ? saltelli_generic_kernel<true> : saltelli_generic_kernel<false>;
     if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, 256, smem, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
-                                             second_order, d_lb, d_span, d_out, BR, m_rowlen, m_D);
+                                             second_order, cs, d_out, BR, m_rowlen, m_D);
   }
   note_launches(1);
   SA_LAUNCH_CHECK();
@@ -454,11 +493,13 @@ extern "C" int sa_eval_sobol_g_f64(void *stream, const double *d_X, uint64_t row
 extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                                             uint64_t first_index, uint64_t n, int D, int Dg,
                                             const int32_t *d_group_of_col, int second_order,
-                                            const double *d_lb, const double *d_span, const double *d_a,
-                                            const double *d_delta, const double *d_alpha, double *d_Y,
-                                            int32_t *d_flag) {
+                                            const double *d_lb, const double *d_span,
+                                            const int32_t *d_dist_code, const double *d_dist_par,
+                                            const double *d_a, const double *d_delta, const double *d_alpha,
+                                            double *d_Y, int32_t *d_flag) {
   int rc = check_sample_args("sa_saltelli_eval_sobol_g_f64", d_sv, first_index, n, D, Dg, d_group_of_col,
-                             d_lb, d_span, d_Y);
+                             d_lb, d_span, d_dist_code, d_dist_par, d_Y);
+  const ColScale cs{d_lb, d_span, d_dist_code, d_dist_par};
   if (rc) return rc;
   SA_REQUIRE(d_a != nullptr, SA_ERR_ARG, "sa_saltelli_eval_sobol_g_f64: null a");
   if (n == 0) return SA_OK;
@@ -475,8 +516,8 @@ extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, 
   auto kern = d_group_of_col ? saltelli_eval_g_kernel<true> : saltelli_eval_g_kernel<false>;
   if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, D, Dg,
-                                                             d_group_of_col, step, second_order, d_lb, d_span,
-                                                             d_a, d_delta, d_alpha, d_Y, d_flag, BR);
+                                                             d_group_of_col, step, second_order, cs, d_a,
+                                                             d_delta, d_alpha, d_Y, d_flag, BR);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -485,10 +526,12 @@ extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, 
 extern "C" int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
                                              uint64_t first_index, uint64_t n, int Dg,
                                              const int32_t *d_group_of_col, int second_order,
-                                             const double *d_lb, const double *d_span, double A, double B,
-                                             double *d_Y) {
+                                             const double *d_lb, const double *d_span,
+                                             const int32_t *d_dist_code, const double *d_dist_par, double A,
+                                             double B, double *d_Y) {
   int rc = check_sample_args("sa_saltelli_eval_ishigami_f64", d_sv, first_index, n, 3, Dg, d_group_of_col,
-                             d_lb, d_span, d_Y);
+                             d_lb, d_span, d_dist_code, d_dist_par, d_Y);
+  const ColScale cs{d_lb, d_span, d_dist_code, d_dist_par};
   if (rc) return rc;
   if (n == 0) return SA_OK;
   const int step = second_order ? 2 * Dg + 2 : Dg + 2;
@@ -496,10 +539,10 @@ extern "C" int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv,
   if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
   if (d_group_of_col)
     saltelli_eval_ishigami_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        d_sv, d_shift, first_index, n, Dg, d_group_of_col, step, second_order, d_lb, d_span, A, B, d_Y);
+        d_sv, d_shift, first_index, n, Dg, d_group_of_col, step, second_order, cs, A, B, d_Y);
   else
     saltelli_eval_ishigami_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        d_sv, d_shift, first_index, n, Dg, nullptr, step, second_order, d_lb, d_span, A, B, d_Y);
+        d_sv, d_shift, first_index, n, Dg, nullptr, step, second_order, cs, A, B, d_Y);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

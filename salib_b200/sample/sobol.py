@@ -67,15 +67,114 @@ def _scramble_state(dims: int, scramble: bool, seed):
 
 def _uniform_bounds(problem: Dict):
     """lower bounds and spans as float64, validated like util/__init__.py:37-43."""
-    if problem.get("dists") is not None:
-        raise NotImplementedError(
-            "salib_b200: non-uniform `dists` scaling (util/__init__.py:126-289) is not on the device path yet")
     lower, upper = _check_bounds(problem["bounds"])
     lower = np.ascontiguousarray(lower, dtype=np.float64)
     upper = np.ascontiguousarray(upper, dtype=np.float64)
     if np.any(lower >= upper):
         raise ValueError("Bounds are not legal (upper bound must be greater than lower bound)")
     return lower, np.ascontiguousarray(upper - lower)
+
+
+_VALID_DISTS = ["unif", "triang", "norm", "truncnorm", "lognorm", "logunif", "weibull"]
+
+
+def _dist_tables(bounds, dists, D):
+    """(codes int32 [D], params float64 [D, 4]) for the device inverse CDFs.
+
+    Parameter checks, messages and the deprecated two-value triangular format follow
+    ``_nonuniform_scale_samples`` (util/__init__.py:126-289) case by case."""
+    from scipy.stats import norm
+
+    if D != len(dists):
+        msg = "Mismatch in number of parameters and distributions.\n"
+        msg += "Num parameters: {}".format(D)
+        msg += "Num distributions: {}".format(len(dists))
+        raise ValueError(msg)
+    code = np.zeros(D, dtype=np.int32)
+    par = np.zeros((D, 4), dtype=np.float64)
+    for i in range(D):
+        b = bounds[i]
+        b1, b2 = b[0], b[1]
+        if dists[i] == "triang":
+            if len(b) == 3:
+                loc_start, b1, b2 = b[0], b[1], b[2]
+            elif len(b) == 2:
+                warnings.warn(
+                    "Two-value format for triangular distributions detected.\n"
+                    "To remove this message, specify the distribution start, "
+                    "end, and peak (three values) "
+                    "instead of the current two-value format "
+                    "(distribution end and peak, with start assumed to be 0)\n"
+                    "The two-value format will be deprecated in SALib v1.5.1",
+                    DeprecationWarning, stacklevel=4)
+                loc_start, b1, b2 = 0, b[0], b[1]
+            else:
+                raise ValueError("Unknown triangular distribution specification. Check problem specification.")
+            if b1 < 0 or b2 < 0 or b2 >= 1 or loc_start > b1:
+                raise ValueError(
+                    """Triangular distribution bound error: Scale must be
+                    greater than zero; peak on interval [0,1], triangular
+                    start value must be smaller than end value""")
+            code[i], par[i, :3] = 1, (loc_start, b1 - loc_start, b2)
+        elif dists[i] == "unif":
+            if b1 >= b2:
+                raise ValueError(
+                    """Uniform distribution: lower bound
+                    must be less than upper bound""")
+            code[i], par[i, :2] = 0, (b1, b2 - b1)
+        elif dists[i] == "logunif":
+            with np.errstate(all="ignore"):
+                la, lb_ = np.log(np.float64(b1)), np.log(np.float64(b2))
+            ok = 0 < b1 < b2
+            code[i], par[i, :2] = 2, ((la, lb_ - la) if ok else (np.nan, np.nan))  # scipy returns nan
+        elif dists[i] == "norm":
+            if b2 <= 0:
+                raise ValueError("""Normal distribution: stdev must be > 0""")
+            code[i], par[i, :2] = 3, (b1, b2)
+        elif dists[i] == "truncnorm":
+            b3, b4 = b[2], b[3]
+            if b4 <= 0:
+                raise ValueError(
+                    """Truncated normal distribution: stdev must
+                    be > 0""")
+            if b1 >= b2:
+                raise ValueError(
+                    """Truncated normal distribution: lower bound
+                    must be less than upper bound""")
+            lo, hi = (b1 - b3) / b4, (b2 - b3) / b4
+            # mass of the standard normal on [lo, hi], from the tail that keeps precision
+            mass = norm.cdf(hi) - norm.cdf(lo) if lo < 0 else norm.sf(lo) - norm.sf(hi)
+            if lo < 0:
+                code[i], par[i] = 4, (norm.cdf(lo), mass, b3, b4)
+            else:
+                code[i], par[i] = 5, (norm.cdf(-hi), mass, b3, b4)
+        elif dists[i] == "lognorm":
+            if b2 <= 0:
+                raise ValueError("""Lognormal distribution: stdev must be > 0""")
+            code[i], par[i, :2] = 6, (b1, b2)
+        elif dists[i] == "weibull":
+            if len(b) == 3:
+                shape, scale, loc_start = b[0], b[1], b[2]
+            elif len(b) == 2:
+                shape, scale, loc_start = b[0], b[1], 0
+            else:
+                raise ValueError("Unknown Weibull distribution specification. Check problem specification.")
+            if shape <= 0 or scale <= 0:
+                raise ValueError("""Weibull distribution: shape and scale must be > 0""")
+            code[i], par[i, :3] = 7, (1.0 / shape, scale, loc_start)
+        else:
+            raise ValueError("Distributions: choose one of %s" % ", ".join(_VALID_DISTS))
+    return code, par
+
+
+def _scaling(problem: Dict):
+    """(lower, span, dist_code, dist_par); the last two are None for plain uniform bounds."""
+    dists = problem.get("dists")
+    if dists is None:
+        lower, span = _uniform_bounds(problem)
+        return lower, span, None, None
+    code, par = _dist_tables(problem["bounds"], dists, problem["num_vars"])
+    return None, None, code, par
 
 
 class SamplePlan:
@@ -86,14 +185,16 @@ class SamplePlan:
         gcol, self.Dg = group_columns(problem)
         self.second_order = bool(calc_second_order)
         self.step = 2 * self.Dg + 2 if self.second_order else self.Dg + 2
-        lower, span = _uniform_bounds(problem)
+        lower, span, code, par = _scaling(problem)
         import torch
 
         self.sv = rt.to_device(sv.astype(np.uint32, copy=False).view(np.int32), torch.int32)
         self.shift = None if shift is None else rt.to_device(shift.astype(np.uint32, copy=False).view(np.int32), torch.int32)
         self.gcol = None if gcol is None else rt.to_device(gcol, torch.int32)
-        self.lb = rt.to_device(lower, torch.float64)
-        self.span = rt.to_device(span, torch.float64)
+        self.lb = None if lower is None else rt.to_device(lower, torch.float64)
+        self.span = None if span is None else rt.to_device(span, torch.float64)
+        self.dist_code = None if code is None else rt.to_device(code, torch.int32)
+        self.dist_par = None if par is None else rt.to_device(par, torch.float64)
 
     def generate(self, first_index: int, n: int, out=None):
         """Rows of base indices [first_index, first_index+n) -> [step*n, D] float64 on the device."""
@@ -103,14 +204,14 @@ class SamplePlan:
             out = rt.empty((self.step * n, self.D), torch.float64)
         _lib.call("sa_saltelli_sample_f64", rt.stream_ptr(), rt.ptr(self.sv), rt.ptr(self.shift),
                   int(first_index), int(n), self.D, self.Dg, rt.ptr(self.gcol), int(self.second_order),
-                  rt.ptr(self.lb), rt.ptr(self.span), rt.ptr(out))
+                  rt.ptr(self.lb), rt.ptr(self.span), rt.ptr(self.dist_code), rt.ptr(self.dist_par), rt.ptr(out))
         return out
 
 
 def _plan(problem, N, calc_second_order, scramble, skip_values, seed, caller_depth=3):
     D = problem["num_vars"]
     first = _validate_skip(N, skip_values)
-    _uniform_bounds(problem)  # host-side validation before any device work
+    _scaling(problem)  # host-side validation before any device work
     sv, shift = _scramble_state(2 * D, scramble, seed)
     if first == 0 and N > 0 and (N & (N - 1)) != 0:
         # scipy's own warning on the first draw of an engine (qmc.Sobol._random)

@@ -27,5 +27,5 @@ def evaluate_sample(plan, first_index: int, n: int, A: float = 7.0, B: float = 0
     Y = out if out is not None else rt.empty((plan.step * n,), torch.float64)
     _lib.call("sa_saltelli_eval_ishigami_f64", rt.stream_ptr(), rt.ptr(plan.sv), rt.ptr(plan.shift),
               int(first_index), int(n), plan.Dg, rt.ptr(plan.gcol), int(plan.second_order), rt.ptr(plan.lb),
-              rt.ptr(plan.span), float(A), float(B), rt.ptr(Y))
+              rt.ptr(plan.span), rt.ptr(plan.dist_code), rt.ptr(plan.dist_par), float(A), float(B), rt.ptr(Y))
     return Y

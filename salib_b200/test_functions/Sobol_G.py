@@ -61,7 +61,8 @@ def evaluate_sample(plan, first_index: int, n: int, a=None, delta=None, alpha=No
     flag = rt.zeros((1,), torch.int32)
     _lib.call("sa_saltelli_eval_sobol_g_f64", rt.stream_ptr(), rt.ptr(plan.sv), rt.ptr(plan.shift),
               int(first_index), int(n), plan.D, plan.Dg, rt.ptr(plan.gcol), int(plan.second_order),
-              rt.ptr(plan.lb), rt.ptr(plan.span), rt.ptr(da), rt.ptr(dd), rt.ptr(dl), rt.ptr(Y), rt.ptr(flag))
+              rt.ptr(plan.lb), rt.ptr(plan.span), rt.ptr(plan.dist_code), rt.ptr(plan.dist_par), rt.ptr(da),
+              rt.ptr(dd), rt.ptr(dl), rt.ptr(Y), rt.ptr(flag))
     if check:
         _raise_on_flag(flag)
     return Y

@@ -54,6 +54,32 @@ def test_scrambled_matches_frozen_reference(name):
     assert np.array_equal(X, z["X"])
 
 
+DIST_PROBLEM = {
+    "num_vars": 9, "names": [f"p{i}" for i in range(9)],
+    "dists": ["unif", "triang", "norm", "truncnorm", "lognorm", "logunif", "weibull", "triang", "truncnorm"],
+    "bounds": [[-2.0, 3.5], [1.0, 3.0, 0.25], [0.5, 2.0], [-1.0, 4.0, 1.0, 2.0], [0.1, 0.6], [1e-3, 10.0],
+               [1.7, 2.5, 0.3], [3.0, 0.5], [2.0, 6.0, 1.0, 1.5]],
+}
+
+
+@pytest.mark.parametrize("name", ["dists_n64_c2_skip64", "dists_n32_c1_skip0", "dists_grp_n32_c2_skip32"])
+def test_nonuniform_dists_match_frozen_reference(name):
+    """Device inverse CDFs (triang, norm, truncnorm, lognorm, logunif, weibull) vs scipy's ppf in the
+    reference (util/__init__.py:126-289).  Transcendental: tolerance, not bit-exact; the `unif` column is
+    bit-exact; u = 0 (first unscrambled point) gives -inf / the lower bound exactly like scipy."""
+    from salib_b200.sample import sobol
+
+    z = golden("sample_" + name)
+    p = {k: (list(v) if isinstance(v, list) else v) for k, v in DIST_PROBLEM.items()}
+    if len(z["groups"]):
+        p["groups"] = [str(g) for g in z["groups"]]
+    X = sobol.sample(p, int(z["N"]), calc_second_order=bool(z["c2"]), scramble=False, skip_values=int(z["skip"]))
+    assert X.shape == z["X"].shape
+    assert np.array_equal(X[:, 0], z["X"][:, 0])
+    assert np.array_equal(np.isinf(X), np.isinf(z["X"]))
+    np.testing.assert_allclose(X, z["X"], rtol=1e-11, atol=1e-13)
+
+
 def test_reference_golden_saltelli_file():
     """reference tests/data/model_input.txt (8192 x 3, %.8e) == saltelli.sample(Ishigami, 1024, skip 2048)."""
     from salib_b200.sample import saltelli
@@ -137,4 +163,4 @@ def test_errors():
     with pytest.raises(ValueError):
         sobol.sample(gprob(2, bounds=[[0, 1], [3, 3]]), 8, scramble=False)
     L = _lib.lib()
-    assert L.sa_saltelli_sample_f64(None, None, None, 0, 8, 2, 2, None, 1, None, None, None) == -1
+    assert L.sa_saltelli_sample_f64(None, None, None, 0, 8, 2, 2, None, 1, None, None, None, None, None) == -1

@@ -89,6 +89,29 @@ def test_sample_validation_matches_reference():
         sm.sample(p, 2 ** 30, scramble=False, skip_values=2)
 
 
+def test_dists_validation_matches_reference():
+    # reference util/__init__.py:160-289 and tests/test_util.py (illegal distribution parameters)
+    from salib_b200.sample.sobol import _dist_tables
+
+    def tab(dist, bound):
+        return _dist_tables([bound], [dist], 1)
+
+    for dist, bound in [("unif", [1, 1]), ("triang", [1, 3, 1.0]), ("triang", [3, 1, 0.5]), ("triang", [1, 2, 3, 4]),
+                        ("norm", [0, 0]), ("truncnorm", [0, 1, 0, 0]), ("truncnorm", [1, 0, 0, 1]),
+                        ("lognorm", [0, -1]), ("weibull", [0, 1]), ("weibull", [1, 1, 1, 1]), ("beta", [0, 1])]:
+        with pytest.raises(ValueError):
+            tab(dist, bound)
+    with pytest.raises(ValueError, match="Mismatch in number"):
+        _dist_tables([[0, 1]], ["unif", "unif"], 1)
+    with pytest.warns(DeprecationWarning, match="Two-value format"):
+        code, par = tab("triang", [3.0, 0.5])
+    assert code[0] == 1 and par[0, :3].tolist() == [0.0, 3.0, 0.5]
+    code, par = tab("truncnorm", [2.0, 6.0, 1.0, 1.5])   # lower bound right of the mean: right-tail form
+    assert code[0] == 5
+    code, par = tab("weibull", [2.0, 3.0])
+    assert code[0] == 7 and par[0, :3].tolist() == [0.5, 3.0, 0.0]
+
+
 def test_saltelli_validation_matches_reference():
     from salib_b200.sample import saltelli
 
