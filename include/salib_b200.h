@@ -119,9 +119,11 @@ int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double
 int sa_row_stride(int Dg, int second_order);
 /* Replaces (Y - mean)/std and separate_output_values (analyze/sobol.py:141,267-279):
  * d_Y [N*step] reference order [A, AB_0.., (BA_0..,) B] -> d_Yn [N*stride (+8 doubles slack)]
- * in analysis layout; if d_Yt != NULL also writes the column-major copy d_Yt[col][Npad],
- * Npad = sa_pad_rows(N): cols A, B, AB_0..AB_{Dg-1} when second_order == 0 (first-order kernel),
- * cols A, B only when second_order != 0 (scalar sums of the tile kernel).                    */
+ * in analysis layout; if d_Yt != NULL also writes the auxiliary array the fast kernels read:
+ *   second_order != 0: column-major copy of A and B, d_Yt[2][Npad], Npad = sa_pad_rows(N);
+ *   second_order == 0: per-row feature matrix d_Yt[N][sa_feature_count(Dg)] =
+ *     { A, B, A^2, B^2, A*B, B*(AB_j - A) (j < Dg), (A - AB_j)^2 (j < Dg) } (+ pad to an even count).  */
+int sa_feature_count(int Dg);
 uint64_t sa_pad_rows(uint64_t N);
 int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
                      const double *d_stats, double *d_Yn, double *d_Yt);
@@ -177,6 +179,8 @@ int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, 
  * MEASURED_PEAKS.json lacks.  fp64: flop = 32 * iters * (*h_threads).                */
 long long sa_launch_count(int reset);
 int sa_microbench_fp64(void *stream, int iters, double *d_out, uint64_t *h_threads);
+/* 8x8 register outer-product DFMA mix of the tile kernel, no memory: flop = 128 * iters * (*h_threads). */
+int sa_microbench_fp64_outer(void *stream, int iters, double *d_out, uint64_t *h_threads);
 int sa_microbench_l2_read(void *stream, const void *d_buf, uint64_t bytes, int reps, double *d_out);
 
 #ifdef __cplusplus

@@ -28,6 +28,7 @@ SIGNATURES = {
     "sa_moments_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _sz]),
     "sa_row_stride": (C.c_int, [_i32, _i32]),
     "sa_pad_rows": (_u64, [_u64]),
+    "sa_feature_count": (C.c_int, [_i32]),
     "sa_normalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]),
     "sa_counts_from_indices": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _u64, _vp, _vp]),
     "sa_counts_philox": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _vp, _vp]),
@@ -37,6 +38,7 @@ SIGNATURES = {
     "sa_sobol_conf_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp]),
     "sa_launch_count": (C.c_longlong, [_i32]),
     "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "sa_microbench_fp64_outer": (C.c_int, [_vp, _i32, _vp, _vp]),
     "sa_microbench_l2_read": (C.c_int, [_vp, _vp, _u64, _i32, _vp]),
 }
 

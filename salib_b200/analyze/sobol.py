@@ -112,7 +112,8 @@ class SobolAnalyzer:
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[algo]
-        kind = self.algo or (4 if (self.c2 and Dg <= 64) else (1 if self.c2 else 3))
+        # tile kernel: Dg <= 64; first-order GEMV kernel: its 4 x 32 feature rows must fit shared memory
+        kind = self.algo or (4 if (self.c2 and Dg <= 64) else (3 if (not self.c2 and Dg <= 90) else 1))
         self.kind = kind
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
         L = _lib.lib()
@@ -135,7 +136,8 @@ class SobolAnalyzer:
         if need_rows:
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
         if need_cols:
-            self.Yt = rt.empty(((2 if self.c2 else self.Dg + 2) * self.Npad,), torch.float64)
+            n_aux = 2 * self.Npad if self.c2 else self.N * int(L.sa_feature_count(self.Dg))
+            self.Yt = rt.empty((n_aux,), torch.float64)
         _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
                   rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
 
@@ -145,9 +147,9 @@ class SobolAnalyzer:
         max_split = max(1, min(4096, self.N // 32))
         if self.kind == 4:       # one warp per resample, 8 per block, one block per SM
             blocks = -(-count // 8)
-        elif self.kind == 3:    # 4 resamples per warp, 8 warps per block, ~2 blocks per SM
-            blocks = -(-count // 32) * -(-self.Dg // 8)
-            return max(1, min(max_split, (2 * self.sms) // blocks))
+        elif self.kind == 3:    # 256 resamples per block, up to ~4 resident blocks per SM
+            blocks = -(-count // 256) * -(-self.nacc // 32)
+            return max(1, min(max_split, (4 * self.sms) // blocks))
         else:                   # one block per resample
             blocks = count
         return max(1, min(max_split, self.sms // blocks if blocks <= self.sms else 1))
@@ -177,7 +179,7 @@ class SobolAnalyzer:
         """Resample batches [c0, c1): bounded by the multiplicity buffer; for the one-warp-per-resample
         kernel sized in whole waves (8 * SMs) with the remainder as its own, row-split, launch."""
         cap = max(1, MAX_COUNT_BYTES // self.Npad)
-        wave = 8 * self.sms if self.kind == 4 else 32 * self.sms
+        wave = 8 * self.sms if self.kind == 4 else 256 * self.sms
         c = lo
         while c < hi:
             left = hi - c

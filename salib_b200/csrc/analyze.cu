@@ -13,10 +13,12 @@
 //     sum_i w*BA_j*AB_k live in registers as one 8x8 (j,k) tile per lane, i.e. a register-tiled
 //     FP64 rank-1 update per row (16 operand doubles feed 64 DFMAs); rows are staged through shared
 //     memory by cp.async.bulk.  FP64-pipe / shared-memory-bandwidth bound.
-//   first-order kernel   (fo_accum_kernel): lanes <-> rows over a column-major copy (coalesced),
-//     C resamples per warp share each row read.  L2-bandwidth bound.
+//   first-order kernel   (fo_gemv_kernel): all first/total-order sums are linear in w, so they are a
+//     skinny GEMM w[R x N] * F[N x (5+2D)] over a per-row feature matrix; lanes <-> resamples.
 //   generic kernel       (accum_generic_kernel): any shape, one accumulator per thread; fallback
 //     for Dg > 64 with second order and an independent cross-check of the two fast kernels.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sa {
@@ -30,7 +32,14 @@ __host__ __device__ inline int part_len(int Dg) { return (round_up8(Dg) >> 3) * 
 __host__ __device__ inline int row_stride(int Dg, int second_order) {
   return (second_order ? 2 : 1) * part_len(Dg) + 2;
 }
-__host__ __device__ inline uint64_t pad_rows(uint64_t N) { return (N + 127) & ~(uint64_t)127; }
+// Row pitch of the multiplicity matrix w[resample][row] (bytes).  A multiple of 128, but never of 4096:
+// the first-order kernel reads 32 bytes of 32 different resamples at once, and a power-of-two pitch
+// would put all of them into the same HBM channel/bank.
+__host__ __device__ inline uint64_t pad_rows(uint64_t N) {
+  uint64_t p = (N + 127) & ~(uint64_t)127;
+  if ((p & 4095) == 0) p += 128;
+  return p;
+}
 // Position of logical column j inside the AB / BA part of an analysis-layout row.
 __host__ __device__ inline int col_pos(int j) { return (j >> 3) * kBlockPitch + (j & 7); }
 __host__ __device__ inline int pair_index(int j, int k, int Dg) {
@@ -274,10 +283,10 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
 // fed by 16 operand doubles), the other 4 diagonal triangles (112 pairs) are spread 4 per lane.
 // First/total-order sums ride along (2 columns per lane).  Rows with multiplicity 0 are skipped.
 //
-// Data path: tiles of 32 contiguous rows (one cp.async.bulk each, 34 KB at Dg = 64) go through a
-// 4-stage shared-memory ring with one mbarrier per stage; the 8 warps of a block (8 resamples)
+// Data path: tiles of 32 contiguous rows (one cp.async.bulk each, 41 KB at Dg = 64) go through a
+// 5-stage shared-memory ring with one mbarrier per stage; the 8 warps of a block (8 resamples)
 // consume the same tiles at their own pace and the last warp to leave a stage re-arms it and issues
-// the copy of tile t+4 -- no block-wide barrier in the loop.  The analysis layout puts the 8-column
+// the copy of tile t+5 -- no block-wide barrier in the loop.  The analysis layout puts the 8-column
 // blocks at an 80-byte pitch (col_pos), so the chunks that different lanes read with the SAME
 // instruction offset fall into different bank groups: all operand loads are conflict-free LDS.128
 // from one base register per operand set.
@@ -288,7 +297,6 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
 // ncu history of this kernel is in profiles/ (L1 version: 118 wavefronts/row, FP64 pipe 38 %).
 constexpr int kS2Warps = 8;
 constexpr int kTileRows = 32;
-constexpr int kStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -398,6 +406,7 @@ scalar_sums_kernel(const double *__restrict__ Yt, uint64_t Npad, uint64_t N, con
   }
 }
 
+template <int kStages, bool W1FAST>
 __global__ void __launch_bounds__(kS2Warps * 32, 1)
 s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
                      const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
@@ -518,7 +527,8 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   };
   // one row: rank-1 update with (P, Qc); prefetch the next row into (P, Qn); diagonal leftovers and
   // first/total order ("side work") are loaded after the second chunk and consumed at the end
-  auto do_row = [&](uint32_t row, uint32_t nrow, double wv, double(&Qc)[8], double(&Qn)[8]) {
+  auto do_row = [&](uint32_t row, uint32_t nrow, double wv, double(&Qc)[8], double(&Qn)[8], auto scale_tag) {
+    constexpr bool SCALE = decltype(scale_tag)::value;  // false: weight 1, no multiplications by it
     double ya = 0.0, yb = 0.0, t0, t1;
     double2 xa = make_double2(0.0, 0.0), xb = xa, ab;
 #pragma unroll
@@ -526,7 +536,7 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int a = 2 * q + e;
-        const double wx = wv * P[a];
+        const double wx = SCALE ? wv * P[a] : P[a];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Qc[k], acc[a][k]);
       }
@@ -545,20 +555,29 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
       }
     }
     if (hasB) {  // warp-uniform
-      ya *= wv;
-      yb *= wv;
+      if (SCALE) {
+        ya *= wv;
+        yb *= wv;
+      }
       accB[0] = fma(xa.x, ya, accB[0]);
       accB[1] = fma(xa.y, ya, accB[1]);
       accB[2] = fma(xb.x, yb, accB[2]);
       accB[3] = fma(xb.y, yb, accB[3]);
     }
-    const double wb = wv * ab.y;
+    const double wb = SCALE ? wv * ab.y : ab.y;
     t0 -= ab.x;
     t1 -= ab.x;
     s1_0 = fma(wb, t0, s1_0);
     s1_1 = fma(wb, t1, s1_1);
-    st_0 = fma(wv * t0, t0, st_0);
-    st_1 = fma(wv * t1, t1, st_1);
+    st_0 = fma(SCALE ? wv * t0 : t0, t0, st_0);
+    st_1 = fma(SCALE ? wv * t1 : t1, t1, st_1);
+  };
+  auto row_any = [&](uint32_t row, uint32_t nrow, int hi, double(&Qc)[8], double(&Qn)[8]) {
+    if (W1FAST && hi == 0x3FF00000) {  // multiplicity 1 (58 % of the processed rows)
+      do_row(row, nrow, 1.0, Qc, Qn, std::false_type{});
+    } else {
+      do_row(row, nrow, __hiloint2double(hi, 0), Qc, Qn, std::true_type{});
+    }
   };
 
   for (int t = 0; t < ntiles; ++t) {
@@ -586,19 +605,19 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
       {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
-        const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
+        const int hi = __shfl_sync(kFull, whi, b);
         const uint32_t row = tile + (uint32_t)b * row_bytes;
         const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-        do_row(row, nrow, wv, Q0, Q1);
+        row_any(row, nrow, hi, Q0, Q1);
       }
       if (!mask) break;
       {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1;
-        const double wv = __hiloint2double(__shfl_sync(kFull, whi, b), 0);
+        const int hi = __shfl_sync(kFull, whi, b);
         const uint32_t row = tile + (uint32_t)b * row_bytes;
         const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-        do_row(row, nrow, wv, Q1, Q0);
+        row_any(row, nrow, hi, Q1, Q0);
       }
     }
     // release the stage; the last warp out refills it with tile t + kStages
@@ -651,84 +670,156 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 }
 
 // ------------------------------------------------------------------------------------------
-// first/total-order accumulate: lanes <-> rows (column-major Yt), C resamples per warp
+// first/total-order accumulate: a skinny GEMM  acc[c][q] += w[c][i] * F[i][q]
 // ------------------------------------------------------------------------------------------
+// Every first/total-order sum is linear in the multiplicities: with the per-row features
+//   F[i] = [ A, B, A^2, B^2, A*B,  B*(AB_j - A) (j < Dg),  (A - AB_j)^2 (j < Dg) ]
+// (written once by normalize_features_kernel) the SA_NACC sums of resample c are sum_i w_c[i] * F[i][q],
+// in exactly the order of the psum layout.  Lanes <-> resamples: a warp owns 32 resamples, every lane
+// keeps its NF (<= 32 per grid.z chunk) accumulators in registers, the feature row is warp-uniform
+// (one broadcast load per 16 bytes for 32 resamples) and the only per-lane data is one weight byte per
+// row, read 32 rows at a time.  One DFMA per (resample, row, feature): 5 + 2*Dg flop-pairs instead of
+// the 7 + 8*Dg operations of evaluating the estimator terms per resample.
 constexpr int kFoWarps = 8;
-constexpr int kFoJC = 8;
-constexpr int kFoC = 4;
+constexpr int kFoRows = 32;   // rows per weight fetch (32 bytes per resample)
 
+__host__ __device__ inline int feature_count(int Dg) { return (5 + 2 * Dg + 1) & ~1; }  // padded to even
+
+__global__ void __launch_bounds__(256)
+normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step,
+                          const double *__restrict__ stats, double *__restrict__ F) {
+  const double mean = stats[0], sd = stats[1];
+  const int NF = feature_count(Dg);
+  const uint64_t total = N * (uint64_t)NF;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = idx / (uint64_t)NF;
+    const int q = (int)(idx - i * (uint64_t)NF);
+    const double *row = Y + i * (uint64_t)step;
+    const double a = __ddiv_rn(__dsub_rn(row[0], mean), sd);
+    const double b = __ddiv_rn(__dsub_rn(row[step - 1], mean), sd);
+    double v = 0.0;
+    if (q == 0) v = a;
+    else if (q == 1) v = b;
+    else if (q == 2) v = __dmul_rn(a, a);
+    else if (q == 3) v = __dmul_rn(b, b);
+    else if (q == 4) v = __dmul_rn(a, b);
+    else if (q < 5 + 2 * Dg) {
+      const int j = (q - 5 < Dg) ? q - 5 : q - 5 - Dg;
+      const double ab = __ddiv_rn(__dsub_rn(row[1 + j], mean), sd);
+      if (q - 5 < Dg) v = __dmul_rn(b, __dsub_rn(ab, a));          // B * (AB_j - A)
+      else { const double t = __dsub_rn(a, ab); v = __dmul_rn(t, t); }  // (A - AB_j)^2
+    }
+    F[idx] = v;
+  }
+}
+
+constexpr int kFoStages = 4;
+
+template <int CH>  // accumulators (features) per lane and grid.z slice: 8, 16, 24 or 32
 __global__ void __launch_bounds__(kFoWarps * 32)
-fo_accum_kernel(const double *__restrict__ Yt, uint64_t Npad, uint64_t N, int Dg,
-                const uint8_t *__restrict__ w, uint64_t count, uint64_t rows_per_split,
-                double *__restrict__ psum, int nacc) {
+fo_gemv_kernel(const double *__restrict__ F, int NF, uint64_t N, const uint8_t *__restrict__ w, uint64_t Npad,
+               uint64_t count, uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  // Feature rows are streamed through a shared-memory ring exactly like the tile kernel's rows:
+  // 32-row tiles (contiguous in HBM) by cp.async.bulk, one mbarrier per stage, last warp out refills.
+  extern __shared__ __align__(128) unsigned char smraw[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const uint64_t cbase = ((uint64_t)blockIdx.x * kFoWarps + warp) * kFoC;
-  if (cbase >= count) return;
+  const uint64_t c = ((uint64_t)blockIdx.x * kFoWarps + (threadIdx.x >> 5)) * 32 + lane;
+  const bool live = c < count;
   const int sp = blockIdx.y;
-  const int j0 = blockIdx.z * kFoJC;
+  const int q0 = blockIdx.z * CH;
   const uint64_t row0 = (uint64_t)sp * rows_per_split;
   uint64_t row1 = row0 + rows_per_split;
   if (row1 > N) row1 = N;
-
-  double s1[kFoC][kFoJC], st[kFoC][kFoJC], sc[kFoC][5];
-#pragma unroll
-  for (int c = 0; c < kFoC; ++c) {
-#pragma unroll
-    for (int j = 0; j < kFoJC; ++j) s1[c][j] = st[c][j] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) sc[c][q] = 0.0;
+  const int ntiles = (row1 > row0) ? (int)((row1 - row0 + kFoRows - 1) / kFoRows) : 0;
+  const uint32_t row_bytes = (uint32_t)NF * 8u;
+  const uint32_t stage_bytes = kFoRows * row_bytes;
+  const uint32_t sm_base = smem_u32(smraw);
+  const uint32_t bar_base = sm_base + kFoStages * stage_bytes;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(smraw + kFoStages * stage_bytes + kFoStages * 8);
+  auto issue = [&](int t) {
+    const int s = t % kFoStages;
+    const uint64_t r = row0 + (uint64_t)t * kFoRows;
+    const uint32_t rows = (uint32_t)((row1 - r < (uint64_t)kFoRows) ? (row1 - r) : kFoRows);
+    mbar_arrive_expect_tx(bar_base + 8u * s, rows * row_bytes);
+    bulk_g2s(sm_base + s * stage_bytes, F + r * (uint64_t)NF, rows * row_bytes, bar_base + 8u * s);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFoStages; ++s) {
+      mbar_init(bar_base + 8u * s, 1);
+      cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const double *colA = Yt;
-  const double *colB = Yt + Npad;
-  const double *colAB = Yt + (uint64_t)(2 + j0) * Npad;
-  int nj = Dg - j0;
-  if (nj > kFoJC) nj = kFoJC;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int t = 0; t < kFoStages && t < ntiles; ++t) issue(t);
 
-  for (uint64_t i = row0 + lane; i < row1; i += 32) {
-    const double a = colA[i], b = colB[i];
-    double t[kFoJC];
+  double acc[CH];
 #pragma unroll
-    for (int j = 0; j < kFoJC; ++j) t[j] = (j < nj) ? colAB[(uint64_t)j * Npad + i] - a : 0.0;
+  for (int q = 0; q < CH; ++q) acc[q] = 0.0;
+  const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
+  const double ones = (!w && live) ? 1.0 : 0.0;  // point estimate: weight 1 for every row
+  // this lane's 32 weights of a tile (rows_per_split is a multiple of 32, Npad of 128: in bounds)
+  auto load_w = [&](int t, uint4 &wa, uint4 &wb) {
+    wa = make_uint4(0, 0, 0, 0);
+    wb = wa;
+    if (wrow && t < ntiles) {
+      const uint8_t *p = wrow + row0 + (uint64_t)t * kFoRows;
+      wa = __ldg(reinterpret_cast<const uint4 *>(p));
+      wb = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+    }
+  };
+  uint4 na, nb;
+  load_w(0, na, nb);
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kFoStages;
+    const uint32_t wreg[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+    load_w(t + 1, na, nb);
+    const uint64_t i0 = row0 + (uint64_t)t * kFoRows;
+    const int nrows = (int)((row1 - i0 < (uint64_t)kFoRows) ? (row1 - i0) : kFoRows);
+    while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)(t / kFoStages) & 1u)) {
+    }
+    const uint32_t tile = sm_base + s * stage_bytes + (uint32_t)q0 * 8u;
 #pragma unroll
-    for (int c = 0; c < kFoC; ++c) {
-      if (cbase + c < count) {  // warp-uniform
-        const double wv = w ? (double)w[(cbase + c) * Npad + i] : 1.0;
-        const double wa = wv * a, wb = wv * b;
-        sc[c][0] += wa;
-        sc[c][1] += wb;
-        sc[c][2] = fma(wa, a, sc[c][2]);
-        sc[c][3] = fma(wb, b, sc[c][3]);
-        sc[c][4] = fma(wb, a, sc[c][4]);
+    for (int wi = 0; wi < 8; ++wi) {
 #pragma unroll
-        for (int j = 0; j < kFoJC; ++j) {
-          s1[c][j] = fma(wb, t[j], s1[c][j]);
-          st[c][j] = fma(wv * t[j], t[j], st[c][j]);
+      for (int bb = 0; bb < 4; ++bb) {
+        const int r = 4 * wi + bb;
+        if (r < nrows) {  // uniform; false only in the last tile of a split
+          const uint32_t byte = (wreg[wi] >> (8 * bb)) & 0xffu;
+          // small integer -> double without the conversion pipe: 2^52 + n has n in the low mantissa bits
+          const double wv = w ? (__hiloint2double(0x43300000, (int)byte) - 4503599627370496.0) : ones;
+          const uint32_t f = tile + (uint32_t)r * row_bytes;
+#pragma unroll
+          for (int q = 0; q < CH; q += 2) {
+            if (q0 + q < NF) {  // uniform
+              const double2 v = lds_f64x2(f + 8u * q);  // warp-uniform address: one broadcast
+              acc[q] = fma(wv, v.x, acc[q]);
+              acc[q + 1] = fma(wv, v.y, acc[q + 1]);
+            }
+          }
         }
       }
     }
-  }
-#pragma unroll
-  for (int c = 0; c < kFoC; ++c) {
-    if (cbase + c >= count) continue;
-    double *out = psum + ((uint64_t)sp * count + cbase + c) * (uint64_t)nacc;
-    if (blockIdx.z == 0) {
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const double v = warp_sum(sc[c][q]);
-        if (lane == 0) out[q] = v;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kFoJC; ++j) {
-      const double v1 = warp_sum(s1[c][j]);
-      const double vt = warp_sum(st[c][j]);
-      if (lane == 0 && j < nj) {
-        out[5 + j0 + j] = v1;
-        out[5 + Dg + j0 + j] = vt;
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "r"(smem_u32(cnt + s))
+                   : "memory");
+      if (old == kFoWarps - 1) {
+        cnt[s] = 0;
+        if (t + kFoStages < ntiles) issue(t + kFoStages);
       }
     }
   }
+  if (!live) return;
+  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+#pragma unroll
+  for (int q = 0; q < CH; ++q)
+    if (q0 + q < nacc) out[q0 + q] = acc[q];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -878,6 +969,7 @@ using namespace sa;
 
 extern "C" int sa_row_stride(int Dg, int second_order) { return row_stride(Dg, second_order); }
 extern "C" uint64_t sa_pad_rows(uint64_t N) { return pad_rows(N); }
+extern "C" int sa_feature_count(int Dg) { return feature_count(Dg); }
 extern "C" size_t sa_moments_workspace_bytes(void) { return (size_t)kMomBlocks * 6 * sizeof(double); }
 
 extern "C" int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double *d_stats,
@@ -915,12 +1007,18 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
     note_launches(1);
   }
   if (d_Yt) {
-    SA_REQUIRE(Dg + 2 <= 65535, SA_ERR_UNSUPPORTED, "sa_normalize_f64: too many groups for the column copy");
-    const uint64_t Npad = pad_rows(N);
-    uint64_t bx = ceil_div_u64(Npad, 256);
-    if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)(second_order ? 2 : Dg + 2));
-    normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
+    if (second_order) {  // A and B columns for scalar_sums_kernel
+      const uint64_t Npad = pad_rows(N);
+      uint64_t bx = ceil_div_u64(Npad, 256);
+      if (bx > 4096) bx = 4096;
+      dim3 grid((unsigned)bx, 2u);
+      normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
+    } else {             // feature matrix for fo_gemv_kernel
+      const uint64_t total = N * (uint64_t)feature_count(Dg);
+      uint64_t blocks = ceil_div_u64(total, 256);
+      if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
+      normalize_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, d_stats, d_Yt);
+    }
     note_launches(1);
   }
   SA_LAUNCH_CHECK();
@@ -984,7 +1082,7 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   const int nacc = SA_NACC(Dg, second_order);
   uint64_t rps = ceil_div_u64(N, nsplit);
   rps = (rps + 31) & ~(uint64_t)31;
-  if (algo == 0) algo = second_order ? (Dg <= 64 ? 4 : 1) : 3;
+  if (algo == 0) algo = second_order ? (Dg <= 64 ? 4 : 1) : (Dg <= 90 ? 3 : 1);
   if (algo == 4) {
     SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
     SA_REQUIRE(d_Yn && d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn / d_Yt is null");
@@ -992,21 +1090,31 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
     const uint64_t bx = ceil_div_u64(count, kS2Warps);
     const uint64_t bsc = ceil_div_u64(count, kScC);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
-    const size_t smem = (size_t)kStages * kTileRows * stride * 8 + kStages * 8 + kStages * 4 + 16;
-    SA_CUDA(cudaFuncSetAttribute(s2_accum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // 5 stages of 32 rows (207 KB at Dg = 64).  The weight-1 fast path (no multiplications for 58 % of
+    // the rows) is compiled out: measured no gain, the kernel is bound by shared-memory wavefronts.
+    constexpr int stages = 5;
+    auto kern = s2_accum_smem_kernel<stages, false>;
+    const size_t smem = (size_t)stages * kTileRows * stride * 8 + stages * 8 + stages * 4 + 16;
+    SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     scalar_sums_kernel<<<dim3((unsigned)bsc, (unsigned)nsplit), 256, 0, st>>>(d_Yt, Npad, N, d_w, count, rps, d_psum,
                                                                                nacc);
-    s2_accum_smem_kernel<<<dim3((unsigned)bx, (unsigned)nsplit), kS2Warps * 32, smem, st>>>(
+    kern<<<dim3((unsigned)bx, (unsigned)nsplit), kS2Warps * 32, smem, st>>>(
         d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc);
     note_launches(1);
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
-    SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt is null");
-    const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * kFoC);
-    const int nz = (Dg + kFoJC - 1) / kFoJC;
+    SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt (feature matrix) is null");
+    const int NF = feature_count(Dg);
+    const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * 32);
+    const int ch = nacc <= 8 ? 8 : (nacc <= 16 ? 16 : (nacc <= 24 ? 24 : 32));
+    const int nz = (nacc + ch - 1) / ch;
     SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the first-order kernel");
     dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-    fo_accum_kernel<<<grid, kFoWarps * 32, 0, st>>>(d_Yt, Npad, N, Dg, d_w, count, rps, d_psum, nacc);
+    auto kern = ch == 8 ? fo_gemv_kernel<8> : (ch == 16 ? fo_gemv_kernel<16> : (ch == 24 ? fo_gemv_kernel<24> : fo_gemv_kernel<32>));
+    const size_t smem = (size_t)kFoStages * kFoRows * NF * 8 + kFoStages * 12 + 16;
+    SA_REQUIRE(smem <= 200 * 1024, SA_ERR_UNSUPPORTED, "too many groups for the first-order kernel (Dg = %d)", Dg);
+    SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kFoWarps * 32, smem, st>>>(d_Yt, NF, N, d_w, Npad, count, rps, d_psum, nacc);
   } else if (algo == 1) {
     SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
     SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");

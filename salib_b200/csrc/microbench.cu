@@ -20,6 +20,36 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
   if (s == 123.456) out[0] = s;  // keep the chains alive
 }
 
+// The tile kernel's instruction mix without any memory traffic: an 8x8 register outer-product update
+// (64 DFMA with three distinct register operands + 8 DMUL per step).  Its throughput is the practical
+// ceiling of the register-tiled design (register-file read bandwidth included).
+__global__ void __launch_bounds__(256, 1) fp64_outer_kernel(int iters, double seed, double *__restrict__ out) {
+  double acc[8][8], X[8], Y[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    X[a] = seed + a * 1e-3 + threadIdx.x * 1e-6;
+    Y[a] = seed - a * 1e-3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[a][k] = 0.0;
+  }
+  double w = 1.0 + 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double wx = w * X[a];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[a][k] = fma(wx, Y[k], acc[a][k]);
+    }
+    w += 1e-12;  // keeps the multiplies inside the loop
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[a][k];
+  if (s == 123.456) out[0] = s;
+}
+
 // Every thread block streams the same `bytes` buffer (L2 resident when bytes << 126 MB) `reps` times.
 __global__ void __launch_bounds__(256)
 l2_read_kernel(const double2 *__restrict__ buf, uint64_t n16, int reps, double *__restrict__ out) {
@@ -43,6 +73,17 @@ extern "C" int sa_microbench_fp64(void *stream, int iters, double *d_out, uint64
   SA_REQUIRE(d_out && iters > 0, SA_ERR_ARG, "sa_microbench_fp64: bad arguments");
   const int blocks = sm_count() * 8;
   fp64_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, d_out);
+  if (h_threads) *h_threads = (uint64_t)blocks * 256;
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// 8x8 outer-product mix: flop counted = 2 * 64 * iters * threads (the 8 DMUL per step are overhead, as
+// in the tile kernel's algorithmic count).  One block of 256 threads per SM, like the tile kernel.
+extern "C" int sa_microbench_fp64_outer(void *stream, int iters, double *d_out, uint64_t *h_threads) {
+  SA_REQUIRE(d_out && iters > 0, SA_ERR_ARG, "sa_microbench_fp64_outer: bad arguments");
+  const int blocks = sm_count();
+  fp64_outer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, d_out);
   if (h_threads) *h_threads = (uint64_t)blocks * 256;
   SA_LAUNCH_CHECK();
   return SA_OK;

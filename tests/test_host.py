@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) == declared
     assert _lib.lib().sa_version() >= 100
     assert _lib.lib().sa_row_stride(64, 1) == 162 and _lib.lib().sa_row_stride(3, 0) == 12
-    assert _lib.lib().sa_pad_rows(1000) == 1024
+    assert _lib.lib().sa_pad_rows(1000) == 1024 and _lib.lib().sa_pad_rows(4096) == 4224
 
 
 def test_direction_vectors_match_oracle_and_scipy():
