@@ -75,6 +75,12 @@ int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d
                            const double *d_span, const int32_t *d_dist_code, const double *d_dist_par,
                            double *d_out);
 
+/* Plain Sobol' points first_index .. first_index+n-1 in `dims` dimensions, d_out [n, dims] row-major, values
+ * x * 2^-30.  Replaces sample/sobol_sequence.py:49-91 (`sobol_sequence.sample`, the generator behind
+ * sample/saltelli.py:157 and sample/finite_diff.py).                                              */
+int sa_sobol_points_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                        uint64_t first_index, uint64_t n, int dims, double *d_out);
+
 /* ---- test functions on the path -----------------------------------------------------------
  * sa_eval_ishigami_f64 replaces test_functions/Ishigami.py:55-59, sa_eval_sobol_g_f64 replaces
  * test_functions/Sobol_G.py:66-86 (X -> Y).  d_flag (int32, may be NULL) is OR-ed with 1 if any

@@ -34,7 +34,8 @@ from scipy.stats import norm
 from .. import _lib, _runtime as rt
 from ..util import ResultDict, extract_group_names
 
-__all__ = ["analyze", "to_df", "Si_to_pandas_dict", "CONST_RESULT_MSG"]
+__all__ = ["analyze", "analyze_device", "first_order", "total_order", "second_order", "separate_output_values",
+           "to_df", "Si_to_pandas_dict", "CONST_RESULT_MSG"]
 
 CONST_RESULT_MSG = (
     "Constant values encountered, indicating model evaluations "
@@ -138,6 +139,11 @@ class SobolAnalyzer:
         if need_cols:
             n_aux = 2 * self.Npad if self.c2 else self.N * int(L.sa_feature_count(self.Dg))
             self.Yt = rt.empty((n_aux,), torch.float64)
+        _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
+                  rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
+
+    def load_normalized(self, Yd):
+        """Re-run only the normalise/re-layout step with the current ``self.stats``."""
         _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
                   rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
 
@@ -349,6 +355,58 @@ def analyze(
         for df in S.to_df():
             print(df)
     return S
+
+
+def separate_output_values(Y, D, N, calc_second_order):
+    """(A, B, AB, BA) views of the model output (reference :267-279): Y.reshape(N, step) columns."""
+    step = 2 * D + 2 if calc_second_order else D + 2
+    M = np.asarray(Y).reshape(N, step)
+    return M[:, 0], M[:, step - 1], M[:, 1:1 + D], (M[:, 1 + D:1 + 2 * D] if calc_second_order else None)
+
+
+def _estimates_from_columns(A, ABs, BAs, B):
+    """Run the device estimators on explicit columns (no normalisation): returns the `est` vector of a
+    problem with len(ABs) factors; second order iff BAs is given."""
+    A, B = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
+    c2 = BAs is not None
+    cols = [A] + [np.asarray(x, dtype=np.float64) for x in ABs] + ([np.asarray(x, dtype=np.float64) for x in BAs] if c2 else []) + [B]
+    Y = np.stack(cols, axis=1)
+    N, Dg = Y.shape[0], len(ABs)
+    eng = SobolAnalyzer(Dg, N, c2)
+    Yd = rt.to_device(Y.reshape(-1), torch.float64)
+    eng.load(Yd)                                   # moments give the ptp([A;B]) == 0 test ...
+    eng.stats[0:2] = torch.tensor([0.0, 1.0], dtype=torch.float64, device=eng.stats.device)
+    eng.load_normalized(Yd)                        # ... but the data is used as given: (y - 0) / 1
+    est = eng.point()[0].cpu().numpy()
+    stats = eng.stats.cpu().numpy()
+    if not (stats[4] < stats[5]):
+        warn(CONST_RESULT_MSG)
+    return est
+
+
+def _columnwise(fn, arrays):
+    """The reference calls the estimators on 1-D arrays and on [N, R] stacks of resampled columns."""
+    if np.ndim(arrays[0]) == 1:
+        return np.float64(fn(*arrays))
+    R = np.shape(arrays[0])[1]
+    return np.array([fn(*[np.asarray(a)[:, c] for a in arrays]) for c in range(R)])
+
+
+def first_order(A, AB, B):
+    """mean(B * (AB - A)) / var([A; B]) -- Saltelli et al. 2010 (reference :209-219), on the device."""
+    return _columnwise(lambda a, ab, b: _estimates_from_columns(a, [ab], None, b)[0], (A, AB, B))
+
+
+def total_order(A, AB, B):
+    """0.5 * mean((A - AB)^2) / var([A; B]) (reference :222-232), on the device."""
+    return _columnwise(lambda a, ab, b: _estimates_from_columns(a, [ab], None, b)[1], (A, AB, B))
+
+
+def second_order(A, ABj, ABk, BAj, B):
+    """mean(BAj * ABk - A * B) / var([A; B]) - S1_j - S1_k (reference :235-246), on the device."""
+    def one(a, abj, abk, baj, b):
+        return _estimates_from_columns(a, [abj, abk], [baj, np.zeros_like(baj)], b)[4]
+    return _columnwise(one, (A, ABj, ABk, BAj, B))
 
 
 def Si_to_pandas_dict(S_dict):

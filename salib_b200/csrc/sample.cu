@@ -373,6 +373,28 @@ saltelli_eval_ishigami_kernel(const uint32_t *__restrict__ sv, const uint32_t *_
   }
 }
 
+// Plain Sobol' points [n, dims] (no cross-matrix, no scaling): sample/sobol_sequence.py:49-91.
+// Block <-> run of 64 consecutive points, thread <-> dimension: closed form once, then one XOR per point;
+// a warp writes 32 consecutive dimensions of a row.
+constexpr int kPointRows = 64;
+__global__ void __launch_bounds__(256)
+sobol_points_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift, uint64_t first_index,
+                    uint64_t n, int dims, double *__restrict__ out) {
+  const uint64_t r0 = (uint64_t)blockIdx.x * kPointRows;
+  const uint64_t r1 = (r0 + kPointRows < n) ? r0 + kPointRows : n;
+  for (int d = threadIdx.x; d < dims; d += blockDim.x) {
+    const uint32_t *v = sv + (size_t)d * SA_SOBOL_BITS;
+    uint64_t k = first_index + r0;
+    uint32_t x = sobol_point(sv, shift ? shift[d] : 0u, d, k);
+    for (uint64_t r = r0; r < r1; ++r) {
+      out[r * (uint64_t)dims + d] = (double)x * kTwoPowMinus30;
+      ++k;
+      const int c = __ffsll((long long)k) - 1;
+      if (c < SA_SOBOL_BITS) x ^= __ldg(v + c);
+    }
+  }
+}
+
 static bool reg_path_ok(int D) {
   if (D < 2 || (D & 1)) return false;
   const int h = D / 2;
@@ -447,6 +469,21 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     kern<<<(unsigned)blocks, 256, smem, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
                                              second_order, cs, d_out, BR, m_rowlen, m_D);
   }
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_sobol_points_f64(void *stream, const uint32_t *d_sv, const uint32_t *d_shift,
+                                   uint64_t first_index, uint64_t n, int dims, double *d_out) {
+  SA_REQUIRE(d_sv && d_out, SA_ERR_ARG, "sa_sobol_points_f64: null pointer");
+  SA_REQUIRE(dims >= 1 && dims <= SA_SOBOL_MAXDIM, SA_ERR_RANGE, "sa_sobol_points_f64: dims=%d out of range", dims);
+  SA_REQUIRE(first_index + n <= (1ull << SA_SOBOL_BITS), SA_ERR_RANGE,
+             "sa_sobol_points_f64: index range exceeds 2^30 points");
+  if (n == 0) return SA_OK;
+  const uint64_t blocks = ceil_div_u64(n, kPointRows);
+  SA_REQUIRE(blocks < (1ull << 31), SA_ERR_UNSUPPORTED, "sa_sobol_points_f64: grid too large");
+  sobol_points_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, dims, d_out);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

@@ -94,6 +94,29 @@ def test_matches_oracle_over_shapes(D, N, c2, R):
     _cmp(S, So, D, c2, rtol=1e-9, atol=1e-12)
 
 
+def test_estimator_functions():
+    """first_order / total_order / second_order / separate_output_values as standalone calls
+    (reference :209-246,267-279; used by tests/test_sobol.py:96-145 and other analyzers)."""
+    from oracle import analyze as o
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_g8_n512_r64")
+    Y, D, N = z["Y"], 8, 512
+    A, B, AB, BA = sobol.separate_output_values(Y, D, N, True)
+    Ao, Bo, ABo, BAo = o.split(Y, D, N, True)
+    assert np.array_equal(A, Ao) and np.array_equal(AB, ABo) and np.array_equal(BA, BAo) and np.array_equal(B, Bo)
+    np.testing.assert_allclose(sobol.first_order(A, AB[:, 2], B), o.first_order(A, AB[:, 2], B), rtol=1e-11)
+    np.testing.assert_allclose(sobol.total_order(A, AB[:, 0], B), o.total_order(A, AB[:, 0], B), rtol=1e-11)
+    np.testing.assert_allclose(sobol.second_order(A, AB[:, 0], AB[:, 1], BA[:, 0], B),
+                               o.second_order(A, AB[:, 0], AB[:, 1], BA[:, 0], B), rtol=1e-9, atol=1e-13)
+    r = z["r"].astype(np.int64)[:, :3]
+    np.testing.assert_allclose(sobol.first_order(A[r], AB[r, 1], B[r]), o.first_order(A[r], AB[r, 1], B[r]), rtol=1e-11)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert sobol.first_order(np.ones(64), np.arange(64.0), np.ones(64)) == 0.0
+    assert any("Constant values" in str(x.message) for x in w)
+
+
 def test_device_resident_input_and_seed_zero():
     """Y may already live on the GPU; seed=0 is falsy -> legacy global RNG like the reference (:113)."""
     import torch

@@ -156,6 +156,22 @@ def test_large_structure_properties():
         assert torch.equal(torch.sort(M, dim=0).values, grid[:, None].expand(N, D))
 
 
+def test_sobol_sequence_dropin():
+    """reference tests/test_sobol.py:21-36 (first ten Joe-Kuo points) + oracle over many dims / a skip."""
+    from oracle import sobol_seq
+    from salib_b200.sample import sobol_sequence
+
+    expected = np.array([[0, 0, 0], [0.5, 0.5, 0.5], [0.75, 0.25, 0.25], [0.25, 0.75, 0.75],
+                         [0.375, 0.375, 0.625], [0.875, 0.875, 0.125], [0.625, 0.125, 0.875],
+                         [0.125, 0.625, 0.375], [0.1875, 0.3125, 0.9375], [0.6875, 0.8125, 0.4375]])
+    assert np.array_equal(sobol_sequence.sample(10, 3), expected)
+    assert np.array_equal(sobol_sequence.sample(1000, 300), sobol_seq.points_closed_form(1000, 300))
+    assert np.array_equal(sobol_sequence.sample(77, 5, skip=12345), sobol_seq.points_closed_form(77, 5, skip=12345))
+    with pytest.raises(ValueError, match="not enough dimensions"):
+        sobol_sequence.sample(4, 21202)
+    assert sobol_sequence.index_of_least_significant_zero_bit(0b1011) == 3
+
+
 def test_errors():
     from salib_b200 import _lib
     from salib_b200.sample import sobol
