@@ -312,8 +312,13 @@ def main():
         flop_per_row = 6 * D + 6
         kernel = "fo_accum_kernel"
     achieved = flop_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
+    # DRAM bytes of one tile-kernel launch from the committed ncu capture (1184 resamples = one wave at
+    # N = 2^20: Y in analysis layout 1.36 GB + multiplicities 1.24 GB, each read once)
+    traffic = 2.636e9 if (c2 and D == 64 and a.log2n == 20) else None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp64_peak) if achieved else None, "traffic": None, "kernel": kernel,
+                "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_s2_accum_smem_ncu_n20_r1184.csv (dram read+write per 1184-resample launch)"
+                if traffic else None, "kernel": kernel,
                 "kernel_ms_per_step": k_ms / a.steps, "kernel_share_of_step": (k_ms / 1e3) / t_an,
                 "algorithmic_flop_per_resample_row": flop_per_row,
                 "peak_source": "measured here: sa_microbench_fp64 (16 independent DFMA chains/thread)",
