@@ -34,7 +34,7 @@ from scipy.stats import norm
 from .. import _lib, _runtime as rt
 from ..util import ResultDict, extract_group_names
 
-__all__ = ["analyze", "analyze_device", "first_order", "total_order", "second_order", "separate_output_values",
+__all__ = ["analyze", "analyze_device", "analyze_outputs", "first_order", "total_order", "second_order", "separate_output_values",
            "to_df", "Si_to_pandas_dict", "CONST_RESULT_MSG"]
 
 CONST_RESULT_MSG = (
@@ -198,21 +198,29 @@ class SobolAnalyzer:
 
     def bootstrap(self, resampler, lo, hi):
         """Estimates of resamples [lo, hi) -> device [hi-lo, nest]."""
-        est = rt.empty((hi - lo, self.nest), torch.float64)
-        w = None
-        for c0, c1 in self._batches(lo, hi):
-            n = c1 - c0
-            if w is None or w.numel() < n * self.Npad:
-                w = rt.empty((n * self.Npad,), torch.uint8)
-            resampler.counts(c0, n, w)
-            self._accumulate(w, n, est[c0 - lo:c1 - lo])
-        return est
+        return bootstrap_shared([self], resampler, lo, hi)[0]
 
     def conf(self, est, z):
         out = rt.empty((self.nest,), torch.float64)
         _lib.call("sa_sobol_conf_f64", rt.stream_ptr(), rt.ptr(est), int(est.shape[0]), self.nest, float(z),
                   rt.ptr(out))
         return out
+
+
+def bootstrap_shared(engines, resampler, lo, hi):
+    """Estimates of resamples [lo, hi) for several model outputs of the same design (same N, Dg, order):
+    the multiplicities of each batch are built once and every output's rows are accumulated against them."""
+    lead = engines[0]
+    ests = [rt.empty((hi - lo, e.nest), torch.float64) for e in engines]
+    w = None
+    for c0, c1 in lead._batches(lo, hi):
+        n = c1 - c0
+        if w is None or w.numel() < n * lead.Npad:
+            w = rt.empty((n * lead.Npad,), torch.uint8)
+        resampler.counts(c0, n, w)
+        for e, est in zip(engines, ests):
+            e._accumulate(w, n, est[c0 - lo:c1 - lo])
+    return ests
 
 
 def allgather_estimates(est_local, R, rank, world):
@@ -262,36 +270,41 @@ def _assemble(Dg, c2, keep, point, conf, est_all, const_y):
     return S
 
 
-def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
-                   keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
-                   kernel_events=None):
-    """``analyze`` with the device knobs exposed.
-
-    Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
-    ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
-    ``algo``: force an accumulate kernel ("generic" | "tile8" | "first_order"); ``distributed``: shard the
-    resamples over the initialised torch.distributed job.
-    """
-    _, Dg = extract_group_names(problem)
-    size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+def _n_from_size(size, Dg, calc_second_order):
     if calc_second_order and size % (2 * Dg + 2) == 0:
-        N = size // (2 * Dg + 2)
-    elif not calc_second_order and size % (Dg + 2) == 0:
-        N = size // (Dg + 2)
-    else:
-        raise RuntimeError(
-            """
+        return size // (2 * Dg + 2)
+    if not calc_second_order and size % (Dg + 2) == 0:
+        return size // (Dg + 2)
+    raise RuntimeError(
+        """
         Incorrect number of samples in model output file.
         Confirm that calc_second_order matches option used during sampling."""
-        )
+    )
+
+
+def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf_level=0.95,
+                    keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
+                    kernel_events=None):
+    """Analyze several model outputs of one design in one pass: ``Ys`` is a list of [N*step] arrays
+    (host or CUDA).  All outputs share one resample draw -- with a ``seed`` that is exactly what the
+    reference's per-output calls produce (``ProblemSpec.analyze``, util/problem.py:368-371, re-seeds each
+    call); without a seed the reference would redraw per output, which is statistically equivalent.
+    Returns a list of ResultDicts."""
+    _, Dg = extract_group_names(problem)
+    sizes = {int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y)) for Y in Ys}
+    if len(sizes) != 1:
+        raise ValueError("all outputs must have the same number of model evaluations")
+    N = _n_from_size(sizes.pop(), Dg, calc_second_order)
     if not 0 < conf_level < 1:
         raise RuntimeError("Confidence level must be between 0-1.")
 
     rt.require_cuda()
-    Yd = rt.to_device(Y, torch.float64).reshape(-1)
-    eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
-    eng.kernel_events = kernel_events
-    eng.load(Yd)
+    engines = []
+    for Y in Ys:
+        eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
+        eng.kernel_events = kernel_events
+        eng.load(rt.to_device(Y, torch.float64).reshape(-1))
+        engines.append(eng)
     Z = norm.ppf(0.5 + conf_level / 2)
 
     if r is not None:
@@ -303,32 +316,52 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
         R = int(num_resamples)
         rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
 
-    point = eng.point()
+    points = [eng.point() for eng in engines]
     rank, world = rt.world() if distributed else (0, 1)
-    est = None
+    ests = [None] * len(engines)
     if R > 0:
         lo, hi = rt.shard_range(R, rank, world)
-        est = eng.bootstrap(rs, lo, hi)
+        ests = bootstrap_shared(engines, rs, lo, hi)
         if world > 1:
-            est = allgather_estimates(est, R, rank, world)
-        conf = eng.conf(est, Z)
+            ests = [allgather_estimates(e, R, rank, world) for e in ests]
+        confs = [eng.conf(e, Z) for eng, e in zip(engines, ests)]
     else:
-        conf = torch.full((eng.nest,), float("nan"), dtype=torch.float64, device=point.device)
-
-    stats = eng.stats.cpu().numpy()
+        confs = [torch.full((eng.nest,), float("nan"), dtype=torch.float64, device=points[0].device)
+                 for eng in engines]
     if rs is not None:
         rs.check()
-    # ptp([A;B]) == 0 -- or a constant Y, whose normalisation is 0/0 (the tested outcome is zeros)
-    const_y = not (stats[4] < stats[5])
-    if const_y:
-        warn(CONST_RESULT_MSG)
+
     keep = bool(keep_resamples)
-    S = _assemble(Dg, bool(calc_second_order), keep, point[0].cpu().numpy(), conf.cpu().numpy(),
-                  est[:, :2 * Dg].cpu().numpy() if (keep and est is not None) else (np.zeros((0, 2 * Dg)) if keep else None),
-                  const_y)
-    S.problem = problem
-    S.to_df = MethodType(to_df, S)
-    return S
+    out = []
+    for eng, point, est, conf in zip(engines, points, ests, confs):
+        stats = eng.stats.cpu().numpy()
+        # ptp([A;B]) == 0 -- or a constant Y, whose normalisation is 0/0 (tested outcome is zeros)
+        const_y = not (stats[4] < stats[5])
+        if const_y:
+            warn(CONST_RESULT_MSG)
+        kept = None
+        if keep:
+            kept = est[:, :2 * Dg].cpu().numpy() if est is not None else np.zeros((0, 2 * Dg))
+        S = _assemble(Dg, bool(calc_second_order), keep, point[0].cpu().numpy(), conf.cpu().numpy(), kept, const_y)
+        S.problem = problem
+        S.to_df = MethodType(to_df, S)
+        out.append(S)
+    return out
+
+
+def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
+                   keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
+                   kernel_events=None):
+    """``analyze`` with the device knobs exposed.
+
+    Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
+    ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
+    ``algo``: force an accumulate kernel ("generic" | "tile8" | "first_order"); ``distributed``: shard the
+    resamples over the initialised torch.distributed job.
+    """
+    return analyze_outputs(problem, [Y], calc_second_order=calc_second_order, num_resamples=num_resamples,
+                           conf_level=conf_level, keep_resamples=keep_resamples, seed=seed, resample=resample,
+                           r=r, algo=algo, distributed=distributed, kernel_events=kernel_events)[0]
 
 
 def analyze(

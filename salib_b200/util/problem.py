@@ -134,9 +134,28 @@ class ProblemSpec(dict):
         return self.sample(saltelli.sample, *args, **kwargs)
 
     def analyze_sobol(self, *args, **kwargs):
+        """``analyze(sobol.analyze, ...)``; with several outputs the columns are analysed in one pass that
+        shares the resample multiplicities (same results as per-column calls with the same ``seed``)."""
         from ..analyze import sobol
 
-        return self.analyze(sobol.analyze, *args, **kwargs)
+        res = self._results
+        if res is None or len(res.shape) == 1 or res.shape[1] == 1 or args:
+            return self.analyze(sobol.analyze, *args, **kwargs)
+        if self["num_vars"] == 1:
+            return self.analyze(sobol.analyze, *args, **kwargs)  # raises the reference's ValueError
+        kwargs.pop("nprocs", None)
+        for ignored in ("parallel", "n_processors"):
+            kwargs.pop(ignored, None)
+        show = kwargs.pop("print_to_console", False)
+        if self.get("outputs") is None:
+            self["outputs"] = [f"Y{i}" for i in range(1, res.shape[1] + 1)]
+        outs = sobol.analyze_outputs(self, [res[:, i] for i in range(res.shape[1])], **kwargs)
+        self._analysis = dict(zip(self["outputs"], outs))
+        if show:
+            for S in outs:
+                for df in S.to_df():
+                    print(df)
+        return self
 
     # -- views -----------------------------------------------------------------------------
     def to_df(self):

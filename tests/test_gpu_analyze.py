@@ -230,3 +230,9 @@ def test_problem_spec_chain_on_device():
         sp2.analyze_sobol(num_resamples=20, seed=3)
         assert set(sp2.analysis) == {"Y1", "Y2"}
         np.testing.assert_allclose(sp2.analysis["Y1"]["S1"], sp2.analysis["Y2"]["S1"], rtol=1e-9, atol=1e-12)
+        # the shared-multiplicity pass equals one reference-style call per output column
+        from salib_b200.analyze import sobol as an
+        for i, name in enumerate(("Y1", "Y2")):
+            Si = an.analyze(sp2, sp2.results[:, i], num_resamples=20, seed=3)
+            for k in ("S1", "S1_conf", "ST", "ST_conf"):
+                np.testing.assert_allclose(sp2.analysis[name][k], Si[k], rtol=1e-12, atol=1e-14)
