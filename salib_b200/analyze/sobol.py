@@ -104,6 +104,37 @@ class _Resampler:
             raise OverflowError("a row was drawn more than 255 times in one resample")
 
 
+def plan_row_splits(kind, count, N, sms, nacc):
+    """Row splits so that `count` resamples fill `sms` SMs (at least 32 rows per split).  Pure host logic."""
+    max_split = max(1, min(4096, N // 32))
+    if kind == 4:        # tile kernel: one warp per resample, 8 per block, one block per SM
+        blocks = -(-count // 8)
+    elif kind == 3:      # first-order GEMV kernel: 256 resamples per block, ~4 resident blocks per SM
+        blocks = -(-count // 256) * -(-nacc // 32)
+        return max(1, min(max_split, (4 * sms) // blocks))
+    else:                # generic kernel: one block per resample
+        blocks = count
+    return max(1, min(max_split, sms // blocks if blocks <= sms else 1))
+
+
+def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None):
+    """Resample batches [c0, c1) covering [lo, hi): bounded by the multiplicity buffer (max_bytes); for the
+    one-warp-per-resample tile kernel sized in whole waves (8 * sms), the remainder being its own
+    (row-split) launch.  Pure host logic."""
+    cap = max(1, (max_bytes or MAX_COUNT_BYTES) // Npad)
+    wave = 8 * sms if kind == 4 else 256 * sms
+    out, c = [], lo
+    while c < hi:
+        left = hi - c
+        if left >= wave:
+            n = min((cap // wave) * wave, (left // wave) * wave) or min(cap, left)
+        else:
+            n = min(cap, left)
+        out.append((c, c + n))
+        c += n
+    return out
+
+
 class SobolAnalyzer:
     """Device state of one ``analyze`` call; also usable directly with a device-resident Y."""
 
@@ -149,16 +180,7 @@ class SobolAnalyzer:
 
     # -- work decomposition ----------------------------------------------------------------
     def _nsplit(self, count):
-        """Row splits so that `count` resamples fill the machine (at least 32 rows per split)."""
-        max_split = max(1, min(4096, self.N // 32))
-        if self.kind == 4:       # one warp per resample, 8 per block, one block per SM
-            blocks = -(-count // 8)
-        elif self.kind == 3:    # 256 resamples per block, up to ~4 resident blocks per SM
-            blocks = -(-count // 256) * -(-self.nacc // 32)
-            return max(1, min(max_split, (4 * self.sms) // blocks))
-        else:                   # one block per resample
-            blocks = count
-        return max(1, min(max_split, self.sms // blocks if blocks <= self.sms else 1))
+        return plan_row_splits(self.kind, count, self.N, self.sms, self.nacc)
 
     def _accumulate(self, w, count, est_out):
         """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
@@ -182,19 +204,7 @@ class SobolAnalyzer:
         return est
 
     def _batches(self, lo, hi):
-        """Resample batches [c0, c1): bounded by the multiplicity buffer; for the one-warp-per-resample
-        kernel sized in whole waves (8 * SMs) with the remainder as its own, row-split, launch."""
-        cap = max(1, MAX_COUNT_BYTES // self.Npad)
-        wave = 8 * self.sms if self.kind == 4 else 256 * self.sms
-        c = lo
-        while c < hi:
-            left = hi - c
-            if left >= wave:
-                n = min((cap // wave) * wave, (left // wave) * wave) or min(cap, left)
-            else:
-                n = min(cap, left)
-            yield c, c + n
-            c += n
+        return plan_batches(self.kind, lo, hi, self.Npad, self.sms)
 
     def bootstrap(self, resampler, lo, hi):
         """Estimates of resamples [lo, hi) -> device [hi-lo, nest]."""

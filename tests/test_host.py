@@ -229,6 +229,27 @@ def test_result_assembly_and_to_df():
     assert "S2" not in F and F["ST"].tolist() == [4.0, 5.0, 6.0]
 
 
+def test_work_decomposition_plans():
+    """Batching of resamples and row splits (host logic of analyze): full coverage, whole waves for the tile
+    kernel, buffer cap respected, small counts split over rows so they fill the machine."""
+    from salib_b200.analyze.sobol import plan_batches, plan_row_splits
+
+    sms, Npad = 148, (1 << 20) + 128
+    b = plan_batches(4, 0, 10000, Npad, sms)
+    assert b[0][0] == 0 and b[-1][1] == 10000 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    assert all((c1 - c0) % (8 * sms) == 0 for c0, c1 in b[:-1]) and b[-1][1] - b[-1][0] == 10000 % (8 * sms)
+    small_cap = plan_batches(4, 5, 5000, Npad, sms, max_bytes=2000 * Npad)
+    assert max(c1 - c0 for c0, c1 in small_cap) <= 2000 and small_cap[0][0] == 5 and small_cap[-1][1] == 5000
+    assert plan_batches(3, 0, 1000, Npad, sms) == [(0, 1000)]
+    assert plan_batches(4, 7, 7, Npad, sms) == []
+    assert plan_row_splits(4, 1184, 1 << 20, sms, 2149) == 1          # a full wave needs no split
+    assert plan_row_splits(4, 1, 1 << 20, sms, 2149) == 148           # point estimate: one block per SM
+    assert plan_row_splits(4, 528, 1 << 20, sms, 2149) == 2
+    assert plan_row_splits(4, 16, 100, sms, 11) == 3                  # never fewer than 32 rows per split
+    assert plan_row_splits(3, 1000, 1 << 20, sms, 21) == 148
+    assert plan_row_splits(1, 1000, 4096, sms, 50) == 1
+
+
 def test_shard_range_covers_everything():
     from salib_b200._runtime import shard_range
 
