@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsalib_b200.so")
+# SALIB_B200_LIB: load another build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("SALIB_B200_LIB") or os.path.join(_HERE, "lib", "libsalib_b200.so")
 
 _vp, _u64, _i32, _dbl, _sz = C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_size_t
 

@@ -104,11 +104,17 @@ class _Resampler:
             raise OverflowError("a row was drawn more than 255 times in one resample")
 
 
-def plan_row_splits(kind, count, N, sms, nacc):
+def tile_groups(Dg):
+    """Warps (tile groups of 32 lane tiles) that carry one resample in the tile kernel."""
+    TB = -(-Dg // 8)
+    return 1 if TB <= 8 else -(-(TB * (TB + 1) // 2) // 32)
+
+
+def plan_row_splits(kind, count, N, sms, nacc, groups=1):
     """Row splits so that `count` resamples fill `sms` SMs (at least 32 rows per split).  Pure host logic."""
     max_split = max(1, min(4096, N // 32))
-    if kind == 4:        # tile kernel: one warp per resample, 8 per block, one block per SM
-        blocks = -(-count // 8)
+    if kind == 4:        # tile kernel: `groups` warps per resample, 8 warps per block, one block per SM
+        blocks = -(-count // 8) * groups
     elif kind == 3:      # first-order GEMV kernel: 256 resamples per block, ~4 resident blocks per SM
         blocks = -(-count // 256) * -(-nacc // 32)
         return max(1, min(max_split, (4 * sms) // blocks))
@@ -117,12 +123,12 @@ def plan_row_splits(kind, count, N, sms, nacc):
     return max(1, min(max_split, sms // blocks if blocks <= sms else 1))
 
 
-def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None):
+def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None, groups=1):
     """Resample batches [c0, c1) covering [lo, hi): bounded by the multiplicity buffer (max_bytes); for the
     one-warp-per-resample tile kernel sized in whole waves (8 * sms), the remainder being its own
     (row-split) launch.  Pure host logic."""
     cap = max(1, (max_bytes or MAX_COUNT_BYTES) // Npad)
-    wave = 8 * sms if kind == 4 else 256 * sms
+    wave = max(8, 8 * sms // groups) if kind == 4 else 256 * sms
     out, c = [], lo
     while c < hi:
         left = hi - c
@@ -144,9 +150,10 @@ class SobolAnalyzer:
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[algo]
-        # tile kernel: Dg <= 64; first-order GEMV kernel: its 4 x 32 feature rows must fit shared memory
-        kind = self.algo or (4 if (self.c2 and Dg <= 64) else (3 if (not self.c2 and Dg <= 90) else 1))
+        # tile kernel: Dg <= 512; first-order GEMV kernel: its 4 x 32 feature rows must fit shared memory
+        kind = self.algo or (4 if (self.c2 and Dg <= 512) else (3 if (not self.c2 and Dg <= 90) else 1))
         self.kind = kind
+        self.groups = tile_groups(Dg) if kind == 4 else 1
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
         L = _lib.lib()
         self.stride = L.sa_row_stride(self.Dg, int(self.c2))
@@ -180,7 +187,7 @@ class SobolAnalyzer:
 
     # -- work decomposition ----------------------------------------------------------------
     def _nsplit(self, count):
-        return plan_row_splits(self.kind, count, self.N, self.sms, self.nacc)
+        return plan_row_splits(self.kind, count, self.N, self.sms, self.nacc, self.groups)
 
     def _accumulate(self, w, count, est_out):
         """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
@@ -204,7 +211,7 @@ class SobolAnalyzer:
         return est
 
     def _batches(self, lo, hi):
-        return plan_batches(self.kind, lo, hi, self.Npad, self.sms)
+        return plan_batches(self.kind, lo, hi, self.Npad, self.sms, groups=self.groups)
 
     def bootstrap(self, resampler, lo, hi):
         """Estimates of resamples [lo, hi) -> device [hi-lo, nest]."""

@@ -296,7 +296,6 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
 // a second buffer -- so only the first row of a tile waits for shared memory.
 // ncu history of this kernel is in profiles/ (L1 version: 118 wavefronts/row, FP64 pipe 38 %).
 constexpr int kS2Warps = 8;
-constexpr int kTileRows = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -406,11 +405,12 @@ scalar_sums_kernel(const double *__restrict__ Yt, uint64_t Npad, uint64_t N, con
   }
 }
 
-template <int kStages, bool W1FAST>
+template <int kTileRows, int kStagesT, bool GROUPED>  // kStagesT == 0: ring depth given at run time
 __global__ void __launch_bounds__(kS2Warps * 32, 1)
 s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
                      const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
-                     uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+                     uint64_t rows_per_split, double *__restrict__ psum, int nacc, int stages_rt) {
+  const int kStages = kStagesT ? kStagesT : stages_rt;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -450,12 +450,20 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   }
 
   // ---- lane roles ------------------------------------------------------------------------
-  // full 8x8 tile: off-diagonal (tj < tk) first, then diagonal tiles while lanes remain
+  // Tile list: off-diagonal tiles (tj < tk) in row-major order, then the diagonal tiles.  Up to Dg = 64
+  // (TB <= 8) one warp carries a resample: 32 full tiles, the diagonal tiles that do not fit are spread
+  // over the lanes 4 pairs each (below).  For larger Dg the list is cut into groups of 32 tiles and
+  // blockIdx.z selects the group: a resample is carried by ceil(TB(TB+1)/64) warps in different blocks.
+  constexpr bool grouped = GROUPED;  // host: TB > 8
+  constexpr bool W1FAST = false;     // weight-1 fast path: measured no gain (shared-memory bound)
+  const int group = grouped ? blockIdx.z : 0;
   const int ntOff = TB * (TB - 1) / 2;
+  const int ndiag_full = grouped ? TB : ((32 - ntOff < TB) ? (32 - ntOff) : TB);  // diagonal tiles done as full tiles
+  const int tile_id = group * 32 + lane;
   int tj = 0, tk = 0;
   bool actA = false;
-  if (lane < ntOff) {
-    int idx = lane;
+  if (tile_id < ntOff) {
+    int idx = tile_id;
     for (int t = 0; t < TB; ++t) {
       const int n = TB - 1 - t;
       if (idx < n) {
@@ -466,11 +474,10 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
       }
       idx -= n;
     }
-  } else if (lane - ntOff < TB) {
-    tj = tk = lane - ntOff;
+  } else if (tile_id - ntOff < ndiag_full) {
+    tj = tk = tile_id - ntOff;
     actA = true;
   }
-  const int ndiag_full = (32 - ntOff < TB) ? (32 - ntOff) : TB;  // diagonal tiles done as full tiles
   const int PL = TB * kBlockPitch;                                              // doubles per AB / BA part
   const uint32_t offX = actA ? (uint32_t)(PL + kBlockPitch * tj) * 8u : 0u;  // BA block tj
   const uint32_t offY = actA ? (uint32_t)(kBlockPitch * tk) * 8u : 0u;       // AB block tk
@@ -489,7 +496,7 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   // first/total order: two columns per lane; block order {0,4,1,5} / {2,6,3,7} over the quarter-warps
   // keeps the two blocks a half-warp reads with one LDS.64 in disjoint banks
   const int cblk0 = ((lane >> 3) & 1) * 4 + (lane >> 4);
-  const int jC0 = 8 * cblk0 + (lane & 7), jC1 = jC0 + 16;
+  const int jC0 = 64 * group + 8 * cblk0 + (lane & 7), jC1 = jC0 + 16;  // group g: columns 64g .. 64g+63
   const uint32_t offC0 = (jC0 < Dp) ? (uint32_t)col_pos(jC0) * 8u : 0u;
   const uint32_t offC1 = (jC1 < Dp) ? (uint32_t)col_pos(jC1) * 8u : 0u;
   const uint32_t offAB = 2u * PL * 8u;
@@ -505,7 +512,7 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
   const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
   auto load_w = [&](int t) -> unsigned {
     const uint64_t i = row0 + (uint64_t)t * kTileRows + lane;
-    if (!live || t >= ntiles || i >= row1) return 0u;
+    if (!live || t >= ntiles || lane >= kTileRows || i >= row1) return 0u;
     return wrow ? (unsigned)__ldg(wrow + i) : 1u;
   };
   unsigned wl_next = load_w(0);
@@ -580,45 +587,62 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     }
   };
 
+  // Row stream.  The operands of the upcoming row always sit in (P, Q[phase]); the last row of a tile
+  // prefetches the first row of the NEXT tile (whose barrier is waited for just before), so a warp meets a
+  // cold start only at its very first row (or after a tile in which its resample has no row at all).
+  int phase = 0;        // which AB buffer holds the upcoming row: 0 -> Q0, 1 -> Q1
+  bool have = false;    // operands of the upcoming row already loaded
+  bool waited = false;  // barrier of the upcoming tile already passed
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kStages;
-    const uint32_t parity = (uint32_t)(t / kStages) & 1u;
     const unsigned wl = wl_next;
     wl_next = load_w(t + 1);
     unsigned mask = __ballot_sync(kFull, wl != 0);
     // multiplicities are small integers: as doubles their low word is 0, so one 32-bit shuffle of
     // the high word moves them between lanes and no int->double conversion sits in the row loop
     const int whi = __double2hiint((double)wl);
-    const uint32_t bar = bar_base + 8u * s;
-    while (!mbar_try_wait(bar, parity)) {
+    if (!waited) {
+      const uint32_t bar = bar_base + 8u * s;
+      const uint32_t parity = (uint32_t)(t / kStages) & 1u;
+      while (!mbar_try_wait(bar, parity)) {
+      }
     }
+    waited = false;
     const uint32_t tile = sm_base + s * stage_bytes;
-    if (mask) {  // cold start of the tile: operands of its first row
+    if (mask && !have) {  // cold start
       const uint32_t row = tile + (uint32_t)(__ffs(mask) - 1) * row_bytes;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         ldP(row, q);
-        ldQ(Q0, row, q);
+        if (phase) ldQ(Q1, row, q);
+        else ldQ(Q0, row, q);
       }
     }
+    if (mask) have = false;
     while (mask) {
-      {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int hi = __shfl_sync(kFull, whi, b);
-        const uint32_t row = tile + (uint32_t)b * row_bytes;
-        const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-        row_any(row, nrow, hi, Q0, Q1);
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int hi = __shfl_sync(kFull, whi, b);
+      const uint32_t row = tile + (uint32_t)b * row_bytes;
+      uint32_t nrow = row;  // nothing to prefetch: reload this row (harmless)
+      if (mask) {
+        nrow = tile + (uint32_t)(__ffs(mask) - 1) * row_bytes;
+      } else if (t + 1 < ntiles) {  // last row of the tile: chain into the next tile
+        const unsigned mask_n = __ballot_sync(kFull, wl_next != 0);
+        if (mask_n) {
+          const int sn = (t + 1) % kStages;
+          const uint32_t bar = bar_base + 8u * sn;
+          const uint32_t parity = (uint32_t)((t + 1) / kStages) & 1u;
+          while (!mbar_try_wait(bar, parity)) {
+          }
+          waited = true;
+          have = true;
+          nrow = sm_base + sn * stage_bytes + (uint32_t)(__ffs(mask_n) - 1) * row_bytes;
+        }
       }
-      if (!mask) break;
-      {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int hi = __shfl_sync(kFull, whi, b);
-        const uint32_t row = tile + (uint32_t)b * row_bytes;
-        const uint32_t nrow = mask ? tile + (uint32_t)(__ffs(mask) - 1) * row_bytes : row;
-        row_any(row, nrow, hi, Q1, Q0);
-      }
+      if (phase) row_any(row, nrow, hi, Q1, Q0);
+      else row_any(row, nrow, hi, Q0, Q1);
+      phase ^= 1;
     }
     // release the stage; the last warp out refills it with tile t + kStages
     __syncwarp();
@@ -1082,24 +1106,35 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   const int nacc = SA_NACC(Dg, second_order);
   uint64_t rps = ceil_div_u64(N, nsplit);
   rps = (rps + 31) & ~(uint64_t)31;
-  if (algo == 0) algo = second_order ? (Dg <= 64 ? 4 : 1) : (Dg <= 90 ? 3 : 1);
+  if (algo == 0) algo = second_order ? (Dg <= 512 ? 4 : 1) : (Dg <= 90 ? 3 : 1);
   if (algo == 4) {
-    SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "tile8 kernel needs second order and Dg <= 64");
+    SA_REQUIRE(second_order && Dg <= 512, SA_ERR_UNSUPPORTED, "tile kernel needs second order and Dg <= 512");
     SA_REQUIRE(d_Yn && d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn / d_Yt is null");
     SA_REQUIRE(((uintptr_t)d_Yn & 15) == 0, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn not 16-byte aligned");
     const uint64_t bx = ceil_div_u64(count, kS2Warps);
     const uint64_t bsc = ceil_div_u64(count, kScC);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
-    // 5 stages of 32 rows (207 KB at Dg = 64).  The weight-1 fast path (no multiplications for 58 % of
-    // the rows) is compiled out: measured no gain, the kernel is bound by shared-memory wavefronts.
-    constexpr int stages = 5;
-    auto kern = s2_accum_smem_kernel<stages, false>;
-    const size_t smem = (size_t)stages * kTileRows * stride * 8 + stages * 8 + stages * 4 + 16;
+    // Ring geometry: 32-row tiles and up to 5 stages while they fit 224 KB (Dg <= 64: 5 x 41 KB);
+    // longer rows get fewer stages, then 16- or 8-row tiles.  The weight-1 fast path (no multiplications
+    // for 58 % of the rows) is compiled out: measured no gain, the kernel is bound by shared-memory wavefronts.
+    const size_t row_bytes = (size_t)stride * 8, budget = 224 * 1024;
+    int tile_rows = 32;
+    while (tile_rows > 8 && 2 * tile_rows * row_bytes > budget) tile_rows >>= 1;
+    int stages = (int)(budget / (tile_rows * row_bytes));
+    if (stages > 5) stages = 5;
+    SA_REQUIRE(stages >= 2, SA_ERR_UNSUPPORTED, "tile kernel: rows of %zu bytes do not fit shared memory", row_bytes);
+    const int TBh = Dp >> 3;
+    const int ngroups = TBh > 8 ? (TBh * (TBh + 1) / 2 + 31) / 32 : 1;
+    auto kern = TBh <= 8 ? (stages == 5 ? s2_accum_smem_kernel<32, 5, false> : s2_accum_smem_kernel<32, 0, false>)
+                         : (tile_rows == 32 ? s2_accum_smem_kernel<32, 0, true>
+                                            : (tile_rows == 16 ? s2_accum_smem_kernel<16, 0, true>
+                                                               : s2_accum_smem_kernel<8, 0, true>));
+    const size_t smem = (size_t)stages * tile_rows * row_bytes + stages * 12 + 16;
     SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     scalar_sums_kernel<<<dim3((unsigned)bsc, (unsigned)nsplit), 256, 0, st>>>(d_Yt, Npad, N, d_w, count, rps, d_psum,
                                                                                nacc);
-    kern<<<dim3((unsigned)bx, (unsigned)nsplit), kS2Warps * 32, smem, st>>>(
-        d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc);
+    kern<<<dim3((unsigned)bx, (unsigned)nsplit, (unsigned)ngroups), kS2Warps * 32, smem, st>>>(
+        d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc, stages);
     note_launches(1);
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");

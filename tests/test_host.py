@@ -232,7 +232,10 @@ def test_result_assembly_and_to_df():
 def test_work_decomposition_plans():
     """Batching of resamples and row splits (host logic of analyze): full coverage, whole waves for the tile
     kernel, buffer cap respected, small counts split over rows so they fill the machine."""
-    from salib_b200.analyze.sobol import plan_batches, plan_row_splits
+    from salib_b200.analyze.sobol import plan_batches, plan_row_splits, tile_groups
+
+    assert [tile_groups(d) for d in (3, 64, 65, 128, 200)] == [1, 1, 2, 5, 11]
+    assert plan_row_splits(4, 100, 1 << 16, 148, 8389, groups=5) == 2
 
     sms, Npad = 148, (1 << 20) + 128
     b = plan_batches(4, 0, 10000, Npad, sms)
