@@ -127,8 +127,9 @@ int sa_row_stride(int Dg, int second_order);
  * d_Y [N*step] reference order [A, AB_0.., (BA_0..,) B] -> d_Yn [N*stride (+8 doubles slack)]
  * in analysis layout; if d_Yt != NULL also writes the auxiliary array the fast kernels read:
  *   second_order != 0: column-major copy of A and B, d_Yt[2][Npad], Npad = sa_pad_rows(N);
- *   second_order == 0: per-row feature matrix d_Yt[N][sa_feature_count(Dg)] =
- *     { A, B, A^2, B^2, A*B, B*(AB_j - A) (j < Dg), (A - AB_j)^2 (j < Dg) } (+ pad to an even count).  */
+ *   second_order == 0: per-row feature matrix, sa_feature_count(Dg) doubles per row in total, stored in
+ *     chunks of CW = 8/16/24/32 features as d_Yt[chunk][N][CW]; features in SA_NACC order
+ *     { A, B, A^2, B^2, A*B, B*(AB_j - A) (j < Dg), (A - AB_j)^2 (j < Dg) }, zero padded.            */
 int sa_feature_count(int Dg);
 uint64_t sa_pad_rows(uint64_t N);
 int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,

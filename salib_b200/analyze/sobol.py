@@ -150,8 +150,8 @@ class SobolAnalyzer:
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[algo]
-        # tile kernel: Dg <= 512; first-order GEMV kernel: its 4 x 32 feature rows must fit shared memory
-        kind = self.algo or (4 if (self.c2 and Dg <= 512) else (3 if (not self.c2 and Dg <= 90) else 1))
+        # second order: tile kernel (Dg <= 512); first/total order only: GEMV kernel (any Dg)
+        kind = self.algo or (4 if (self.c2 and Dg <= 512) else (3 if not self.c2 else 1))
         self.kind = kind
         self.groups = tile_groups(Dg) if kind == 4 else 1
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count

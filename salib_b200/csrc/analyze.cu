@@ -707,18 +707,30 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 constexpr int kFoWarps = 8;
 constexpr int kFoRows = 32;   // rows per weight fetch (32 bytes per resample)
 
-__host__ __device__ inline int feature_count(int Dg) { return (5 + 2 * Dg + 1) & ~1; }  // padded to even
+// Feature matrix layout: chunks of CW features, F[chunk][row][CW] (each chunk is what one grid.z slice of
+// fo_gemv_kernel streams).  CW = 8/16/24 when all 5 + 2*Dg features fit one chunk, else 32.
+__host__ __device__ inline int feature_width(int Dg) {
+  const int n = 5 + 2 * Dg;
+  return n <= 24 ? ((n + 7) & ~7) : 32;
+}
+__host__ __device__ inline int feature_chunks(int Dg) {
+  const int cw = feature_width(Dg);
+  return (5 + 2 * Dg + cw - 1) / cw;
+}
 
 __global__ void __launch_bounds__(256)
 normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step,
                           const double *__restrict__ stats, double *__restrict__ F) {
   const double mean = stats[0], sd = stats[1];
-  const int NF = feature_count(Dg);
-  const uint64_t total = N * (uint64_t)NF;
+  const int CW = feature_width(Dg), NZ = feature_chunks(Dg);
+  const uint64_t per_chunk = N * (uint64_t)CW;
+  const uint64_t total = per_chunk * NZ;
   for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = idx / (uint64_t)NF;
-    const int q = (int)(idx - i * (uint64_t)NF);
+    const int z = (int)(idx / per_chunk);
+    const uint64_t rem = idx - (uint64_t)z * per_chunk;
+    const uint64_t i = rem / (uint64_t)CW;
+    const int q = z * CW + (int)(rem - i * (uint64_t)CW);  // global feature index
     const double *row = Y + i * (uint64_t)step;
     const double a = __ddiv_rn(__dsub_rn(row[0], mean), sd);
     const double b = __ddiv_rn(__dsub_rn(row[step - 1], mean), sd);
@@ -740,10 +752,12 @@ normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int 
 
 constexpr int kFoStages = 4;
 
-template <int CH>  // accumulators (features) per lane and grid.z slice: 8, 16, 24 or 32
+template <int CH>  // accumulators (features) per lane = chunk width of the feature matrix: 8, 16, 24 or 32
 __global__ void __launch_bounds__(kFoWarps * 32)
-fo_gemv_kernel(const double *__restrict__ F, int NF, uint64_t N, const uint8_t *__restrict__ w, uint64_t Npad,
+fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__restrict__ w, uint64_t Npad,
                uint64_t count, uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  constexpr int NF = CH;                                           // row length of this chunk
+  const double *__restrict__ F = Fall + (uint64_t)blockIdx.z * N * CH;  // chunk blockIdx.z: [N][CH]
   // Feature rows are streamed through a shared-memory ring exactly like the tile kernel's rows:
   // 32-row tiles (contiguous in HBM) by cp.async.bulk, one mbarrier per stage, last warp out refills.
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -804,7 +818,7 @@ fo_gemv_kernel(const double *__restrict__ F, int NF, uint64_t N, const uint8_t *
     const int nrows = (int)((row1 - i0 < (uint64_t)kFoRows) ? (row1 - i0) : kFoRows);
     while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)(t / kFoStages) & 1u)) {
     }
-    const uint32_t tile = sm_base + s * stage_bytes + (uint32_t)q0 * 8u;
+    const uint32_t tile = sm_base + s * stage_bytes;
 #pragma unroll
     for (int wi = 0; wi < 8; ++wi) {
 #pragma unroll
@@ -817,11 +831,9 @@ fo_gemv_kernel(const double *__restrict__ F, int NF, uint64_t N, const uint8_t *
           const uint32_t f = tile + (uint32_t)r * row_bytes;
 #pragma unroll
           for (int q = 0; q < CH; q += 2) {
-            if (q0 + q < NF) {  // uniform
-              const double2 v = lds_f64x2(f + 8u * q);  // warp-uniform address: one broadcast
-              acc[q] = fma(wv, v.x, acc[q]);
-              acc[q + 1] = fma(wv, v.y, acc[q + 1]);
-            }
+            const double2 v = lds_f64x2(f + 8u * q);  // warp-uniform address: one broadcast
+            acc[q] = fma(wv, v.x, acc[q]);
+            acc[q + 1] = fma(wv, v.y, acc[q + 1]);
           }
         }
       }
@@ -993,7 +1005,7 @@ using namespace sa;
 
 extern "C" int sa_row_stride(int Dg, int second_order) { return row_stride(Dg, second_order); }
 extern "C" uint64_t sa_pad_rows(uint64_t N) { return pad_rows(N); }
-extern "C" int sa_feature_count(int Dg) { return feature_count(Dg); }
+extern "C" int sa_feature_count(int Dg) { return feature_width(Dg) * feature_chunks(Dg); }
 extern "C" size_t sa_moments_workspace_bytes(void) { return (size_t)kMomBlocks * 6 * sizeof(double); }
 
 extern "C" int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double *d_stats,
@@ -1038,7 +1050,7 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
       dim3 grid((unsigned)bx, 2u);
       normalize_cols_kernel<<<grid, 256, 0, st>>>(d_Y, N, Npad, Dg, step, d_stats, d_Yt);
     } else {             // feature matrix for fo_gemv_kernel
-      const uint64_t total = N * (uint64_t)feature_count(Dg);
+      const uint64_t total = N * (uint64_t)feature_width(Dg) * feature_chunks(Dg);
       uint64_t blocks = ceil_div_u64(total, 256);
       if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
       normalize_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, d_stats, d_Yt);
@@ -1106,7 +1118,7 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   const int nacc = SA_NACC(Dg, second_order);
   uint64_t rps = ceil_div_u64(N, nsplit);
   rps = (rps + 31) & ~(uint64_t)31;
-  if (algo == 0) algo = second_order ? (Dg <= 512 ? 4 : 1) : (Dg <= 90 ? 3 : 1);
+  if (algo == 0) algo = second_order ? (Dg <= 512 ? 4 : 1) : 3;
   if (algo == 4) {
     SA_REQUIRE(second_order && Dg <= 512, SA_ERR_UNSUPPORTED, "tile kernel needs second order and Dg <= 512");
     SA_REQUIRE(d_Yn && d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn / d_Yt is null");
@@ -1139,17 +1151,13 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
     SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt (feature matrix) is null");
-    const int NF = feature_count(Dg);
+    const int ch = feature_width(Dg), nz = feature_chunks(Dg);
     const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * 32);
-    const int ch = nacc <= 8 ? 8 : (nacc <= 16 ? 16 : (nacc <= 24 ? 24 : 32));
-    const int nz = (nacc + ch - 1) / ch;
     SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the first-order kernel");
     dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
     auto kern = ch == 8 ? fo_gemv_kernel<8> : (ch == 16 ? fo_gemv_kernel<16> : (ch == 24 ? fo_gemv_kernel<24> : fo_gemv_kernel<32>));
-    const size_t smem = (size_t)kFoStages * kFoRows * NF * 8 + kFoStages * 12 + 16;
-    SA_REQUIRE(smem <= 200 * 1024, SA_ERR_UNSUPPORTED, "too many groups for the first-order kernel (Dg = %d)", Dg);
-    SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kFoWarps * 32, smem, st>>>(d_Yt, NF, N, d_w, Npad, count, rps, d_psum, nacc);
+    const size_t smem = (size_t)kFoStages * kFoRows * ch * 8 + kFoStages * 12 + 16;
+    kern<<<grid, kFoWarps * 32, smem, st>>>(d_Yt, N, d_w, Npad, count, rps, d_psum, nacc);
   } else if (algo == 1) {
     SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
     SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
