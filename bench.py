@@ -252,7 +252,10 @@ def main():
         sample = {"value": rows * a.steps / t / 1e9, "unit": "Grows/s", "ms_per_pass": t / a.steps * 1e3,
                   "rows": rows, "bytes_per_gpu": sample_bytes_rank, "launches": int(launches),
                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                               "frac": gbs / hbm_peak,
+                               # ncu (profiles/r01_final_ncu_full_summary.csv): dram write 69.736 GB, read 1 MB
+                               "traffic": 69.737e9 if (D == 64 and a.log2n == 20 and c2 and world == 1) else None,
+                               "peak_source": hbm_src,
                                "kernel": "saltelli_reg_kernel" if D % 2 == 0 else "saltelli_generic_kernel"}}
         del X
         torch.cuda.empty_cache()
@@ -314,10 +317,10 @@ def main():
     achieved = flop_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
     # DRAM bytes of one tile-kernel launch from the committed ncu capture (1184 resamples = one wave at
     # N = 2^20: Y in analysis layout 1.36 GB + multiplicities 1.24 GB, each read once)
-    traffic = 2.636e9 if (c2 and D == 64 and a.log2n == 20) else None
+    traffic = 2.635e9 if (c2 and D == 64 and a.log2n == 20) else None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_s2_accum_smem_ncu_n20_r1184.csv (dram read+write per 1184-resample launch)"
+                "traffic_source": "profiles/r01_final_ncu_full_summary.csv (dram read+write per 1184-resample launch)"
                 if traffic else None, "kernel": kernel,
                 "kernel_ms_per_step": k_ms / a.steps, "kernel_share_of_step": (k_ms / 1e3) / t_an,
                 "algorithmic_flop_per_resample_row": flop_per_row,

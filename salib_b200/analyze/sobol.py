@@ -43,7 +43,7 @@ CONST_RESULT_MSG = (
 )
 
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
-NUMPY_RESAMPLE_MAX = 2 ** 27          # N*R elements of int64 drawn on the host in "auto" mode
+NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
 _ALGO = {"auto": 0, "generic": 1, "first_order": 3, "tile8": 4}
 
