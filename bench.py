@@ -26,6 +26,16 @@ import numpy as np  # noqa: E402
 
 G_A8 = [0, 1, 4.5, 9, 99, 99, 99, 99]
 
+# stdout must carry exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner comes
+# from C code), so file descriptor 1 is pointed at stderr for the whole run and the result line is written to
+# the saved original descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -118,7 +128,7 @@ def run_reference_arm(a):
         "cpu_baseline": {"value": val, "unit": "resample-rows/s", "cores": procs, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "resample-rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -368,7 +378,7 @@ def main():
             "result_check": {"S1_0": float(S["S1"][0]), "ST_0": float(S["ST"][0]), "S1_conf_0": float(S["S1_conf"][0]),
                              "ST_conf_0": float(S["ST_conf"][0]), "analytic_S1_0": analytic[0], "analytic_ST_0": analytic[1]},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

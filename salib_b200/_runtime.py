@@ -42,6 +42,28 @@ def to_device(a, dtype=None):
     return t.to(dev, non_blocking=False)
 
 
+def to_device_sharded(a, dtype, min_bytes=64 << 20):
+    """Host array that every rank of the torch.distributed job holds -> full device copy on every rank,
+    moved as world_size shards over PCIe (one per rank) and all-gathered over NVLink.  Falls back to
+    ``to_device`` for device tensors, single-process runs and small arrays."""
+    import torch.distributed as dist
+
+    rank, world_size = world()
+    if world_size == 1 or (isinstance(a, torch.Tensor) and a.is_cuda):
+        return to_device(a, dtype)
+    flat = a.reshape(-1) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a).reshape(-1))
+    if flat.numel() * flat.element_size() < min_bytes:
+        return to_device(a, dtype)
+    n = flat.numel()
+    per = -(-n // world_size)
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    part = torch.zeros((per,), dtype=dtype, device=device())
+    part[: hi - lo] = flat[lo:hi].to(device=device(), dtype=dtype, non_blocking=True)
+    full = torch.empty((world_size * per,), dtype=dtype, device=device())
+    dist.all_gather_into_tensor(full, part)
+    return full[:n]
+
+
 def empty(shape, dtype):
     return torch.empty(shape, dtype=dtype, device=device())
 

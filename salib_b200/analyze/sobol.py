@@ -320,7 +320,9 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
     for Y in Ys:
         eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
         eng.kernel_events = kernel_events
-        eng.load(rt.to_device(Y, torch.float64).reshape(-1))
+        # multi-GPU: a host Y is uploaded as one shard per rank and all-gathered over NVLink
+        Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
+        eng.load(Yd.reshape(-1))
         engines.append(eng)
     Z = norm.ppf(0.5 + conf_level / 2)
 

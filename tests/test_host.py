@@ -276,7 +276,17 @@ def _gloo_worker(rank, world, port, R, nest, q):
     full = torch.arange(R * nest, dtype=torch.float64).reshape(R, nest)
     lo, hi = shard_range(R, rank, world)
     out = allgather_estimates(full[lo:hi].clone(), R, rank, world)
-    q.put((rank, bool(torch.equal(out, full))))
+    ok = bool(torch.equal(out, full))
+    # sharded upload of a host array: every rank ends with the full array (device() is patched to CPU here)
+    import numpy as np
+
+    from salib_b200 import _runtime as rt
+
+    rt.device = lambda: torch.device("cpu")
+    y = np.arange(1000 * R + 3, dtype=np.float64)
+    got = rt.to_device_sharded(y, torch.float64, min_bytes=0)
+    ok = ok and bool(torch.equal(got, torch.from_numpy(y)))
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
