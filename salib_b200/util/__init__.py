@@ -13,8 +13,9 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from .results import ResultDict  # noqa: F401
+from .util_funcs import read_param_file  # noqa: F401
 
-__all__ = ["ResultDict", "ProblemSpec", "extract_group_names", "compute_groups_matrix"]
+__all__ = ["ResultDict", "ProblemSpec", "extract_group_names", "compute_groups_matrix", "read_param_file"]
 
 
 def _unique_in_order(labels) -> List:

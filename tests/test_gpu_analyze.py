@@ -238,3 +238,29 @@ def test_problem_spec_chain_on_device():
             Si = an.analyze(sp2, sp2.results[:, i], num_resamples=20, seed=3)
             for k in ("S1", "S1_conf", "ST", "ST_conf"):
                 np.testing.assert_allclose(sp2.analysis[name][k], Si[k], rtol=1e-12, atol=1e-14)
+
+
+def test_cli_golden_files(tmp_path, capsys):
+    """reference tests/test_cli_analyze.py:250-275 end to end through the command line: the Saltelli file is
+    byte-identical to the reference's tests/data/model_input.txt and the printed table equals its golden string."""
+    import re
+
+    from salib_b200.scripts import salib as cli
+    from salib_b200.test_functions import Ishigami
+
+    params = tmp_path / "Ishigami.txt"
+    params.write_text("x1 -3.14159265359 3.14159265359\nx2 -3.14159265359 3.14159265359\nx3 -3.14159265359 3.14159265359\n")
+    xin, yout = tmp_path / "model_input.txt", tmp_path / "model_output.txt"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cli.main(f"sample saltelli -p {params} -o {xin} -n 1024 --precision 8 --max-order 2 --skip-values 2048".split())
+    ref = tmp_path / "ref.txt"
+    np.savetxt(ref, golden("model_input_8e.npy"), delimiter=" ", fmt="%.8e")
+    assert xin.read_bytes() == ref.read_bytes()
+    np.savetxt(yout, Ishigami.evaluate(np.loadtxt(xin)))
+    capsys.readouterr()
+    cli.main(f"analyze sobol -p {params} -Y {yout} -c 0 --max-order 2 -r 1000 --seed=100".split())
+    out = re.sub(r"[\n\t\s]*", "", capsys.readouterr().out)
+    assert out == ("STST_confx10.5579470.085851x20.4421890.041396x30.2414020.028607S1S1_confx10.3105760.059615"
+                   "x20.4436530.053436x3-0.0129620.053891S2S2_conf(x1,x2)-0.0143970.083679(x1,x3)0.2462310.103117"
+                   "(x2,x3)0.0005390.064169")

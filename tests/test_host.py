@@ -253,6 +253,33 @@ def test_work_decomposition_plans():
     assert plan_row_splits(1, 1000, 4096, sms, 50) == 1
 
 
+def test_read_param_file_and_cli_parsers(tmp_path):
+    # reference tests/conftest.py fixtures + util_funcs.read_param_file; CLI options of sample/analyze
+    from salib_b200.scripts import salib as cli
+    from salib_b200.util import read_param_file
+
+    f = tmp_path / "p.txt"
+    f.write_text("#x0 0 1\nx1 -3.14159265359 3.14159265359\nx2 0 1\nx3 2.5 7\n")
+    p = read_param_file(str(f))
+    assert p == {"names": ["x1", "x2", "x3"], "bounds": [[-3.14159265359, 3.14159265359], [0.0, 1.0], [2.5, 7.0]],
+                 "num_vars": 3, "groups": None, "dists": None}
+    g = tmp_path / "g.csv"
+    g.write_text("a,0,1,G1,unif\nb,0,2,G2,triang\nc,1,3,NA,norm\n")
+    p = read_param_file(str(g))
+    assert p["groups"] == ["G1", "G2", "c"] and p["dists"] == ["unif", "triang", "norm"] and p["num_vars"] == 3
+    one = tmp_path / "one.csv"
+    one.write_text("a,0,1,G\nb,0,2,G\n")
+    with pytest.raises(ValueError, match="Only one group"):
+        read_param_file(str(one))
+    a = cli._sample_parser("saltelli").parse_args("-n 8 -p p -o o --max-order 1 --skip-values 16".split())
+    assert (a.samples, a.max_order, a.skip_values, a.precision, a.delimiter) == (8, 1, 16, 8, " ")
+    with pytest.raises(SystemExit):
+        cli._sample_parser("saltelli").parse_args("-n 8 -p p -o o --seed 3".split())   # no seed for saltelli
+    b = cli._analyze_parser("sobol").parse_args("-p p -Y y -c 2 -r 1000 --seed=100".split())
+    assert (b.column, b.resamples, b.seed, b.max_order, b.parallel) == (2, 1000, 100, 2, False)
+    assert cli.main([]) == 0
+
+
 def test_shard_range_covers_everything():
     from salib_b200._runtime import shard_range
 
