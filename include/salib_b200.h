@@ -166,7 +166,8 @@ int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt
                             int nsplit, double *d_psum);
 /* Same, with an explicit kernel choice for tests: algo 0 = auto, 1 = generic (any shape),
  * 3 = first/total-order kernel, 4 = second-order 8x8 register-tile kernel with rows staged in
- * shared memory by cp.async.bulk (Dg <= 64; what "auto" picks).                              */
+ * shared memory by cp.async.bulk (what "auto" picks for second order), 5 = EXPERIMENTAL FP64
+ * tensor-core (mma.sync m8n8k4.f64) variant of 4, opt-in only (BASELINE rules tensor cores out).  */
 int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                                int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                                int nsplit, double *d_psum, int algo);

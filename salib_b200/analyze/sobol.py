@@ -45,7 +45,7 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
-_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "tile8": 4}
+_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "tile8": 4, "dmma": 5}
 
 
 def _nacc(Dg, c2):
@@ -113,7 +113,7 @@ def tile_groups(Dg):
 def plan_row_splits(kind, count, N, sms, nacc, groups=1):
     """Row splits so that `count` resamples fill `sms` SMs (at least 32 rows per split).  Pure host logic."""
     max_split = max(1, min(4096, N // 32))
-    if kind == 4:        # tile kernel: `groups` warps per resample, 8 warps per block, one block per SM
+    if kind in (4, 5):   # tile kernels: `groups` warps per resample, 8 warps per block, one block per SM
         blocks = -(-count // 8) * groups
     elif kind == 3:      # first-order GEMV kernel: 256 resamples per block, ~4 resident blocks per SM
         blocks = -(-count // 256) * -(-nacc // 32)
@@ -128,7 +128,7 @@ def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None, groups=1):
     one-warp-per-resample tile kernel sized in whole waves (8 * sms), the remainder being its own
     (row-split) launch.  Pure host logic."""
     cap = max(1, (max_bytes or MAX_COUNT_BYTES) // Npad)
-    wave = max(8, 8 * sms // groups) if kind == 4 else 256 * sms
+    wave = max(8, 8 * sms // groups) if kind in (4, 5) else 256 * sms
     out, c = [], lo
     while c < hi:
         left = hi - c
@@ -170,8 +170,8 @@ class SobolAnalyzer:
         work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)
         _lib.call("sa_moments_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.step, rt.ptr(self.stats),
                   rt.ptr(work), int(work.numel()))
-        need_rows = self.kind in (1, 4)
-        need_cols = self.kind in (3, 4)   # kind 4 only needs the A and B columns
+        need_rows = self.kind in (1, 4, 5)
+        need_cols = self.kind in (3, 4, 5)   # kinds 4, 5 only need the A and B columns
         if need_rows:
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
         if need_cols:

@@ -694,6 +694,185 @@ s2_accum_smem_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 }
 
 // ------------------------------------------------------------------------------------------
+// EXPERIMENTAL, opt-in (algo 5): second-order accumulate on the FP64 tensor cores
+// ------------------------------------------------------------------------------------------
+// BASELINE's north_star rules tensor cores out for this path, so the shipped default is the DFMA tile
+// kernel above.  This variant exists to quantify what that rule costs: the weighted Gram matrix
+// G = BA^T diag(w) AB is fed to mma.sync.m8n8k4.f64 (DMMA, 37.2 TFLOP/s measured, the same peak as the
+// FMA pipe) four nonzero rows at a time.  A warp still owns one resample; per K-step a lane loads 8 + 8
+// fragment doubles for 36 tile MMAs, i.e. 4x less shared-memory traffic per flop than the register tiles.
+// Same ring, weights, first/total-order side work and output layout as s2_accum_smem_kernel.  Dg <= 64.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(kS2Warps * 32, 1)
+s2_accum_dmma_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t N, int Dg,
+                     const uint8_t *__restrict__ w, uint64_t Npad, uint64_t count,
+                     uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
+  constexpr int kTileRows = 32;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t c = (uint64_t)blockIdx.x * kS2Warps + warp;
+  const bool live = c < count;
+  const int sp = blockIdx.y;
+  const uint64_t row0 = (uint64_t)sp * rows_per_split;
+  uint64_t row1 = row0 + rows_per_split;
+  if (row1 > N) row1 = N;
+  const int ntiles = (row1 > row0) ? (int)((row1 - row0 + kTileRows - 1) / kTileRows) : 0;
+  const int TB = Dp >> 3;
+  const uint32_t row_bytes = (uint32_t)stride * 8u;
+  const uint32_t stage_bytes = kTileRows * row_bytes;
+  const uint32_t sm_base = smem_u32(smraw);
+  const uint32_t bar_base = sm_base + kStages * stage_bytes;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(smraw + kStages * stage_bytes + kStages * 8);
+  auto issue = [&](int t) {
+    const int s = t % kStages;
+    const uint64_t r = row0 + (uint64_t)t * kTileRows;
+    const uint32_t rows = (uint32_t)((row1 - r < (uint64_t)kTileRows) ? (row1 - r) : kTileRows);
+    mbar_arrive_expect_tx(bar_base + 8u * s, rows * row_bytes);
+    bulk_g2s(sm_base + s * stage_bytes, Yn + r * (uint64_t)stride, rows * row_bytes, bar_base + 8u * s);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_base + 8u * s, 1);
+      cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+
+  const int PL = TB * kBlockPitch;
+  const int gid = lane >> 2, kq = lane & 3;  // fragment coordinates: M/N index and K index of this lane
+  const uint32_t offA = (uint32_t)(PL + gid) * 8u;  // + 80 B per j-block
+  const uint32_t offB = (uint32_t)gid * 8u;         // + 80 B per k-block
+  const int cblk0 = ((lane >> 3) & 1) * 4 + (lane >> 4);
+  const int jC0 = 8 * cblk0 + (lane & 7), jC1 = jC0 + 16;
+  const uint32_t offC0 = (jC0 < Dp) ? (uint32_t)col_pos(jC0) * 8u : 0u;
+  const uint32_t offC1 = (jC1 < Dp) ? (uint32_t)col_pos(jC1) * 8u : 0u;
+  const uint32_t offAB = 2u * PL * 8u;
+
+  double acc[36][2];
+#pragma unroll
+  for (int t = 0; t < 36; ++t) acc[t][0] = acc[t][1] = 0.0;
+  double s1_0 = 0.0, s1_1 = 0.0, st_0 = 0.0, st_1 = 0.0;
+
+  const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
+  auto load_w = [&](int t) -> unsigned {
+    const uint64_t i = row0 + (uint64_t)t * kTileRows + lane;
+    if (!live || t >= ntiles || i >= row1) return 0u;
+    return wrow ? (unsigned)__ldg(wrow + i) : 1u;
+  };
+  unsigned wl_next = load_w(0);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kStages;
+    const unsigned wl = wl_next;
+    wl_next = load_w(t + 1);
+    unsigned mask = __ballot_sync(kFull, wl != 0);
+    const int whi = __double2hiint((double)wl);
+    while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)(t / kStages) & 1u)) {
+    }
+    const uint32_t tile = sm_base + s * stage_bytes;
+    while (mask) {
+      // the next (up to) four nonzero rows form one K-step
+      int r[4];
+      int n = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r[q] = mask ? __ffs(mask) - 1 : 0;
+        if (mask) {
+          ++n;
+          mask &= mask - 1;
+        }
+      }
+      const int myrow = (kq == 0) ? r[0] : (kq == 1 ? r[1] : (kq == 2 ? r[2] : r[3]));
+      const int hi = __shfl_sync(kFull, whi, myrow);
+      const double wq = (kq < n) ? __hiloint2double(hi, 0) : 0.0;
+      const uint32_t rowa = tile + (uint32_t)myrow * row_bytes;
+      double fa[8], fb[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < TB) {  // uniform
+          fa[b] = wq * lds_f64(rowa + offA + 80u * b);
+          fb[b] = lds_f64(rowa + offB + 80u * b);
+        } else {
+          fa[b] = 0.0;
+          fb[b] = 0.0;
+        }
+      }
+      int ti = 0;
+#pragma unroll
+      for (int jb = 0; jb < 8; ++jb)
+#pragma unroll
+        for (int kb = jb; kb < 8; ++kb) {
+          if (kb < TB) dmma884(acc[ti], fa[jb], fb[kb]);  // uniform
+          ++ti;
+        }
+      // first/total order for the rows of this K-step
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < n) {  // uniform
+          const double wv = __hiloint2double(__shfl_sync(kFull, whi, r[q]), 0);
+          const uint32_t row = tile + (uint32_t)r[q] * row_bytes;
+          const double2 ab = lds_f64x2(row + offAB);
+          const double wb = wv * ab.y;
+          const double t0 = lds_f64(row + offC0) - ab.x;
+          const double t1 = lds_f64(row + offC1) - ab.x;
+          s1_0 = fma(wb, t0, s1_0);
+          s1_1 = fma(wb, t1, s1_1);
+          st_0 = fma(wv * t0, t0, st_0);
+          st_1 = fma(wv * t1, t1, st_1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
+                   : "=r"(old)
+                   : "r"(smem_u32(cnt + s))
+                   : "memory");
+      if (old == kS2Warps - 1) {
+        cnt[s] = 0;
+        if (t + kStages < ntiles) issue(t + kStages);
+      }
+    }
+  }
+  if (!live) return;
+  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+  if (jC0 < Dg) {
+    out[5 + jC0] = s1_0;
+    out[5 + Dg + jC0] = st_0;
+  }
+  if (jC1 < Dg) {
+    out[5 + jC1] = s1_1;
+    out[5 + Dg + jC1] = st_1;
+  }
+  double *o2 = out + 5 + 2 * Dg;
+  int ti = 0;
+#pragma unroll
+  for (int jb = 0; jb < 8; ++jb)
+#pragma unroll
+    for (int kb = jb; kb < 8; ++kb) {
+      // C fragment: row = lane / 4, columns 2 * (lane % 4) and + 1
+      const int j = 8 * jb + gid;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 8 * kb + 2 * kq + e;
+        if (kb < TB && j < k && k < Dg) o2[pair_index(j, k, Dg)] = acc[ti][e];
+      }
+      ++ti;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // first/total-order accumulate: a skinny GEMM  acc[c][q] += w[c][i] * F[i][q]
 // ------------------------------------------------------------------------------------------
 // Every first/total-order sum is linear in the multiplicities: with the per-row features
@@ -1103,7 +1282,7 @@ extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_
   return SA_OK;
 }
 
-// algo: 0 auto, 1 generic, 3 first/total order, 4 second-order 8x8 register tiles
+// algo: 0 auto, 1 generic, 3 first/total order, 4 second-order 8x8 register tiles, 5 experimental DMMA
 extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,
                                           int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                                           int nsplit, double *d_psum, int algo) {
@@ -1147,6 +1326,19 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
                                                                                nacc);
     kern<<<dim3((unsigned)bx, (unsigned)nsplit, (unsigned)ngroups), kS2Warps * 32, smem, st>>>(
         d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc, stages);
+    note_launches(1);
+  } else if (algo == 5) {  // experimental FP64 tensor-core variant (not the default, see the kernel header)
+    SA_REQUIRE(second_order && Dg <= 64, SA_ERR_UNSUPPORTED, "DMMA kernel needs second order and Dg <= 64");
+    SA_REQUIRE(d_Yn && d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn / d_Yt is null");
+    const uint64_t bx = ceil_div_u64(count, kS2Warps);
+    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
+    constexpr int stages = 5;
+    const size_t smem = (size_t)stages * 32 * stride * 8 + stages * 12 + 16;
+    SA_CUDA(cudaFuncSetAttribute(s2_accum_dmma_kernel<stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scalar_sums_kernel<<<dim3((unsigned)ceil_div_u64(count, kScC), (unsigned)nsplit), 256, 0, st>>>(
+        d_Yt, Npad, N, d_w, count, rps, d_psum, nacc);
+    s2_accum_dmma_kernel<stages><<<dim3((unsigned)bx, (unsigned)nsplit), kS2Warps * 32, smem, st>>>(
+        d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc);
     note_launches(1);
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");

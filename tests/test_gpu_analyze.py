@@ -45,9 +45,12 @@ def test_matches_frozen_reference(name):
 
 @pytest.mark.parametrize("name,algo", [("g8_n512_r64", "generic"), ("g16_n256_r32", "generic"),
                                        ("g8_n512_c1_r64", "generic"), ("g64_n128_r16", "generic"),
-                                       ("grp3_n512_r40", "generic")])
+                                       ("grp3_n512_r40", "generic"), ("g64_n128_r16", "dmma"),
+                                       ("g16_n256_r32", "dmma"), ("g8_n512_r64", "dmma"),
+                                       ("ishigami_n1024_r100", "dmma")])
 def test_generic_kernel_matches_frozen_reference(name, algo):
-    """The fallback kernel is an independent implementation of the same sums."""
+    """The fallback kernel is an independent implementation of the same sums; "dmma" is the experimental
+    opt-in FP64 tensor-core variant of the tile kernel."""
     from salib_b200.analyze import sobol
 
     z = golden("analyze_" + name)

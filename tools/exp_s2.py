@@ -22,7 +22,7 @@ psum = rt.empty((R * eng.nacc,), torch.float64)
 sms = eng.sms
 def run(label, rows):
     def f():
-        _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(eng.Yn), rt.ptr(eng.Yt), N, D, 1, rt.ptr(w), R, 1, rt.ptr(psum), 4)
+        _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(eng.Yn), rt.ptr(eng.Yt), N, D, 1, rt.ptr(w), R, 1, rt.ptr(psum), int(os.environ.get("ALGO", 4)))
     for _ in range(2): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
