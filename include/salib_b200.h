@@ -75,6 +75,11 @@ int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const uint32_t *d
                            const double *d_span, const int32_t *d_dist_code, const double *d_dist_par,
                            double *d_out);
 
+/* In-place scaling of d_X [rows, D] (values in [0,1]) to bounds or per-column distributions; replaces
+ * util/__init__.py:25-90 (`scale_samples`, `_scale_samples`, `_nonuniform_scale_samples`) as a stand-alone call. */
+int sa_scale_samples_f64(void *stream, double *d_X, uint64_t rows, int D, const double *d_lb,
+                         const double *d_span, const int32_t *d_dist_code, const double *d_dist_par);
+
 /* Plain Sobol' points first_index .. first_index+n-1 in `dims` dimensions, d_out [n, dims] row-major, values
  * x * 2^-30.  Replaces sample/sobol_sequence.py:49-91 (`sobol_sequence.sample`, the generator behind
  * sample/saltelli.py:157 and sample/finite_diff.py).                                              */

@@ -19,6 +19,7 @@ SIGNATURES = {
     "sa_last_error": (C.c_char_p, []),
     "sa_direction_vectors": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "sa_saltelli_sample_f64": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "sa_scale_samples_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _vp, _vp]),
     "sa_sobol_points_f64": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _i32, _vp]),
     "sa_eval_ishigami_f64": (C.c_int, [_vp, _vp, _u64, _dbl, _dbl, _vp]),
     "sa_eval_sobol_g_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _vp, _vp, _vp]),

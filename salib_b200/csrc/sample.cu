@@ -397,6 +397,23 @@ sobol_points_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
   }
 }
 
+// Stand-alone scaling of a [rows, D] matrix of unit-cube values (util/__init__.py:56-90): the same
+// per-column transforms as the fused sample kernels, in place.
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(double *__restrict__ X, uint64_t total, int D, const ColScale cs) {
+  const uint64_t S = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int col = (int)(idx % (uint64_t)D);
+  const int dcol = (int)(S % (uint64_t)D);
+  for (; idx < total; idx += S) {
+    const double u = X[idx];
+    X[idx] = cs.code ? dist_transform(u, cs.code[col], cs.par + 4 * (size_t)col)
+                     : __dadd_rn(__dmul_rn(u, cs.span[col]), cs.lb[col]);
+    col += dcol;
+    if (col >= D) col -= D;
+  }
+}
+
 static bool reg_path_ok(int D) {
   if (D < 2 || (D & 1)) return false;
   const int h = D / 2;
@@ -477,6 +494,22 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     kern<<<(unsigned)blocks, 256, smem, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
                                              second_order, cs, d_out, BR, m_rowlen, m_D);
   }
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_scale_samples_f64(void *stream, double *d_X, uint64_t rows, int D, const double *d_lb,
+                                    const double *d_span, const int32_t *d_dist_code, const double *d_dist_par) {
+  SA_REQUIRE(d_X && D >= 1, SA_ERR_ARG, "sa_scale_samples_f64: bad arguments");
+  SA_REQUIRE((d_dist_code && d_dist_par) || (!d_dist_code && d_lb && d_span), SA_ERR_ARG,
+             "sa_scale_samples_f64: need either lb/span or dist_code/dist_par");
+  if (rows == 0) return SA_OK;
+  const uint64_t total = rows * (uint64_t)D;
+  uint64_t blocks = ceil_div_u64(total, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  const ColScale cs{d_lb, d_span, d_dist_code, d_dist_par};
+  scale_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_X, total, D, cs);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

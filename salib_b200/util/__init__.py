@@ -15,7 +15,8 @@ import numpy as np
 from .results import ResultDict  # noqa: F401
 from .util_funcs import read_param_file  # noqa: F401
 
-__all__ = ["ResultDict", "ProblemSpec", "extract_group_names", "compute_groups_matrix", "read_param_file"]
+__all__ = ["ResultDict", "ProblemSpec", "extract_group_names", "compute_groups_matrix", "read_param_file",
+           "scale_samples"]
 
 
 def _unique_in_order(labels) -> List:
@@ -70,6 +71,40 @@ def group_columns(problem: Dict):
     names = _unique_in_order(groups)
     pos = {g: i for i, g in enumerate(names)}
     return np.array([pos[g] for g in groups], dtype=np.int32), len(names)
+
+
+def scale_samples(params, problem: Dict):
+    """Scale unit-cube samples [n, D] to the problem's bounds / distributions on the device
+    (reference util/__init__.py:56-90).  Uniform bounds are scaled in place like the reference (and bit-exactly);
+    sets ``problem["sample_scaled"] = True`` and returns the scaled array."""
+    import torch
+
+    from .. import _lib, _runtime as rt
+    from ..sample.sobol import _scaling
+
+    lower, span, code, par = _scaling(problem)
+    if problem.get("dists") is not None and params.shape[1] != len(problem["dists"]):
+        raise ValueError("Mismatch in number of parameters and distributions.")
+    is_np = isinstance(params, np.ndarray)
+    X = rt.to_device(params, torch.float64)
+    if X.data_ptr() == getattr(params, "data_ptr", lambda: None)():
+        pass  # a CUDA tensor is scaled in place
+    elif not is_np:
+        X = X.clone()
+    dev = lambda v, dt: None if v is None else rt.to_device(v, dt)  # noqa: E731
+    # keep the device copies alive until the call has been enqueued (their pointers cross the C ABI)
+    d_lb, d_span = dev(lower, torch.float64), dev(span, torch.float64)
+    d_code, d_par = dev(code, torch.int32), dev(par, torch.float64)
+    _lib.call("sa_scale_samples_f64", rt.stream_ptr(), rt.ptr(X), int(X.shape[0]), int(X.shape[1]),
+              rt.ptr(d_lb), rt.ptr(d_span), rt.ptr(d_code), rt.ptr(d_par))
+    problem["sample_scaled"] = True
+    if not is_np:
+        return X
+    out = X.cpu().numpy()
+    if code is None:
+        params[...] = out  # the reference scales uniform bounds in place (np.multiply(..., out=params))
+        return params
+    return out
 
 
 from .problem import ProblemSpec  # noqa: E402,F401

@@ -156,6 +156,31 @@ def test_large_structure_properties():
         assert torch.equal(torch.sort(M, dim=0).values, grid[:, None].expand(N, D))
 
 
+def test_scale_samples_standalone():
+    """util.scale_samples (reference util/__init__.py:56-90, tests/test_util.py:123-166): uniform bounds bit-exact
+    and in place, distributions against the frozen reference matrix."""
+    from oracle import saltelli as o
+    from salib_b200.sample import sobol_sequence
+    from salib_b200.util import scale_samples
+
+    rng = np.random.default_rng(3)
+    U = rng.random((500, 4))
+    p = gprob(4, bounds=[[10.0, 100.0], [-3.0, 7.5], [0.0, 1e-3], [5.0, 6.0]])
+    expect = o.scale_uniform(U.copy(), p["bounds"])
+    got = U.copy()
+    ret = scale_samples(got, p)
+    assert ret is got and np.array_equal(got, expect) and p["sample_scaled"] is True
+    with pytest.raises(ValueError):
+        scale_samples(U.copy(), gprob(4, bounds=[[0, 1], [2, 1], [0, 1], [0, 1]]))
+    # distributions: rebuild the frozen dists matrix from plain Sobol' points + cross matrix + scale_samples
+    z = golden("sample_dists_n32_c1_skip0")
+    base = sobol_sequence.sample(32, 18)
+    X01 = o.cross_matrix(base, 9, np.arange(9, dtype=np.int32), 9, False)
+    pd_ = {k: (list(v) if isinstance(v, list) else v) for k, v in DIST_PROBLEM.items()}
+    X = scale_samples(X01, pd_)
+    np.testing.assert_allclose(X, z["X"], rtol=1e-11, atol=1e-13)
+
+
 def test_sobol_sequence_dropin():
     """reference tests/test_sobol.py:21-36 (first ten Joe-Kuo points) + oracle over many dims / a skip."""
     from oracle import sobol_seq
