@@ -267,3 +267,28 @@ def test_cli_golden_files(tmp_path, capsys):
     assert out == ("STST_confx10.5579470.085851x20.4421890.041396x30.2414020.028607S1S1_confx10.3105760.059615"
                    "x20.4436530.053436x3-0.0129620.053891S2S2_conf(x1,x2)-0.0143970.083679(x1,x3)0.2462310.103117"
                    "(x2,x3)0.0005390.064169")
+
+
+@pytest.mark.parametrize("D,N,c2,R", [(2, 2, True, 3), (2, 1, False, 2), (3, 31, True, 1), (2, 33, False, 1),
+                                      (1, 40, True, 5), (9, 5, True, 4)])
+def test_edge_shapes_match_oracle(D, N, c2, R):
+    """Smallest problems: N below one ring tile, a single resample (std(ddof=1) of one value is NaN like
+    NumPy's), one factor (no pairs), N = 1."""
+    from oracle import analyze as o_analyze
+    from salib_b200.analyze import sobol
+
+    rng = np.random.default_rng(100 * D + N)
+    step = 2 * D + 2 if c2 else D + 2
+    Y = rng.normal(size=N * step) * 2.0 + 1.0
+    r = rng.integers(N, size=(N, R))
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0, 1]] * D}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S = sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r)
+        So = o_analyze.analyze(D, Y, c2, R, keep_resamples=True, r=r)
+    for k in ("S1", "ST", "S1_conf_all", "ST_conf_all", "S1_conf", "ST_conf"):
+        np.testing.assert_allclose(S[k], So[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+    if c2 and D > 1:
+        iu = np.triu_indices(D, 1)
+        np.testing.assert_allclose(S["S2"][iu], So["S2"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(S["S2_conf"][iu], So["S2_conf"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
