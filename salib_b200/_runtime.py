@@ -2,8 +2,6 @@
 
 Every helper here raises if CUDA is unavailable -- there is no CPU path.
 """
-import os
-
 import numpy as np
 import torch
 
@@ -86,10 +84,3 @@ def shard_range(total, rank, world_size):
     base, rem = divmod(int(total), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
-
-
-def env_int(name, default):
-    try:
-        return int(os.environ.get(name, default))
-    except ValueError:
-        return default
