@@ -186,6 +186,24 @@ int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg
 int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
                       double *d_conf);
 
+/* ---- DGSM on the same machinery ------------------------------------------------
+ * sa_finite_diff_expand_f64: rows of sample/finite_diff.py:76-91 from scaled Sobol' points d_base [n, D]:
+ *   d_out [n*(D+1), D]; row 1+j moves column j by base_j*delta, clipped to [d_lo[j], d_hi[j]].
+ * sa_dgsm_features_f64: F[chunk][N][CW] with features ((Y_j - Y_base)/(x_j - x_base))^2 (q < D) and their
+ *   squares (D <= q < 2D) from the finite_diff matrix d_X and output d_Y (analyze/dgsm.py:105-121);
+ *   sa_chunked_feature_doubles(2*D) doubles per row in total.
+ * sa_feature_sums_f64: psum[nsplit][count][nfeat] = sum_i w[c][i] * F[i][q] (d_w NULL: weight 1, count 1) --
+ *   the bootstrap means of dgsm.py:133-137 for all resamples at once.
+ * sa_reduce_splits_f64: d_out[count][nfeat] = scale * sum over splits.                                  */
+int sa_chunked_feature_doubles(int nfeat);
+int sa_finite_diff_expand_f64(void *stream, const double *d_base, uint64_t n, int D, double delta,
+                              const double *d_lo, const double *d_hi, double *d_out);
+int sa_dgsm_features_f64(void *stream, const double *d_X, const double *d_Y, uint64_t N, int D, double *d_F);
+int sa_feature_sums_f64(void *stream, const double *d_F, uint64_t N, int nfeat, const uint8_t *d_w,
+                        uint64_t count, int nsplit, double *d_psum);
+int sa_reduce_splits_f64(void *stream, const double *d_psum, uint64_t count, int nfeat, int nsplit,
+                         double scale, double *d_out);
+
 /* ---- measurement helpers (bench.py only) ----------------------------------------------------
  * sa_launch_count: kernels enqueued by this library since the last reset (bench.py "gpu_launches").
  * sa_microbench_fp64 / sa_microbench_l2_read: the FP64-FMA and L2-read roofline denominators that

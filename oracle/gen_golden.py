@@ -133,6 +133,21 @@ run_analyze("grp3_n512_r40", {**ISHI, "groups": ["A", "B", "A"]}, 512, True, 40,
 a64 = np.linspace(1.0, 60.0, 64)
 run_analyze("g64_n128_r16", gprob(64), 128, True, 16, 5, lambda X: Sobol_G.evaluate(X, a=a64))
 
+# ---- 4b. finite_diff sample + dgsm analyze (consumers of the same Sobol' generator)
+from SALib.analyze import dgsm as ref_dgsm  # noqa: E402
+from SALib.sample import finite_diff as ref_fd  # noqa: E402
+
+for name, p, N, delta, skip, R, seed in [("ishigami_n256", dict(ISHI), 256, 0.001, 1024, 50, 9),
+                                         ("g8_n128", gprob(8, bounds=[[0.0, 1.0 + 0.25 * i] for i in range(8)]), 128, 0.01, 64, 30, 4)]:
+    X = ref_fd.sample(dict(p), N, delta=delta, skip_values=skip)
+    Y = Ishigami.evaluate(X) if p["num_vars"] == 3 else Sobol_G.evaluate(X / np.array(p["bounds"])[:, 1])
+    S = ref_dgsm.analyze(dict(p), X, Y, num_resamples=R, conf_level=0.95, seed=seed)
+    np.random.seed(seed)
+    rs = np.stack([np.random.randint(N, size=(R, N)) for _ in range(p["num_vars"])])
+    save("dgsm_" + name, X=X, Y=Y, N=N, delta=delta, skip=skip, R=R, seed=seed, D=p["num_vars"],
+         bounds=np.array(p["bounds"], dtype=np.float64), r=rs.astype(np.int32),
+         **{k: np.asarray(v) for k, v in S.items() if k != "names"})
+
 # ---- 5. the CLI golden (tests/test_cli_analyze.py:250-275, F7): Y from the 8-digit X, R=1000, seed=100
 Y = Ishigami.evaluate(mi)
 S = ref_analyze.analyze(dict(ISHI), Y, calc_second_order=True, num_resamples=1000, conf_level=0.95, seed=100)

@@ -39,6 +39,11 @@ SIGNATURES = {
     "sa_sobol_accumulate_ex_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp, _i32]),
     "sa_sobol_finalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _u64, _i32, _vp, _vp]),
     "sa_sobol_conf_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp]),
+    "sa_chunked_feature_doubles": (C.c_int, [_i32]),
+    "sa_finite_diff_expand_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp, _vp, _vp]),
+    "sa_dgsm_features_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp]),
+    "sa_feature_sums_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _u64, _i32, _vp]),
+    "sa_reduce_splits_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _dbl, _vp]),
     "sa_launch_count": (C.c_longlong, [_i32]),
     "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),
     "sa_microbench_fp64_outer": (C.c_int, [_vp, _i32, _vp, _vp]),

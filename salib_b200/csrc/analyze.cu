@@ -888,14 +888,13 @@ constexpr int kFoRows = 32;   // rows per weight fetch (32 bytes per resample)
 
 // Feature matrix layout: chunks of CW features, F[chunk][row][CW] (each chunk is what one grid.z slice of
 // fo_gemv_kernel streams).  CW = 8/16/24 when all 5 + 2*Dg features fit one chunk, else 32.
-__host__ __device__ inline int feature_width(int Dg) {
-  const int n = 5 + 2 * Dg;
-  return n <= 24 ? ((n + 7) & ~7) : 32;
+__host__ __device__ inline int chunk_width(int nfeat) { return nfeat <= 24 ? ((nfeat + 7) & ~7) : 32; }
+__host__ __device__ inline int chunk_count(int nfeat) {
+  const int cw = chunk_width(nfeat);
+  return (nfeat + cw - 1) / cw;
 }
-__host__ __device__ inline int feature_chunks(int Dg) {
-  const int cw = feature_width(Dg);
-  return (5 + 2 * Dg + cw - 1) / cw;
-}
+__host__ __device__ inline int feature_width(int Dg) { return chunk_width(5 + 2 * Dg); }
+__host__ __device__ inline int feature_chunks(int Dg) { return chunk_count(5 + 2 * Dg); }
 
 __global__ void __launch_bounds__(256)
 normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step,
@@ -1035,6 +1034,70 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
 #pragma unroll
   for (int q = 0; q < CH; ++q)
     if (q0 + q < nacc) out[q0 + q] = acc[q];
+}
+
+// ------------------------------------------------------------------------------------------
+// DGSM (analyze/dgsm.py): the bootstrap of mean((dY/dx_j)^2) is the same skinny GEMM with other features
+// ------------------------------------------------------------------------------------------
+// F[chunk][i][CW], features q < D: ((Y_j[i] - base[i]) / (X_j[i][j] - X_base[i][j]))^2 (dgsm.py:118-120),
+// D <= q < 2D: its square (for vi_std).  X is the finite_diff matrix [N*(D+1), D], Y the model output.
+__global__ void __launch_bounds__(256)
+dgsm_features_kernel(const double *__restrict__ X, const double *__restrict__ Y, uint64_t N, int D,
+                     double *__restrict__ F) {
+  const int nfeat = 2 * D, CW = chunk_width(nfeat), NZ = chunk_count(nfeat);
+  const uint64_t per_chunk = N * (uint64_t)CW, total = per_chunk * NZ;
+  const int step = D + 1;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(idx / per_chunk);
+    const uint64_t rem = idx - (uint64_t)z * per_chunk;
+    const uint64_t i = rem / (uint64_t)CW;
+    const int q = z * CW + (int)(rem - i * (uint64_t)CW);
+    double v = 0.0;
+    if (q < nfeat) {
+      const int j = q < D ? q : q - D;
+      const uint64_t r0 = i * (uint64_t)step, rj = r0 + 1 + j;
+      const double dy = __dsub_rn(Y[rj], Y[r0]);
+      const double dx = __dsub_rn(X[rj * (uint64_t)D + j], X[r0 * (uint64_t)D + j]);
+      const double g = __ddiv_rn(dy, dx);
+      v = __dmul_rn(g, g);
+      if (q >= D) v = __dmul_rn(v, v);
+    }
+    F[idx] = v;
+  }
+}
+
+// out[c][q] = scale * sum_sp psum[sp][c][q]
+__global__ void __launch_bounds__(256)
+reduce_splits_kernel(const double *__restrict__ psum, uint64_t count, int nfeat, int nsplit, double scale,
+                     double *__restrict__ out) {
+  const uint64_t total = count * (uint64_t)nfeat;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) v += psum[(uint64_t)sp * total + idx];
+    out[idx] = v * scale;
+  }
+}
+
+// finite_diff rows (sample/finite_diff.py:76-91): per base point its D+1 rows -- the point, then the point
+// with column j moved by base_j * delta and clipped to [lo_j, hi_j].
+__global__ void __launch_bounds__(256)
+finite_diff_expand_kernel(const double *__restrict__ base, uint64_t n, int D, double delta,
+                          const double *__restrict__ lo, const double *__restrict__ hi, double *__restrict__ out) {
+  const uint64_t rowlen = (uint64_t)(D + 1) * D, total = n * rowlen;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = idx / rowlen;
+    const uint32_t q = (uint32_t)(idx - i * rowlen);
+    const int s = q / D, j = q - s * D;
+    double v = base[i * (uint64_t)D + j];
+    if (s == j + 1) {
+      v = __dadd_rn(v, __dmul_rn(v, delta));
+      v = fmax(fmin(v, hi[j]), lo[j]);
+    }
+    out[idx] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1182,6 +1245,21 @@ conf_kernel(const double *__restrict__ est, uint64_t R, int ncols, double z, dou
 
 using namespace sa;
 
+// psum[nsplit][count][nfeat] = sum over the rows of each split of w[c][i] * F[i][q]
+static int launch_feature_gemv(cudaStream_t st, const double *d_F, uint64_t N, int nfeat, const uint8_t *d_w,
+                               uint64_t Npad, uint64_t count, int nsplit, uint64_t rps, double *d_psum) {
+  const int ch = chunk_width(nfeat), nz = chunk_count(nfeat);
+  const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * 32);
+  SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
+  dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
+  auto kern = ch == 8 ? fo_gemv_kernel<8> : (ch == 16 ? fo_gemv_kernel<16> : (ch == 24 ? fo_gemv_kernel<24> : fo_gemv_kernel<32>));
+  const size_t smem = (size_t)kFoStages * kFoRows * ch * 8 + kFoStages * 12 + 16;
+  kern<<<grid, kFoWarps * 32, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
 extern "C" int sa_row_stride(int Dg, int second_order) { return row_stride(Dg, second_order); }
 extern "C" uint64_t sa_pad_rows(uint64_t N) { return pad_rows(N); }
 extern "C" int sa_feature_count(int Dg) { return feature_width(Dg) * feature_chunks(Dg); }
@@ -1190,7 +1268,7 @@ extern "C" size_t sa_moments_workspace_bytes(void) { return (size_t)kMomBlocks *
 extern "C" int sa_moments_f64(void *stream, const double *d_Y, uint64_t N, int step, double *d_stats,
                               void *d_work, size_t work_bytes) {
   SA_REQUIRE(d_Y && d_stats && d_work, SA_ERR_ARG, "sa_moments_f64: null pointer");
-  SA_REQUIRE(N >= 1 && step >= 2, SA_ERR_ARG, "sa_moments_f64: bad N/step");
+  SA_REQUIRE(N >= 1 && step >= 1, SA_ERR_ARG, "sa_moments_f64: bad N/step");
   SA_REQUIRE(work_bytes >= sa_moments_workspace_bytes(), SA_ERR_WORKSPACE, "sa_moments_f64: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t total = N * (uint64_t)step;
@@ -1343,13 +1421,7 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
   } else if (algo == 3) {
     SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
     SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt (feature matrix) is null");
-    const int ch = feature_width(Dg), nz = feature_chunks(Dg);
-    const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * 32);
-    SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the first-order kernel");
-    dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-    auto kern = ch == 8 ? fo_gemv_kernel<8> : (ch == 16 ? fo_gemv_kernel<16> : (ch == 24 ? fo_gemv_kernel<24> : fo_gemv_kernel<32>));
-    const size_t smem = (size_t)kFoStages * kFoRows * ch * 8 + kFoStages * 12 + 16;
-    kern<<<grid, kFoWarps * 32, smem, st>>>(d_Yt, N, d_w, Npad, count, rps, d_psum, nacc);
+    return launch_feature_gemv(st, d_Yt, N, nacc, d_w, Npad, count, nsplit, rps, d_psum);
   } else if (algo == 1) {
     SA_REQUIRE(d_Yn, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yn is null");
     SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
@@ -1389,6 +1461,53 @@ extern "C" int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, 
   SA_REQUIRE(R >= 1 && ncols >= 1, SA_ERR_ARG, "sa_sobol_conf_f64: bad shape");
   dim3 block(32, 16);
   conf_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, z, d_conf);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// ---- DGSM / finite_diff ------------------------------------------------------------
+extern "C" int sa_chunked_feature_doubles(int nfeat) { return chunk_width(nfeat) * chunk_count(nfeat); }
+
+extern "C" int sa_finite_diff_expand_f64(void *stream, const double *d_base, uint64_t n, int D, double delta,
+                                         const double *d_lo, const double *d_hi, double *d_out) {
+  SA_REQUIRE(d_base && d_lo && d_hi && d_out && D >= 1, SA_ERR_ARG, "sa_finite_diff_expand_f64: bad arguments");
+  if (n == 0) return SA_OK;
+  uint64_t blocks = ceil_div_u64(n * (uint64_t)(D + 1) * D, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  finite_diff_expand_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_base, n, D, delta, d_lo, d_hi, d_out);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_dgsm_features_f64(void *stream, const double *d_X, const double *d_Y, uint64_t N, int D,
+                                    double *d_F) {
+  SA_REQUIRE(d_X && d_Y && d_F && N >= 1 && D >= 1, SA_ERR_ARG, "sa_dgsm_features_f64: bad arguments");
+  uint64_t blocks = ceil_div_u64(N * (uint64_t)sa_chunked_feature_doubles(2 * D), 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  dgsm_features_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, N, D, d_F);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_feature_sums_f64(void *stream, const double *d_F, uint64_t N, int nfeat, const uint8_t *d_w,
+                                   uint64_t count, int nsplit, double *d_psum) {
+  SA_REQUIRE(d_F && d_psum && N >= 1 && nfeat >= 1 && count >= 1 && nsplit >= 1 && nsplit <= 65535, SA_ERR_ARG,
+             "sa_feature_sums_f64: bad arguments");
+  SA_REQUIRE(d_w != nullptr || count == 1, SA_ERR_ARG, "sa_feature_sums_f64: unweighted sums need count == 1");
+  uint64_t rps = ceil_div_u64(N, nsplit);
+  rps = (rps + 31) & ~(uint64_t)31;
+  return launch_feature_gemv((cudaStream_t)stream, d_F, N, nfeat, d_w, pad_rows(N), count, nsplit, rps, d_psum);
+}
+
+extern "C" int sa_reduce_splits_f64(void *stream, const double *d_psum, uint64_t count, int nfeat, int nsplit,
+                                    double scale, double *d_out) {
+  SA_REQUIRE(d_psum && d_out && count >= 1 && nfeat >= 1 && nsplit >= 1, SA_ERR_ARG, "sa_reduce_splits_f64: bad arguments");
+  uint64_t blocks = ceil_div_u64(count * (uint64_t)nfeat, 256);
+  if (blocks > (uint64_t)sm_count() * 8) blocks = (uint64_t)sm_count() * 8;
+  reduce_splits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_psum, count, nfeat, nsplit, scale, d_out);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

@@ -157,6 +157,16 @@ class ProblemSpec(dict):
                     print(df)
         return self
 
+    def sample_finite_diff(self, *args, **kwargs):
+        from ..sample import finite_diff
+
+        return self.sample(finite_diff.sample, *args, **kwargs)
+
+    def analyze_dgsm(self, *args, **kwargs):
+        from ..analyze import dgsm
+
+        return self.analyze(dgsm.analyze, *args, **kwargs)
+
     # -- views -----------------------------------------------------------------------------
     def to_df(self):
         res = self._analysis

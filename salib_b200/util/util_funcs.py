@@ -8,7 +8,7 @@ Lines whose name starts with ``#`` are comments.  Returns the SALib problem dict
 import csv
 from typing import Dict, Optional
 
-__all__ = ["read_param_file"]
+__all__ = ["read_param_file", "handle_seed"]
 
 _FIELDS = ("name", "lower_bound", "upper_bound", "group", "dist")
 
@@ -37,3 +37,15 @@ def read_param_file(filename: str, delimiter: Optional[str] = None) -> Dict:
     if all(d == "unif" for d in dists):
         dists = None  # uniform everywhere: plain bounds scaling
     return {"names": names, "bounds": bounds, "num_vars": len(names), "groups": groups, "dists": dists}
+
+
+def handle_seed(seed):
+    """Seed-like -> ``numpy.random.Generator`` (reference util_funcs.py:184-202): a Generator is spawned, ints /
+    None / BitGenerator / SeedSequence / int sequences seed a new one, anything else is a ValueError."""
+    import numpy as np
+
+    if isinstance(seed, np.random.Generator):
+        return seed.spawn(1)[0]
+    if isinstance(seed, (np.random.BitGenerator, np.random.SeedSequence, int, type(None), list, tuple, np.ndarray)):
+        return np.random.default_rng(seed)
+    raise ValueError(f"Unsupported seed type: {type(seed)}")
