@@ -7,6 +7,8 @@ sample/sobol.py:192-251, sample/saltelli.py:205-264, analyze/sobol.py:442-491)::
     salib sample saltelli -n 1024 -p params.txt -o X.txt [--max-order 2] [--skip-values M] [--precision 8]
     salib sample sobol    -n 1024 -p params.txt -o X.txt [--max-order 2] [--scramble 1] [-s SEED]
     salib analyze sobol   -p params.txt -Y Y.txt [-c 0] [--max-order 2] [-r 100] [-s SEED]
+    salib sample finite_diff -n 1000 -p params.txt -o X.txt [-d 0.01]
+    salib analyze dgsm    -p params.txt -X X.txt -Y Y.txt [-c 0] [-r 1000] [-s SEED]
 
 Text I/O stays NumPy's (``np.savetxt`` with ``%.<precision>e``, ``np.loadtxt``) so files are byte-identical to
 the reference's; the numbers come from the CUDA path."""
@@ -17,8 +19,8 @@ import numpy as np
 
 from ..util.util_funcs import read_param_file
 
-SAMPLERS = ("saltelli", "sobol")
-ANALYZERS = ("sobol",)
+SAMPLERS = ("saltelli", "sobol", "finite_diff")
+ANALYZERS = ("sobol", "dgsm")
 
 
 def _sample_parser(method):
@@ -31,6 +33,10 @@ def _sample_parser(method):
         p.add_argument("-s", "--seed", type=int, required=False, default=None, help="Random Seed")
     p.add_argument("--delimiter", type=str, required=False, default=" ", help="Column delimiter")
     p.add_argument("--precision", type=int, required=False, default=8, help="Output floating-point precision")
+    if method == "finite_diff":  # sample/finite_diff.py:96-110
+        p.add_argument("-d", "--delta", type=float, required=False, default=0.01,
+                       help="Finite difference step size (percent)")
+        return p
     p.add_argument("--max-order", type=int, required=False, default=2, choices=[1, 2],
                    help="Maximum order of sensitivity indices to calculate")
     if method == "sobol":
@@ -48,6 +54,11 @@ def _analyze_parser(method):
     p.add_argument("-c", "--column", type=int, required=False, default=0, help="Column of output to analyze")
     p.add_argument("--delimiter", type=str, required=False, default=" ", help="Column delimiter in model output file")
     p.add_argument("-s", "--seed", type=int, required=False, default=None, help="Random Seed")
+    if method == "dgsm":  # analyze/dgsm.py:143-161
+        p.add_argument("-X", "--model-input-file", type=str, required=True, default=None, help="Model input file")
+        p.add_argument("-r", "--resamples", type=int, required=False, default=1000,
+                       help="Number of bootstrap resamples for confidence intervals")
+        return p
     p.add_argument("--max-order", type=int, required=False, default=2, choices=[1, 2],
                    help="Maximum order of sensitivity indices to calculate")
     p.add_argument("-r", "--resamples", type=int, required=False, default=100,
@@ -61,6 +72,12 @@ def _analyze_parser(method):
 def run_sample(method, opts):
     args = _sample_parser(method).parse_args(opts)
     problem = read_param_file(args.paramfile)
+    if method == "finite_diff":
+        from ..sample import finite_diff
+
+        X = finite_diff.sample(problem, args.samples, args.delta, seed=args.seed)
+        np.savetxt(args.output, X, delimiter=args.delimiter, fmt="%." + str(args.precision) + "e")
+        return
     second = args.max_order == 2
     if method == "saltelli":
         from ..sample import saltelli
@@ -81,6 +98,12 @@ def run_analyze(method, opts):
 
     problem = read_param_file(args.paramfile)
     Y = np.loadtxt(args.model_output_file, delimiter=args.delimiter, usecols=(args.column,))
+    if method == "dgsm":
+        from ..analyze import dgsm
+
+        X = np.loadtxt(args.model_input_file, delimiter=args.delimiter, ndmin=2)
+        dgsm.analyze(problem, X, Y, num_resamples=args.resamples, print_to_console=True, seed=args.seed)
+        return
     sobol.analyze(problem, Y, (args.max_order == 2), num_resamples=args.resamples, print_to_console=True,
                   parallel=args.parallel, n_processors=args.n_processors, seed=args.seed)
 

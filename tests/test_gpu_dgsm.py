@@ -56,3 +56,24 @@ def test_dgsm_philox_and_problem_spec():
     np.testing.assert_allclose(Sp["dgsm_conf"], Sn["dgsm_conf"], rtol=5.0 / np.sqrt(2 * 399))
     # reference tests/test_regression.py:465-474 (N = 10000): dgsm ~ [2.229, 7.066, 3.180]
     np.testing.assert_allclose(Sp["dgsm"], [2.229, 7.066, 3.180], atol=5e-2, rtol=1e-1)
+
+
+def test_dgsm_cli(tmp_path, capsys):
+    """reference tests/test_cli_analyze.py:77-105: finite_diff -> Ishigami -> `salib analyze dgsm`; the expected
+    values lie within the printed confidence intervals."""
+    import pandas as pd
+    from io import StringIO
+
+    from salib_b200.scripts import salib as cli
+    from salib_b200.test_functions import Ishigami
+
+    params = tmp_path / "Ishigami.txt"
+    params.write_text("x1 -3.14159265359 3.14159265359\nx2 -3.14159265359 3.14159265359\nx3 -3.14159265359 3.14159265359\n")
+    xin, yout = tmp_path / "x.txt", tmp_path / "y.txt"
+    cli.main(f"sample finite_diff -p {params} -o {xin} -d 0.001 --precision=8 -n 1000 -s 100".split())
+    np.savetxt(yout, Ishigami.evaluate(np.loadtxt(xin)))
+    capsys.readouterr()
+    cli.main(f"analyze dgsm -p {params} -X {xin} -Y {yout} -c 0 -r 1000 --seed=100".split())
+    df = pd.read_csv(StringIO(capsys.readouterr().out), sep=r"\s+")
+    expected = np.array([2.207554, 7.092019, 3.238259])
+    assert ((df["dgsm"] - df["dgsm_conf"] <= expected) & (expected <= df["dgsm"] + df["dgsm_conf"])).all()
