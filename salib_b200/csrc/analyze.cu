@@ -769,71 +769,10 @@ s2_accum_dmma_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
     if (!live || t >= ntiles || i >= row1) return 0u;
     return wrow ? (unsigned)__ldg(wrow + i) : 1u;
   };
-  unsigned wl_next = load_w(0);
-
-  for (int t = 0; t < ntiles; ++t) {
-    const int s = t % kStages;
-    const unsigned wl = wl_next;
-    wl_next = load_w(t + 1);
-    unsigned mask = __ballot_sync(kFull, wl != 0);
-    const int whi = __double2hiint((double)wl);
-    while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)(t / kStages) & 1u)) {
-    }
-    const uint32_t tile = sm_base + s * stage_bytes;
-    while (mask) {
-      // the next (up to) four nonzero rows form one K-step
-      int r[4];
-      int n = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        r[q] = mask ? __ffs(mask) - 1 : 0;
-        if (mask) {
-          ++n;
-          mask &= mask - 1;
-        }
-      }
-      const int myrow = (kq == 0) ? r[0] : (kq == 1 ? r[1] : (kq == 2 ? r[2] : r[3]));
-      const int hi = __shfl_sync(kFull, whi, myrow);
-      const double wq = (kq < n) ? __hiloint2double(hi, 0) : 0.0;
-      const uint32_t rowa = tile + (uint32_t)myrow * row_bytes;
-      double fa[8], fb[8];
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b < TB) {  // uniform
-          fa[b] = wq * lds_f64(rowa + offA + 80u * b);
-          fb[b] = lds_f64(rowa + offB + 80u * b);
-        } else {
-          fa[b] = 0.0;
-          fb[b] = 0.0;
-        }
-      }
-      int ti = 0;
-#pragma unroll
-      for (int jb = 0; jb < 8; ++jb)
-#pragma unroll
-        for (int kb = jb; kb < 8; ++kb) {
-          if (kb < TB) dmma884(acc[ti], fa[jb], fb[kb]);  // uniform
-          ++ti;
-        }
-      // first/total order for the rows of this K-step
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < n) {  // uniform
-          const double wv = __hiloint2double(__shfl_sync(kFull, whi, r[q]), 0);
-          const uint32_t row = tile + (uint32_t)r[q] * row_bytes;
-          const double2 ab = lds_f64x2(row + offAB);
-          const double wb = wv * ab.y;
-          const double t0 = lds_f64(row + offC0) - ab.x;
-          const double t1 = lds_f64(row + offC1) - ab.x;
-          s1_0 = fma(wb, t0, s1_0);
-          s1_1 = fma(wb, t1, s1_1);
-          st_0 = fma(wv * t0, t0, st_0);
-          st_1 = fma(wv * t1, t1, st_1);
-        }
-      }
-    }
+  auto release = [&](int t) {  // this warp is done with tile t; the last warp out refills its stage
     __syncwarp();
     if (lane == 0) {
+      const int s = t % kStages;
       uint32_t old;
       asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
                    : "=r"(old)
@@ -844,7 +783,105 @@ s2_accum_dmma_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
         if (t + kStages < ntiles) issue(t + kStages);
       }
     }
+  };
+
+  // Row stream state: current tile t, the not yet consumed nonzero rows of it (mask) and the weights (whi).
+  int t = 0;
+  unsigned wl = load_w(0), wl_next = load_w(1);
+  unsigned mask = __ballot_sync(kFull, wl != 0);
+  int whi = __double2hiint((double)wl);
+  uint32_t tile = sm_base;
+  bool tile_ready = false;
+  int done_tiles = 0;  // tiles [0, done_tiles) have been released
+  // A K-step = the next (up to) four nonzero rows; rows never mix tiles.
+  struct Step {
+    uint32_t rowaddr[4];
+    double wv[4];
+    uint32_t myrow;  // row of this lane's K slot
+    double wq;       // its weight (0 for padding)
+    int tile_id;
+    bool valid;
+  };
+  auto pick = [&](Step &st) {
+    while (mask == 0 && t + 1 < ntiles) {  // advance to the next tile that has rows of this resample
+      ++t;
+      wl = wl_next;
+      wl_next = load_w(t + 1);
+      mask = __ballot_sync(kFull, wl != 0);
+      whi = __double2hiint((double)wl);
+      tile = sm_base + (t % kStages) * stage_bytes;
+      tile_ready = false;
+    }
+    st.valid = mask != 0;
+    st.tile_id = t;
+    if (!st.valid) return;
+    if (!tile_ready) {
+      while (!mbar_try_wait(bar_base + 8u * (t % kStages), (uint32_t)(t / kStages) & 1u)) {
+      }
+      tile_ready = true;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = mask ? __ffs(mask) - 1 : 0;
+      st.rowaddr[q] = tile + (uint32_t)r * row_bytes;
+      st.wv[q] = mask ? __hiloint2double(__shfl_sync(kFull, whi, r), 0) : 0.0;
+      if (mask) mask &= mask - 1;
+    }
+    st.myrow = (kq == 0) ? st.rowaddr[0] : (kq == 1 ? st.rowaddr[1] : (kq == 2 ? st.rowaddr[2] : st.rowaddr[3]));
+    st.wq = (kq == 0) ? st.wv[0] : (kq == 1 ? st.wv[1] : (kq == 2 ? st.wv[2] : st.wv[3]));
+  };
+
+  double fa[8], fb[8];  // fragments of the current step; refilled in place for the next step as the MMAs retire them
+  Step cur, nxt;
+  pick(cur);
+  if (cur.valid) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      fa[q] = (q < TB) ? lds_f64(cur.myrow + offA + 80u * q) : 0.0;
+      fb[q] = (q < TB) ? lds_f64(cur.myrow + offB + 80u * q) : 0.0;
+    }
   }
+  while (cur.valid) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) fa[q] *= cur.wq;  // fragments were loaded unscaled
+    pick(nxt);
+    double2 sab = make_double2(0.0, 0.0);
+    double sc0 = 0.0, sc1 = 0.0;
+    int ti = 0;
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) {
+#pragma unroll
+      for (int kb = jb; kb < 8; ++kb) {
+        if (kb < TB) dmma884(acc[ti], fa[jb], fb[kb]);  // uniform
+        ++ti;
+      }
+      if (nxt.valid && jb < TB) {  // block jb is retired: its registers take the next step's fragments
+        fa[jb] = lds_f64(nxt.myrow + offA + 80u * jb);
+        fb[jb] = lds_f64(nxt.myrow + offB + 80u * jb);
+      }
+      // first/total order of the step's rows: row q is loaded after MMA group q and consumed after group q+1
+      if (jb >= 1 && jb <= 4) {
+        const double wv = cur.wv[jb - 1];
+        const double wb = wv * sab.y;
+        const double t0 = sc0 - sab.x, t1 = sc1 - sab.x;
+        s1_0 = fma(wb, t0, s1_0);
+        s1_1 = fma(wb, t1, s1_1);
+        st_0 = fma(wv * t0, t0, st_0);
+        st_1 = fma(wv * t1, t1, st_1);
+      }
+      if (jb <= 3) {
+        sab = lds_f64x2(cur.rowaddr[jb] + offAB);
+        sc0 = lds_f64(cur.rowaddr[jb] + offC0);
+        sc1 = lds_f64(cur.rowaddr[jb] + offC1);
+      }
+    }
+    // tiles left behind by this step can go back to the ring
+    const int upto = nxt.valid ? nxt.tile_id : ntiles;
+    while (done_tiles < upto) release(done_tiles++);
+    cur = nxt;
+  }
+  while (done_tiles < ntiles) release(done_tiles++);
+
   if (!live) return;
   double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
   if (jC0 < Dg) {
