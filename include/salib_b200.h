@@ -150,11 +150,20 @@ int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int se
  *   sa_counts_philox:       device Philox4x32-10 draw of N iid uniform indices per resample,
  *                           keyed by (seed, global resample id c0+c, draw t): independent of
  *                           how resamples are sharded over GPUs.
- * d_overflow (int32, may be NULL) is set to 1 if any multiplicity exceeded 255.               */
+ * d_overflow (int32, may be NULL) is set to 1 if any multiplicity exceeded 255.
+ * The *_rows forms keep only the draws that land in the row window [row0, row0+nrows) of the N rows and
+ * write d_w[count][sa_pad_rows(nrows)] indexed from row0: the multiplicities of one row shard when Y is
+ * partitioned by base-row range across GPUs (SURVEY 8(e) "when Y exceeds one GPU").  The draws are the
+ * same N per resample whatever the window, so the shards of all GPUs add up to the unsharded w.     */
 int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
                            uint64_t count, uint8_t *d_w, int32_t *d_overflow);
 int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
                      uint8_t *d_w, int32_t *d_overflow);
+int sa_counts_from_indices_rows(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
+                                uint64_t count, uint64_t row0, uint64_t nrows, uint8_t *d_w,
+                                int32_t *d_overflow);
+int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                          uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow);
 
 /* ---- analyze: accumulate / finalize -------------------------------------------------------
  * sa_sobol_accumulate_f64 replaces the gathers and reductions inside first_order / total_order

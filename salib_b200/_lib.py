@@ -35,6 +35,8 @@ SIGNATURES = {
     "sa_normalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]),
     "sa_counts_from_indices": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _u64, _vp, _vp]),
     "sa_counts_philox": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "sa_counts_from_indices_rows": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "sa_counts_philox_rows": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
     "sa_sobol_accumulate_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp]),
     "sa_sobol_accumulate_ex_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp, _i32]),
     "sa_sobol_finalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _u64, _i32, _vp, _vp]),

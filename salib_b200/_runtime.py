@@ -2,6 +2,8 @@
 
 Every helper here raises if CUDA is unavailable -- there is no CPU path.
 """
+import warnings
+
 import numpy as np
 import torch
 
@@ -34,7 +36,9 @@ def to_device(a, dtype=None):
         t = a.to(device=dev, dtype=dtype) if (a.device != dev or (dtype and a.dtype != dtype)) else a
         return t.contiguous()
     arr = np.ascontiguousarray(a)
-    t = torch.from_numpy(arr)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)   # read-only host arrays (np.load views) are only read here
+        t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.to(dev, non_blocking=False)

@@ -34,7 +34,7 @@ from scipy.stats import norm
 from .. import _lib, _runtime as rt
 from ..util import ResultDict, extract_group_names
 
-__all__ = ["analyze", "analyze_device", "analyze_outputs", "first_order", "total_order", "second_order", "separate_output_values",
+__all__ = ["analyze", "analyze_device", "analyze_outputs", "analyze_row_sharded", "combine_moments", "allgather_moments", "first_order", "total_order", "second_order", "separate_output_values",
            "to_df", "Si_to_pandas_dict", "CONST_RESULT_MSG"]
 
 CONST_RESULT_MSG = (
@@ -88,13 +88,16 @@ class _Resampler:
         self.r = rt.to_device(np.ascontiguousarray(r, dtype=np.int64), torch.int64)
         return self
 
-    def counts(self, c0, count, w):
+    def counts(self, c0, count, w, rows=None):
+        """w[count][pad_rows(nrows)] <- multiplicities of resamples [c0, c0+count) over the row window
+        ``rows = (row0, nrows)`` (default: all N rows)."""
+        row0, nrows = rows if rows is not None else (0, self.N)
         if self.mode == "numpy":
-            _lib.call("sa_counts_from_indices", rt.stream_ptr(), rt.ptr(self.r), self.N, self.R, int(c0),
-                      int(count), rt.ptr(w), rt.ptr(self.flag))
+            _lib.call("sa_counts_from_indices_rows", rt.stream_ptr(), rt.ptr(self.r), self.N, self.R, int(c0),
+                      int(count), int(row0), int(nrows), rt.ptr(w), rt.ptr(self.flag))
         else:
-            _lib.call("sa_counts_philox", rt.stream_ptr(), self.key, self.N, int(c0), int(count), rt.ptr(w),
-                      rt.ptr(self.flag))
+            _lib.call("sa_counts_philox_rows", rt.stream_ptr(), self.key, self.N, int(c0), int(count),
+                      int(row0), int(nrows), rt.ptr(w), rt.ptr(self.flag))
 
     def check(self):
         f = int(self.flag.item())
@@ -164,12 +167,21 @@ class SobolAnalyzer:
         self.kernel_events = None   # bench.py sets this to a list to time the accumulate launches
 
     # -- normalisation ---------------------------------------------------------------------
-    def load(self, Yd):
-        """Yd: device float64 [N*step] in the reference order -> stats, Yn (and Yt)."""
+    def moments(self, Yd):
+        """stats[0:6] = mean, std, min, max of Yd and min, max of its A and B columns."""
         L = _lib.lib()
         work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)
         _lib.call("sa_moments_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.step, rt.ptr(self.stats),
                   rt.ptr(work), int(work.numel()))
+
+    def load(self, Yd, stats=None):
+        """Yd: device float64 [N*step] in the reference order -> stats, Yn (and Yt).  ``stats`` (8 doubles)
+        replaces the moments of Yd -- the statistics of the whole design when Yd is one row shard of it."""
+        L = _lib.lib()
+        if stats is None:
+            self.moments(Yd)
+        else:
+            self.stats.copy_(rt.to_device(np.asarray(stats, dtype=np.float64), torch.float64))
         need_rows = self.kind in (1, 4, 5)
         need_cols = self.kind in (3, 4, 5)   # kinds 4, 5 only need the A and B columns
         if need_rows:
@@ -189,8 +201,8 @@ class SobolAnalyzer:
     def _nsplit(self, count):
         return plan_row_splits(self.kind, count, self.N, self.sms, self.nacc, self.groups)
 
-    def _accumulate(self, w, count, est_out):
-        """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
+    def _partial_sums(self, w, count):
+        """psum [nsplit, count, nacc] of this engine's rows; returns (psum, nsplit)."""
         nsplit = self._nsplit(count)
         psum = rt.empty((nsplit * count * self.nacc,), torch.float64)
         ev = None
@@ -202,8 +214,16 @@ class SobolAnalyzer:
         if ev is not None:
             ev[1].record()
             self.kernel_events.append((int(count), ev[0], ev[1]))
-        _lib.call("sa_sobol_finalize_f64", rt.stream_ptr(), rt.ptr(psum), self.N, self.Dg, int(self.c2),
+        return psum, nsplit
+
+    def _finalize(self, psum, nsplit, count, n_rows, est_out):
+        _lib.call("sa_sobol_finalize_f64", rt.stream_ptr(), rt.ptr(psum), int(n_rows), self.Dg, int(self.c2),
                   int(count), int(nsplit), rt.ptr(self.stats), rt.ptr(est_out))
+
+    def _accumulate(self, w, count, est_out):
+        """est_out [count, nest] <- estimates of resamples whose multiplicities are w (None = all ones)."""
+        psum, nsplit = self._partial_sums(w, count)
+        self._finalize(psum, nsplit, count, self.N, est_out)
 
     def point(self):
         est = rt.empty((1, self.nest), torch.float64)
@@ -256,6 +276,140 @@ def allgather_estimates(est_local, R, rank, world):
         lo, hi = rt.shard_range(R, g, world)
         parts.append(full[g * per: g * per + (hi - lo)])
     return torch.cat(parts, dim=0)
+
+
+def combine_moments(parts):
+    """Statistics of the union of row shards from per-shard ``(n_values, stats8)`` (pairwise update of
+    Chan, Golub & LeVeque): mean, population std, min, max, min/max over the A and B columns."""
+    n = float(sum(c for c, _ in parts))
+    mean = sum(c * s[0] for c, s in parts) / n
+    m2 = sum(c * (s[1] * s[1] + (s[0] - mean) ** 2) for c, s in parts)
+    out = np.zeros(8)
+    out[0], out[1] = mean, np.sqrt(m2 / n)
+    out[2], out[3] = min(s[2] for _, s in parts), max(s[3] for _, s in parts)
+    out[4], out[5] = min(s[4] for _, s in parts), max(s[5] for _, s in parts)
+    return out
+
+
+def allgather_moments(local, world):
+    """Every rank's per-shard ``(n_values, stats8)`` list -> the list over all ranks (tiny all-gather;
+    ranks may hold different numbers of shards)."""
+    if world == 1:
+        return list(local)
+    import torch.distributed as dist
+
+    n_max = torch.tensor([len(local)], dtype=torch.int64, device=rt.device())
+    dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+    n_max = int(n_max.item())
+    mine = torch.zeros((n_max, 9), dtype=torch.float64, device=rt.device())
+    for i, (c, st) in enumerate(local):
+        mine[i, 0] = c
+        mine[i, 1:] = torch.as_tensor(np.asarray(st, dtype=np.float64))
+    everyone = torch.empty((world * n_max, 9), dtype=torch.float64, device=rt.device())
+    dist.all_gather_into_tensor(everyone, mine)
+    return [(row[0], row[1:]) for row in everyone.cpu().numpy() if row[0] > 0]
+
+
+def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resamples=100, conf_level=0.95,
+                        keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
+                        kernel_events=None):
+    """``analyze`` for a model output partitioned by base-row range ("when Y exceeds one GPU").
+
+    ``shards``: the ``(row0, Y_local)`` pieces this process holds, ``Y_local`` = the ``n_local*step`` outputs
+    of base rows ``[row0, row0+n_local)`` (host or CUDA); over all ranks of the torch.distributed job the
+    pieces tile ``[0, N)``.  Every rank walks all resamples over its own rows: the multiplicity kernels
+    keep the draws that land in the shard's row window, the accumulate kernels produce partial sums
+    ``[count, nacc]``, one all-reduce per batch adds them across ranks, and the estimator algebra runs on
+    the totals -- the all-reduce of partial sums replaces the all-gather of estimates of the resample-sharded
+    path.  Statistics for the normalisation come from per-shard moments combined by ``combine_moments``.
+    """
+    import torch.distributed as dist
+
+    _, Dg = extract_group_names(problem)
+    c2 = bool(calc_second_order)
+    step = 2 * Dg + 2 if c2 else Dg + 2
+    if not 0 < conf_level < 1:
+        raise RuntimeError("Confidence level must be between 0-1.")
+    rt.require_cuda()
+    rank, world = rt.world() if distributed else (0, 1)
+
+    engines, local = [], []
+    for row0, Y in shards:
+        size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+        if size % step or size == 0:
+            raise RuntimeError("row shard size is not a multiple of the Saltelli block length")
+        eng = SobolAnalyzer(Dg, size // step, c2, algo=algo)
+        eng.kernel_events = kernel_events
+        eng.row0 = int(row0)
+        Yd = rt.to_device(Y, torch.float64).reshape(-1)
+        eng.moments(Yd)
+        engines.append((eng, Yd))
+        local.append((float(size), eng.stats.cpu().numpy().copy()))
+    rows_here = sum(e.N for e, _ in engines)
+    parts = allgather_moments(local, world)
+    if int(round(sum(c for c, _ in parts))) != N * step:
+        raise RuntimeError(f"row shards hold {int(sum(c for c, _ in parts)) // step} base rows, expected {N}")
+    stats = combine_moments(parts)
+    for eng, Yd in engines:
+        eng.load(Yd, stats=stats)
+    engines = [e for e, _ in engines]
+    lead = engines[0]
+    Z = norm.ppf(0.5 + conf_level / 2)
+
+    if r is not None:
+        rs = _Resampler.from_indices(r)
+        if rs.N != N:
+            raise ValueError(f"`r` must have {N} rows")
+        R = rs.R
+    else:
+        R = int(num_resamples)
+        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
+
+    def totals(ws, count, est_out):
+        tot = rt.zeros((count * lead.nacc,), torch.float64)
+        red = rt.empty((count * lead.nacc,), torch.float64)
+        for eng, w in zip(engines, ws):
+            psum, nsplit = eng._partial_sums(w, count)
+            _lib.call("sa_reduce_splits_f64", rt.stream_ptr(), rt.ptr(psum), int(count), lead.nacc, int(nsplit),
+                      1.0, rt.ptr(red))
+            tot += red
+        if world > 1:
+            dist.all_reduce(tot)
+        lead._finalize(tot, 1, count, N, est_out)
+
+    point = rt.empty((1, lead.nest), torch.float64)
+    totals([None] * len(engines), 1, point)
+    est = None
+    if R > 0:
+        est = rt.empty((R, lead.nest), torch.float64)
+        big = max(engines, key=lambda e: e.Npad)
+        wbuf = {}
+        for c0, c1 in big._batches(0, R):
+            n = c1 - c0
+            ws = []
+            for i, eng in enumerate(engines):
+                if i not in wbuf or wbuf[i].numel() < n * eng.Npad:
+                    wbuf[i] = rt.empty((n * eng.Npad,), torch.uint8)
+                rs.counts(c0, n, wbuf[i], rows=(eng.row0, eng.N))
+                ws.append(wbuf[i])
+            totals(ws, n, est[c0:c1])
+        conf = lead.conf(est, Z)
+        rs.check()
+    else:
+        conf = torch.full((lead.nest,), float("nan"), dtype=torch.float64, device=point.device)
+
+    const_y = not (stats[4] < stats[5])
+    if const_y:
+        warn(CONST_RESULT_MSG)
+    keep = bool(keep_resamples)
+    kept = None
+    if keep:
+        kept = est[:, :2 * Dg].cpu().numpy() if est is not None else np.zeros((0, 2 * Dg))
+    S = _assemble(Dg, c2, keep, point[0].cpu().numpy(), conf.cpu().numpy(), kept, const_y)
+    S.problem = problem
+    S.to_df = MethodType(to_df, S)
+    S.rows_here = rows_here
+    return S
 
 
 def _assemble(Dg, c2, keep, point, conf, est_all, const_y):
@@ -370,14 +524,31 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
 
 def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
                    keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
-                   kernel_events=None):
+                   kernel_events=None, shard="resamples"):
     """``analyze`` with the device knobs exposed.
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
     ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
     ``algo``: force an accumulate kernel ("generic" | "tile8" | "first_order"); ``distributed``: shard the
-    resamples over the initialised torch.distributed job.
+    resamples over the initialised torch.distributed job; ``shard``: "resamples" (default: every rank holds
+    Y, resample ids are split) or "rows" (every rank keeps only its base-row range of Y and all resamples'
+    partial sums are all-reduced -- ``analyze_row_sharded``).
     """
+    if shard == "rows":
+        _, Dg = extract_group_names(problem)
+        size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+        N = _n_from_size(size, Dg, calc_second_order)
+        step = size // N
+        rank, world = rt.world() if distributed else (0, 1)
+        lo, hi = rt.shard_range(N, rank, world)
+        flat = Y.reshape(-1)
+        return analyze_row_sharded(problem, [(lo, flat[lo * step:hi * step])], N,
+                                   calc_second_order=calc_second_order, num_resamples=num_resamples,
+                                   conf_level=conf_level, keep_resamples=keep_resamples, seed=seed,
+                                   resample=resample, r=r, algo=algo, distributed=distributed,
+                                   kernel_events=kernel_events)
+    if shard != "resamples":
+        raise ValueError(f"unknown shard mode {shard!r}")
     return analyze_outputs(problem, [Y], calc_second_order=calc_second_order, num_resamples=num_resamples,
                            conf_level=conf_level, keep_resamples=keep_resamples, seed=seed, resample=resample,
                            r=r, algo=algo, distributed=distributed, kernel_events=kernel_events)[0]

@@ -211,7 +211,8 @@ normalize_cols_kernel(const double *__restrict__ Y, uint64_t N, uint64_t Npad, i
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 counts_from_indices_kernel(const int64_t *__restrict__ r, uint64_t N, uint64_t R, uint64_t c0,
-                           uint64_t count, uint64_t Npad, uint32_t *__restrict__ w32, int32_t *overflow) {
+                           uint64_t count, uint64_t row0, uint64_t nrows, uint64_t Npad,
+                           uint32_t *__restrict__ w32, int32_t *overflow) {
   const uint64_t total = N * count;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
@@ -222,7 +223,9 @@ counts_from_indices_kernel(const int64_t *__restrict__ r, uint64_t N, uint64_t R
       if (overflow) atomicOr(overflow, 2);
       continue;
     }
-    const uint64_t pos = cl * Npad + (uint64_t)idx;
+    const uint64_t local = (uint64_t)idx - row0;  // rows outside [row0, row0+nrows) belong to other shards
+    if (local >= nrows) continue;
+    const uint64_t pos = cl * Npad + local;
     const unsigned sh = 8u * (unsigned)(pos & 3);
     const uint32_t old = atomicAdd(w32 + (pos >> 2), 1u << sh);
     if (((old >> sh) & 0xffu) == 0xffu && overflow) atomicOr(overflow, 1);
@@ -254,7 +257,8 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 // Draw t of resample c: u64 = philox(counter = (t/2, c), key = seed) word pair (t & 1);
 // index = floor(u64 * N / 2^64).
 __global__ void __launch_bounds__(256)
-counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint32_t *__restrict__ w32) {
+counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t row0, uint64_t nrows, uint64_t Npad,
+                     uint32_t *__restrict__ w32) {
   const uint64_t c = c0 + blockIdx.y;
   uint32_t *wrow = w32 + ((uint64_t)blockIdx.y * Npad >> 2);
   const uint64_t npairs = (N + 1) >> 1;
@@ -264,11 +268,11 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t Npad, uint
                                     (uint32_t)seed, (uint32_t)(seed >> 32));
     const uint64_t u0 = ((uint64_t)p.y << 32) | p.x;
     const uint64_t u1 = ((uint64_t)p.w << 32) | p.z;
-    const uint64_t i0 = __umul64hi(u0, N);
-    atomicAdd(wrow + (i0 >> 2), 1u << (8u * (unsigned)(i0 & 3)));
+    const uint64_t i0 = __umul64hi(u0, N) - row0;
+    if (i0 < nrows) atomicAdd(wrow + (i0 >> 2), 1u << (8u * (unsigned)(i0 & 3)));
     if (2 * t2 + 1 < N) {
-      const uint64_t i1 = __umul64hi(u1, N);
-      atomicAdd(wrow + (i1 >> 2), 1u << (8u * (unsigned)(i1 & 3)));
+      const uint64_t i1 = __umul64hi(u1, N) - row0;
+      if (i1 < nrows) atomicAdd(wrow + (i1 >> 2), 1u << (8u * (unsigned)(i1 & 3)));
     }
   }
 }
@@ -1355,33 +1359,41 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
   return SA_OK;
 }
 
-extern "C" int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
-                                      uint64_t count, uint8_t *d_w, int32_t *d_overflow) {
+extern "C" int sa_counts_from_indices_rows(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
+                                           uint64_t count, uint64_t row0, uint64_t nrows, uint8_t *d_w,
+                                           int32_t *d_overflow) {
   SA_REQUIRE(d_r && d_w, SA_ERR_ARG, "sa_counts_from_indices: null pointer");
   SA_REQUIRE(N >= 1 && c0 + count <= R, SA_ERR_ARG, "sa_counts_from_indices: resample range out of bounds");
+  SA_REQUIRE(nrows >= 1 && row0 + nrows <= N, SA_ERR_ARG, "sa_counts_from_indices: row window out of bounds");
   SA_REQUIRE(((uintptr_t)d_w & 3) == 0, SA_ERR_ARG, "sa_counts_from_indices: d_w not 4-byte aligned");
   if (count == 0) return SA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const uint64_t Npad = pad_rows(N);
+  const uint64_t Npad = pad_rows(nrows);
   SA_CUDA(cudaMemsetAsync(d_w, 0, count * Npad, st));
   uint64_t blocks = ceil_div_u64(N * count, 256);
   if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
-  counts_from_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_r, N, R, c0, count, Npad, (uint32_t *)d_w,
-                                                              d_overflow);
+  counts_from_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_r, N, R, c0, count, row0, nrows, Npad,
+                                                              (uint32_t *)d_w, d_overflow);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
 
-extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
-                                uint8_t *d_w, int32_t *d_overflow) {
+extern "C" int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t N, uint64_t R, uint64_t c0,
+                                      uint64_t count, uint8_t *d_w, int32_t *d_overflow) {
+  return sa_counts_from_indices_rows(stream, d_r, N, R, c0, count, 0, N, d_w, d_overflow);
+}
+
+extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                     uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow) {
   (void)d_overflow;  // P(multiplicity > 255) < 1e-500 for N iid uniform draws over N rows, N >= 256
   SA_REQUIRE(d_w, SA_ERR_ARG, "sa_counts_philox: null pointer");
   SA_REQUIRE(N >= 1, SA_ERR_ARG, "sa_counts_philox: bad N");
+  SA_REQUIRE(nrows >= 1 && row0 + nrows <= N, SA_ERR_ARG, "sa_counts_philox: row window out of bounds");
   SA_REQUIRE(((uintptr_t)d_w & 3) == 0, SA_ERR_ARG, "sa_counts_philox: d_w not 4-byte aligned");
   if (count == 0) return SA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const uint64_t Npad = pad_rows(N);
+  const uint64_t Npad = pad_rows(nrows);
   SA_CUDA(cudaMemsetAsync(d_w, 0, count * Npad, st));
   const uint64_t npairs = (N + 1) / 2;
   uint64_t bx = ceil_div_u64(npairs, 256 * 4);
@@ -1390,11 +1402,17 @@ extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_
   for (uint64_t done = 0; done < count; done += 65535) {
     const uint64_t nb = (count - done < 65535) ? count - done : 65535;
     dim3 grid((unsigned)bx, (unsigned)nb);
-    counts_philox_kernel<<<grid, 256, 0, st>>>(seed, N, c0 + done, Npad, (uint32_t *)(d_w + done * Npad));
+    counts_philox_kernel<<<grid, 256, 0, st>>>(seed, N, c0 + done, row0, nrows, Npad,
+                                               (uint32_t *)(d_w + done * Npad));
     note_launches(1);
   }
   SA_LAUNCH_CHECK();
   return SA_OK;
+}
+
+extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                uint8_t *d_w, int32_t *d_overflow) {
+  return sa_counts_philox_rows(stream, seed, N, c0, count, 0, N, d_w, d_overflow);
 }
 
 // algo: 0 auto, 1 generic, 3 first/total order, 4 second-order 8x8 register tiles, 5 experimental DMMA

@@ -292,3 +292,74 @@ def test_edge_shapes_match_oracle(D, N, c2, R):
         iu = np.triu_indices(D, 1)
         np.testing.assert_allclose(S["S2"][iu], So["S2"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
         np.testing.assert_allclose(S["S2_conf"][iu], So["S2_conf"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_row_window_multiplicities_tile_the_full_ones():
+    """sa_counts_*_rows over windows that tile [0, N) = the unsharded multiplicities, for both sources."""
+    import torch
+
+    from salib_b200 import _lib, _runtime as rt
+    from salib_b200.analyze.sobol import _Resampler
+
+    N, R = 1000, 9
+    L = _lib.lib()
+    Npad = int(L.sa_pad_rows(N))
+    for rs in (_Resampler(N, R, 11, "philox"),
+               _Resampler.from_indices(np.random.default_rng(3).integers(N, size=(N, R)))):
+        full = rt.empty((R * Npad,), torch.uint8)
+        rs.counts(0, R, full)
+        full = full.reshape(R, Npad)[:, :N].cpu().numpy()
+        assert (full.sum(axis=1) == N).all()
+        got = np.zeros_like(full)
+        for lo, hi in ((0, 300), (300, 301), (301, 777), (777, 1000)):
+            npad = int(L.sa_pad_rows(hi - lo))
+            w = rt.empty((R * npad,), torch.uint8)
+            rs.counts(0, R, w, rows=(lo, hi - lo))
+            w = w.reshape(R, npad).cpu().numpy()
+            assert not w[:, hi - lo:].any()
+            got[:, lo:hi] = w[:, :hi - lo]
+        np.testing.assert_array_equal(got, full)
+    with pytest.raises(_lib.SalibB200Error):
+        rs.counts(0, R, rt.empty((R * Npad,), torch.uint8), rows=(900, 200))
+
+
+@pytest.mark.parametrize("name,cuts", [("g64_n128_r16", (0, 50, 128)), ("g8_n512_r64", (0, 100, 101, 512)),
+                                       ("g8_n512_c1_r64", (0, 333, 512)), ("ishigami_n1024_r100", (0, 512, 1024)),
+                                       ("grp3_n512_r40", (0, 64, 512))])
+def test_row_sharded_matches_frozen_reference(name, cuts):
+    """Y partitioned by base-row range: per-shard partial sums added up -> the reference's dict."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_" + name)
+    p = problem_from(z)
+    D, c2 = z["S1"].shape[0], bool(z["c2"])
+    Y = np.asarray(z["Y"], dtype=np.float64)
+    step = Y.size // (cuts[-1])
+    shards = [(lo, Y[lo * step:hi * step]) for lo, hi in zip(cuts, cuts[1:])]
+    S = sobol.analyze_row_sharded(p, shards, cuts[-1], calc_second_order=c2, conf_level=float(z["conf"]),
+                                  keep_resamples=True, r=z["r"].astype(np.int64))
+    _cmp(S, z, D, c2)
+    # the one-call form (one shard per rank; a single process holds everything)
+    S1 = sobol.analyze_device(p, Y, calc_second_order=c2, conf_level=float(z["conf"]), keep_resamples=True,
+                              r=z["r"].astype(np.int64), shard="rows")
+    _cmp(S1, z, D, c2)
+
+
+def test_row_sharded_philox_equals_unsharded():
+    """Device Philox draws do not depend on the row partition: same key -> same CIs to rounding."""
+    from salib_b200.analyze import sobol
+    from salib_b200.sample import sobol as sampler
+    from salib_b200.test_functions import Sobol_G
+
+    D, N = 16, 4096
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+    X = sampler.sample(p, N, scramble=False)
+    Y = Sobol_G.evaluate(X, a=np.linspace(0.0, 20.0, D))
+    step = 2 * D + 2
+    ref = sobol.analyze_device(p, Y, num_resamples=300, seed=7, resample="philox", keep_resamples=True)
+    cuts = (0, 1000, 2600, 4096)
+    S = sobol.analyze_row_sharded(p, [(lo, Y[lo * step:hi * step]) for lo, hi in zip(cuts, cuts[1:])], N,
+                                  num_resamples=300, seed=7, resample="philox", keep_resamples=True)
+    _cmp(S, ref, D, True)
+    with pytest.raises(RuntimeError):
+        sobol.analyze_row_sharded(p, [(0, Y[:1000 * step])], N, num_resamples=10, seed=7)

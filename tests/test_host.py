@@ -313,6 +313,21 @@ def _gloo_worker(rank, world, port, R, nest, q):
     y = np.arange(1000 * R + 3, dtype=np.float64)
     got = rt.to_device_sharded(y, torch.float64, min_bytes=0)
     ok = ok and bool(torch.equal(got, torch.from_numpy(y)))
+    # row-sharded analyze: per-shard moments of every rank (rank 1 holds two shards) -> statistics of the union
+    from salib_b200.analyze.sobol import allgather_moments, combine_moments
+
+    rng = np.random.default_rng(5)
+    data = rng.normal(3.0, 2.0, size=(90, 4))           # 90 base rows, step 4: columns A, AB_0, AB_1, B
+    cuts = [(0, 40)] if rank == 0 else [(40, 47), (47, 90)]
+
+    def moments(block):
+        ab = block[:, [0, 3]]
+        return (float(block.size), np.array([block.mean(), block.std(), block.min(), block.max(), ab.min(), ab.max(), 0, 0]))
+
+    parts = allgather_moments([moments(data[a:b]) for a, b in cuts], world)
+    st = combine_moments(parts)
+    ref = moments(data)[1]
+    ok = ok and len(parts) == 3 and bool(np.allclose(st[:6], ref[:6], rtol=1e-14, atol=0))
     q.put((rank, ok))
     dist.destroy_process_group()
 
