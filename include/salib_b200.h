@@ -213,6 +213,21 @@ int sa_feature_sums_f64(void *stream, const double *d_F, uint64_t N, int nfeat, 
 int sa_reduce_splits_f64(void *stream, const double *d_psum, uint64_t count, int nfeat, int nsplit,
                          double scale, double *d_out);
 
+/* ---- discrepancy indices --------------------------------------------------------
+ * Replaces analyze/discrepancy.py:88-116: X [N, D] and Y [N] are unit-scaled as qmc.scale(reverse=True)
+ * does (X by the problem bounds d_lb/d_ub, Y by its own min/max, :92-94), then for every input i the 2-D
+ * discrepancy of the projection [X_i, Y] (scipy.stats.qmc.discrepancy, :96-99) is computed -- an N^2 pair
+ * sum per input -- and normalised by the sum over inputs (:101); with groups (d_gcol: group index per
+ * column, Dg groups) the group mean of the members is returned (:103-111).
+ *   method: 0 "WD" wrap-around, 1 "CD" centered, 2 "MD" mixture, 3 "L2-star".
+ *   d_out [Dg] normalised indices; d_disc [D] raw discrepancies (may be NULL).
+ *   d_flag (int32, zeroed by the caller, may be NULL): bit 0 = a sample lies outside its bounds
+ *   ("Sample is out of bounds"), bit 1 = Y is constant or NaN (scipy: inconsistent bounds).           */
+size_t sa_discrepancy_workspace_bytes(uint64_t N, int D);
+int sa_discrepancy_f64(void *stream, const double *d_X, const double *d_Y, uint64_t N, int D,
+                       const double *d_lb, const double *d_ub, int method, int Dg, const int32_t *d_gcol,
+                       double *d_out, double *d_disc, void *d_work, size_t work_bytes, int32_t *d_flag);
+
 /* ---- measurement helpers (bench.py only) ----------------------------------------------------
  * sa_launch_count: kernels enqueued by this library since the last reset (bench.py "gpu_launches").
  * sa_microbench_fp64 / sa_microbench_l2_read: the FP64-FMA and L2-read roofline denominators that

@@ -27,6 +27,8 @@ SIGNATURES = {
                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sa_saltelli_eval_ishigami_f64": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _i32, _vp, _i32, _vp, _vp,
                                                 _vp, _vp, _dbl, _dbl, _vp]),
+    "sa_discrepancy_workspace_bytes": (_sz, [_u64, _i32]),
+    "sa_discrepancy_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sa_moments_workspace_bytes": (_sz, []),
     "sa_moments_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _sz]),
     "sa_row_stride": (C.c_int, [_i32, _i32]),

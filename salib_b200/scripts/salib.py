@@ -9,6 +9,7 @@ sample/sobol.py:192-251, sample/saltelli.py:205-264, analyze/sobol.py:442-491)::
     salib analyze sobol   -p params.txt -Y Y.txt [-c 0] [--max-order 2] [-r 100] [-s SEED]
     salib sample finite_diff -n 1000 -p params.txt -o X.txt [-d 0.01]
     salib analyze dgsm    -p params.txt -X X.txt -Y Y.txt [-c 0] [-r 1000] [-s SEED]
+    salib analyze discrepancy -p params.txt -X X.txt -Y Y.txt [-c 0]
 
 Text I/O stays NumPy's (``np.savetxt`` with ``%.<precision>e``, ``np.loadtxt``) so files are byte-identical to
 the reference's; the numbers come from the CUDA path."""
@@ -20,7 +21,7 @@ import numpy as np
 from ..util.util_funcs import read_param_file
 
 SAMPLERS = ("saltelli", "sobol", "finite_diff")
-ANALYZERS = ("sobol", "dgsm")
+ANALYZERS = ("sobol", "dgsm", "discrepancy")
 
 
 def _sample_parser(method):
@@ -54,6 +55,9 @@ def _analyze_parser(method):
     p.add_argument("-c", "--column", type=int, required=False, default=0, help="Column of output to analyze")
     p.add_argument("--delimiter", type=str, required=False, default=" ", help="Column delimiter in model output file")
     p.add_argument("-s", "--seed", type=int, required=False, default=None, help="Random Seed")
+    if method == "discrepancy":  # analyze/discrepancy.py:124-146 (its cli_action passes only the seed on)
+        p.add_argument("-X", "--model-input-file", type=str, required=True, help="Model input file")
+        return p
     if method == "dgsm":  # analyze/dgsm.py:143-161
         p.add_argument("-X", "--model-input-file", type=str, required=True, default=None, help="Model input file")
         p.add_argument("-r", "--resamples", type=int, required=False, default=1000,
@@ -98,6 +102,12 @@ def run_analyze(method, opts):
 
     problem = read_param_file(args.paramfile)
     Y = np.loadtxt(args.model_output_file, delimiter=args.delimiter, usecols=(args.column,))
+    if method == "discrepancy":
+        from ..analyze import discrepancy
+
+        X = np.loadtxt(args.model_input_file, delimiter=args.delimiter)
+        discrepancy.analyze(problem, X, Y, print_to_console=True, seed=args.seed)
+        return
     if method == "dgsm":
         from ..analyze import dgsm
 

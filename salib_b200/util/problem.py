@@ -167,6 +167,11 @@ class ProblemSpec(dict):
 
         return self.analyze(dgsm.analyze, *args, **kwargs)
 
+    def analyze_discrepancy(self, *args, **kwargs):
+        from ..analyze import discrepancy
+
+        return self.analyze(discrepancy.analyze, *args, **kwargs)
+
     # -- views -----------------------------------------------------------------------------
     def to_df(self):
         res = self._analysis
