@@ -147,9 +147,13 @@ int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int se
  *   sa_counts_from_indices: d_r int64 [N, R] C-order as numpy draws it; resamples
  *                           [c0, c0+count) -> d_w[count][Npad].  d_w must be zeroed by the call
  *                           (it is: the function memsets it on `stream`).
- *   sa_counts_philox:       device Philox4x32-10 draw of N iid uniform indices per resample,
- *                           keyed by (seed, global resample id c0+c, draw t): independent of
- *                           how resamples are sharded over GPUs.
+ *   sa_counts_philox:       device Philox4x32-10 draw of N iid uniform indices per resample, as
+ *                           multiplicities ~ Multinomial(N, 1/N): a tree of Binomial(n, 1/2) splits
+ *                           (popcounts of n random bits) down to windows of <= 32768 rows, then
+ *                           uniform draws inside each window, histogrammed in shared memory
+ *                           (when 2^L | N; otherwise N direct draws with global atomics).  Counters
+ *                           are keyed by (seed, global resample id c0+c, tree node | window, word):
+ *                           independent of batching and of how resamples or rows are sharded over GPUs.
  * d_overflow (int32, may be NULL) is set to 1 if any multiplicity exceeded 255.
  * The *_rows forms keep only the draws that land in the row window [row0, row0+nrows) of the N rows and
  * write d_w[count][sa_pad_rows(nrows)] indexed from row0: the multiplicities of one row shard when Y is

@@ -277,6 +277,153 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t row0, uint
   }
 }
 
+// Same distribution without global atomics (the kernel above is bound by the L2 RED rate, 2.2e11/s).
+// The N draws of a resample are a multinomial over the rows; a multinomial splits exactly: the number of
+// draws that land in the left half of a row range holding n draws is Binomial(n, 1/2) -- the popcount of n
+// random bits -- and the draws inside a range are iid uniform over it.  One block owns one resample: it
+// walks L levels of that tree in shared memory (N random bits per level) down to windows of W = N / 2^L
+// <= 32768 rows, then fills one window at a time: n_w uniform draws into a W-byte shared-memory
+// histogram (shared atomics), copied out as coalesced words.  Philox counters are keyed by (seed,
+// resample id, tree node | window, word), so the multiplicities of a resample do not depend on the batch,
+// the GPU or the row window it is generated for.  Requires 2^L | N (N <= 32768: L = 0, any N).
+constexpr int kWinMax = 32768;
+constexpr int kWinThreads = 256;
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch) {
+  v = __reduce_add_sync(kFull, v);
+  __syncthreads();
+  if (threadIdx.x == 0) *scratch = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(scratch, v);
+  __syncthreads();
+  return *scratch;
+}
+
+// popcount of the first min(128, n - 128*word) bits of the 128-bit Philox block `word` of tree node (level, j)
+__device__ __forceinline__ uint32_t tree_bits(uint32_t k0, uint32_t k1, uint64_t c, int level, uint32_t j,
+                                              uint32_t word, uint32_t n) {
+  const Philox4 p = philox4x32_10(word, 0x80000000u | ((uint32_t)level << 20) | j, (uint32_t)c,
+                                  (uint32_t)(c >> 32), k0, k1);
+  const uint32_t left = n - (word << 7);
+  uint32_t v[4] = {p.x, p.y, p.z, p.w};
+  uint32_t s = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t lo = 32u * q;
+    if (left >= lo + 32) s += __popc(v[q]);
+    else if (left > lo) s += __popc(v[q] & ((1u << (left - lo)) - 1u));
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kWinThreads)
+counts_window_kernel(uint64_t seed, uint64_t N, uint64_t c0, int L, uint64_t row0, uint64_t nrows,
+                     uint64_t Npad, uint8_t *__restrict__ w) {
+  extern __shared__ __align__(16) uint32_t wsm[];
+  const uint32_t W = (uint32_t)(N >> L);
+  uint32_t *hist = wsm;                       // W bytes (rounded up to words)
+  uint32_t *heap = wsm + ((W + 3) >> 2) + 1;  // heap[k]: draws in node k (root 1, children 2k, 2k+1)
+  uint32_t *scratch = wsm + ((W + 3) >> 2);
+  const uint64_t c = c0 + blockIdx.x;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) heap[1] = (uint32_t)N;
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const uint32_t nodes = 1u << l;
+    if (nodes < kWinThreads / 32) {
+      for (uint32_t j = 0; j < nodes; ++j) {
+        const uint32_t n = heap[nodes + j];
+        const uint32_t words = (n + 127) >> 7;
+        uint32_t sum = 0;
+        for (uint32_t wd = tid; wd < words; wd += kWinThreads) sum += tree_bits(k0, k1, c, l, j, wd, n);
+        sum = block_sum_u32(sum, scratch);
+        if (tid == 0) {
+          heap[2 * (nodes + j)] = sum;
+          heap[2 * (nodes + j) + 1] = n - sum;
+        }
+        __syncthreads();
+      }
+    } else {
+      for (uint32_t j = warp; j < nodes; j += kWinThreads / 32) {
+        const uint32_t n = heap[nodes + j];
+        const uint32_t words = (n + 127) >> 7;
+        uint32_t sum = 0;
+        for (uint32_t wd = lane; wd < words; wd += 32) sum += tree_bits(k0, k1, c, l, j, wd, n);
+        sum = __reduce_add_sync(kFull, sum);
+        if (lane == 0) {
+          heap[2 * (nodes + j)] = sum;
+          heap[2 * (nodes + j) + 1] = n - sum;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  const bool pow2 = (W & (W - 1)) == 0;
+  const int shift16 = 16 - (31 - __clz(W));  // W = 2^b, b <= 15: index = 16-bit field >> (16 - b)
+  const uint32_t nwin = 1u << L;
+  const uint32_t win_lo = (uint32_t)(row0 / W), win_hi = (uint32_t)((row0 + nrows - 1) / W);
+  uint8_t *wrow = w + (uint64_t)blockIdx.x * Npad;
+  for (uint32_t v = win_lo; v <= win_hi && v < nwin; ++v) {
+    const uint32_t n = heap[nwin + v];
+    for (uint32_t k = tid; k < ((W + 3) >> 2); k += kWinThreads) hist[k] = 0;
+    __syncthreads();
+    if (pow2) {
+      const uint32_t calls = (n + 7) >> 3;
+      for (uint32_t q = tid; q < calls; q += kWinThreads) {
+        const Philox4 p = philox4x32_10(q, 0x40000000u | v, (uint32_t)c, (uint32_t)(c >> 32), k0, k1);
+        const uint32_t f[4] = {p.x, p.y, p.z, p.w};
+        const uint32_t left = n - (q << 3);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          if ((uint32_t)d < left) {
+            const uint32_t idx = ((f[d >> 1] >> (16 * (d & 1))) & 0xffffu) >> shift16;
+            atomicAdd(hist + (idx >> 2), 1u << (8u * (idx & 3)));
+          }
+        }
+      }
+    } else {
+      const uint32_t calls = (n + 1) >> 1;
+      for (uint32_t q = tid; q < calls; q += kWinThreads) {
+        const Philox4 p = philox4x32_10(q, 0x40000000u | v, (uint32_t)c, (uint32_t)(c >> 32), k0, k1);
+        const uint32_t i0 = (uint32_t)__umul64hi(((uint64_t)p.y << 32) | p.x, (uint64_t)W);
+        atomicAdd(hist + (i0 >> 2), 1u << (8u * (i0 & 3)));
+        if (2 * q + 1 < n) {
+          const uint32_t i1 = (uint32_t)__umul64hi(((uint64_t)p.w << 32) | p.z, (uint64_t)W);
+          atomicAdd(hist + (i1 >> 2), 1u << (8u * (i1 & 3)));
+        }
+      }
+    }
+    __syncthreads();
+    // rows [lo, lo+W) of the window, clipped to the caller's row range, -> wrow[row - row0]
+    const uint64_t lo = (uint64_t)v * W;
+    const uint32_t r0 = (uint32_t)(row0 > lo ? row0 - lo : 0);
+    const uint32_t r1 = (uint32_t)((row0 + nrows < lo + W) ? row0 + nrows - lo : W);
+    const int64_t dst0 = (int64_t)lo - (int64_t)row0;  // destination of window row 0
+    if (((dst0 | (int64_t)r0) & 3) == 0) {
+      uint32_t *dw = reinterpret_cast<uint32_t *>(wrow + dst0);
+      const uint32_t full = r1 >> 2;
+      for (uint32_t k = (r0 >> 2) + tid; k < full; k += kWinThreads) dw[k] = hist[k];
+      const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
+      for (uint32_t r = (full << 2) + tid; r < r1; r += kWinThreads) wrow[dst0 + r] = hb[r];
+    } else {
+      const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
+      for (uint32_t r = r0 + tid; r < r1; r += kWinThreads) wrow[dst0 + (int64_t)r] = hb[r];
+    }
+    __syncthreads();
+  }
+}
+
+// levels of the split tree for N rows; -1 if the window scheme does not apply (2^L does not divide N)
+static int window_levels(uint64_t N) {
+  int L = 0;
+  while ((N >> L) > (uint64_t)kWinMax) ++L;
+  if (L > 16 || (N & ((1ull << L) - 1)) != 0) return -1;
+  return L;
+}
+
 // ------------------------------------------------------------------------------------------
 // second-order accumulate (production kernel for Dg <= 64): warp <-> resample,
 // lane <-> 8x8 (j,k) register tile, rows staged in shared memory
@@ -1395,6 +1542,26 @@ extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, ui
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t Npad = pad_rows(nrows);
   SA_CUDA(cudaMemsetAsync(d_w, 0, count * Npad, st));
+  const int L = window_levels(N);
+  if (L >= 0) {
+    // every byte of the row window is written by the kernel; only the pad bytes need the memset above
+    const uint32_t W = (uint32_t)(N >> L);
+    const size_t smem = ((size_t)((W + 3) >> 2) + 1 + ((size_t)2 << L)) * sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+      SA_CUDA(cudaFuncSetAttribute(counts_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_done = true;
+    }
+    SA_REQUIRE(smem <= 96 * 1024, SA_ERR_ARG, "sa_counts_philox: N too large");
+    for (uint64_t done = 0; done < count; done += 1u << 30) {
+      const uint64_t nb = (count - done < (1u << 30)) ? count - done : (1u << 30);
+      counts_window_kernel<<<(unsigned)nb, kWinThreads, smem, st>>>(seed, N, c0 + done, L, row0, nrows, Npad,
+                                                                  d_w + done * Npad);
+      note_launches(1);
+    }
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+  }
   const uint64_t npairs = (N + 1) / 2;
   uint64_t bx = ceil_div_u64(npairs, 256 * 4);
   if (bx < 1) bx = 1;

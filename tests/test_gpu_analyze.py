@@ -363,3 +363,40 @@ def test_row_sharded_philox_equals_unsharded():
     _cmp(S, ref, D, True)
     with pytest.raises(RuntimeError):
         sobol.analyze_row_sharded(p, [(0, Y[:1000 * step])], N, num_resamples=10, seed=7)
+
+
+@pytest.mark.parametrize("N", [1 << 15, 1 << 16, 1 << 18, 100000, 99999, 40000 * 4])
+def test_philox_multiplicities_are_multinomial(N):
+    """Shared-memory window scheme (binomial split tree + in-window draws; N = 99999 takes the global-atomic
+    fallback): every resample has exactly N draws, and the multiplicities behave like Multinomial(N, 1/N):
+    mean 1, variance 1 - 1/N, P(w = k) = Poisson(1) to sampling error, no structure across windows."""
+    import torch
+
+    from salib_b200 import _lib, _runtime as rt
+
+    R = 24
+    Npad = int(_lib.lib().sa_pad_rows(N))
+    w = rt.empty((R * Npad,), torch.uint8)
+    _lib.call("sa_counts_philox", rt.stream_ptr(), 1234, N, 0, R, rt.ptr(w), None)
+    wc = w.reshape(R, Npad).cpu().numpy()
+    assert (wc[:, :N].sum(axis=1, dtype=np.int64) == N).all() and not wc[:, N:].any()
+    x = wc[:, :N].astype(np.float64)
+    M = R * N
+    assert abs(x.var() - (1.0 - 1.0 / N)) < 6.0 * np.sqrt(2.0 / M) + 6.0 / np.sqrt(M)   # var of Poisson-like counts
+    from math import exp, factorial
+    for k in range(5):
+        pk = exp(-1.0) / factorial(k)
+        assert abs((x == k).mean() - pk) < 6.0 * np.sqrt(pk * (1 - pk) / M) + 2.0 / N
+    # draws per block of 4096 rows ~ Binomial(N, 4096/N): chi-square over blocks and resamples
+    nb = N // 4096
+    blocks = x[:, :nb * 4096].reshape(R, nb, 4096).sum(axis=2)
+    chi = ((blocks - 4096.0) ** 2 / 4096.0).sum()
+    dof = R * nb
+    assert abs(chi - dof) < 6.0 * np.sqrt(2.0 * dof)
+    # adjacent rows are uncorrelated
+    corr = np.mean((x[:, :-1] - 1.0) * (x[:, 1:] - 1.0))
+    assert abs(corr) < 6.0 / np.sqrt(M)
+    # determinism and independence of the batch: resample 7 drawn alone equals row 7 of the batch
+    w1 = rt.empty((Npad,), torch.uint8)
+    _lib.call("sa_counts_philox", rt.stream_ptr(), 1234, N, 7, 1, rt.ptr(w1), None)
+    assert np.array_equal(w1.cpu().numpy(), wc[7])
