@@ -118,9 +118,12 @@ def plan_row_splits(kind, count, N, sms, nacc, groups=1):
     max_split = max(1, min(4096, N // 32))
     if kind in (4, 5):   # tile kernels: `groups` warps per resample, 8 warps per block, one block per SM
         blocks = -(-count // 8) * groups
-    elif kind == 3:      # first-order GEMV kernel: 256 resamples per block, ~4 resident blocks per SM
-        blocks = -(-count // 256) * -(-nacc // 32)
-        return max(1, min(max_split, (4 * sms) // blocks))
+    elif kind == 3:      # first-order GEMV kernel (launch_feature_gemv in analyze.cu)
+        if count > 256:  # two resamples per lane, blocks of 4 warps = 256 resamples, 3 resident per SM
+            blocks, resident = -(-count // 256) * -(-nacc // 32), 3
+        else:            # one resample per lane, one block of up to 8 warps
+            blocks, resident = -(-nacc // 32), 4
+        return max(1, min(max_split, (resident * sms) // blocks))
     else:                # generic kernel: one block per resample
         blocks = count
     return max(1, min(max_split, sms // blocks if blocks <= sms else 1))

@@ -1118,7 +1118,14 @@ normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int 
 
 constexpr int kFoStages = 4;
 
-template <int CH>  // accumulators (features) per lane = chunk width of the feature matrix: 8, 16, 24 or 32
+// CH: features per chunk (= chunk width of the feature matrix: 8, 16, 24 or 32); RPL: resamples per lane;
+// FPW: features per warp (CH / FPW warps share a group of 32 * RPL resamples, each taking FPW features).
+// A warp-uniform LDS.128 costs 2 crossbar wavefronts (of the SM's 1 per clock) for 2 features; the 2 DFMAs it
+// feeds with one resample per lane cost 4 pipe-clocks on one of 4 schedulers = 1 SM-clock: <CH, 1, CH> is
+// crossbar-bound at half the FP64 rate (measured 89 % of that bound; used for launches of <= 256
+// resamples).  <CH, 2, CH> reuses every broadcast for 4 DFMAs, which balances the two pipes (cfg2: 3.1 -> 2.65
+// ms; FP64 pipe 55 %, crossbar 55 % -- the rest is the lane-strided weight fetch, see launch_feature_gemv).
+template <int CH, int RPL, int FPW>
 __global__ void __launch_bounds__(kFoWarps * 32)
 fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__restrict__ w, uint64_t Npad,
                uint64_t count, uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
@@ -1128,8 +1135,11 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
   // 32-row tiles (contiguous in HBM) by cp.async.bulk, one mbarrier per stage, last warp out refills.
   extern __shared__ __align__(128) unsigned char smraw[];
   const int lane = threadIdx.x & 31;
-  const uint64_t c = ((uint64_t)blockIdx.x * kFoWarps + (threadIdx.x >> 5)) * 32 + lane;
-  const bool live = c < count;
+  constexpr int FG = CH / FPW;               // warps per resample group
+  const uint32_t nwarps = blockDim.x >> 5;   // a multiple of FG
+  const uint32_t warp = threadIdx.x >> 5;
+  const int fq = (int)(warp % FG) * FPW;     // first feature (within the chunk) of this warp
+  const uint64_t cbase = ((uint64_t)blockIdx.x * (nwarps / FG) + warp / FG) * (32 * RPL) + lane;
   const int sp = blockIdx.y;
   const int q0 = blockIdx.z * CH;
   const uint64_t row0 = (uint64_t)sp * rows_per_split;
@@ -1159,47 +1169,73 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
   if (threadIdx.x == 0)
     for (int t = 0; t < kFoStages && t < ntiles; ++t) issue(t);
 
-  double acc[CH];
+  double acc[RPL][FPW];
+  const uint8_t *wrow[RPL];
+  double ones[RPL];
 #pragma unroll
-  for (int q = 0; q < CH; ++q) acc[q] = 0.0;
-  const uint8_t *wrow = (w && live) ? w + c * Npad : nullptr;
-  const double ones = (!w && live) ? 1.0 : 0.0;  // point estimate: weight 1 for every row
-  // this lane's 32 weights of a tile (rows_per_split is a multiple of 32, Npad of 128: in bounds)
-  auto load_w = [&](int t, uint4 &wa, uint4 &wb) {
-    wa = make_uint4(0, 0, 0, 0);
-    wb = wa;
-    if (wrow && t < ntiles) {
-      const uint8_t *p = wrow + row0 + (uint64_t)t * kFoRows;
-      wa = __ldg(reinterpret_cast<const uint4 *>(p));
-      wb = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+  for (int k = 0; k < RPL; ++k) {
+#pragma unroll
+    for (int q = 0; q < FPW; ++q) acc[k][q] = 0.0;
+    const uint64_t c = cbase + 32u * k;
+    wrow[k] = (w && c < count) ? w + c * Npad : nullptr;
+    ones[k] = (!w && c < count) ? 1.0 : 0.0;  // point estimate: weight 1 for every row
+  }
+  // this lane's weights, 16 rows (one uint4 per resample) at a time: half-tile u covers rows [16u, 16u+16) of
+  // the split (rows_per_split is a multiple of 32, Npad of 128: in bounds); fetched one half-tile ahead
+  auto load_w = [&](int u, uint4 (&wn)[RPL]) {
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      wn[k] = make_uint4(0, 0, 0, 0);
+      if (wrow[k] && u < 2 * ntiles) wn[k] = __ldg(reinterpret_cast<const uint4 *>(wrow[k] + row0 + 16u * (uint64_t)u));
     }
   };
-  uint4 na, nb;
-  load_w(0, na, nb);
+  uint4 wn[RPL];
+  load_w(0, wn);
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kFoStages;
-    const uint32_t wreg[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-    load_w(t + 1, na, nb);
     const uint64_t i0 = row0 + (uint64_t)t * kFoRows;
     const int nrows = (int)((row1 - i0 < (uint64_t)kFoRows) ? (row1 - i0) : kFoRows);
     while (!mbar_try_wait(bar_base + 8u * s, (uint32_t)(t / kFoStages) & 1u)) {
     }
     const uint32_t tile = sm_base + s * stage_bytes;
-#pragma unroll
+    // 4 rows per iteration; the loop is kept rolled (the weight words rotate through wreg[k][0]) so that the
+    // body stays in the instruction cache
+    uint32_t wreg[RPL][4];
+#pragma unroll 1
     for (int wi = 0; wi < 8; ++wi) {
+      if ((wi & 3) == 0) {  // uniform: start of a half-tile
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          wreg[k][0] = wn[k].x; wreg[k][1] = wn[k].y; wreg[k][2] = wn[k].z; wreg[k][3] = wn[k].w;
+        }
+        load_w(2 * t + (wi >> 2) + 1, wn);
+      }
+      uint32_t cur[RPL];
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        cur[k] = wreg[k][0];
+        wreg[k][0] = wreg[k][1]; wreg[k][1] = wreg[k][2]; wreg[k][2] = wreg[k][3];
+      }
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
         const int r = 4 * wi + bb;
         if (r < nrows) {  // uniform; false only in the last tile of a split
-          const uint32_t byte = (wreg[wi] >> (8 * bb)) & 0xffu;
-          // small integer -> double without the conversion pipe: 2^52 + n has n in the low mantissa bits
-          const double wv = w ? (__hiloint2double(0x43300000, (int)byte) - 4503599627370496.0) : ones;
-          const uint32_t f = tile + (uint32_t)r * row_bytes;
+          double wv[RPL];
 #pragma unroll
-          for (int q = 0; q < CH; q += 2) {
+          for (int k = 0; k < RPL; ++k) {
+            const uint32_t byte = (cur[k] >> (8 * bb)) & 0xffu;
+            // small integer -> double without the conversion pipe: 2^52 + n has n in the low mantissa bits
+            wv[k] = w ? (__hiloint2double(0x43300000, (int)byte) - 4503599627370496.0) : ones[k];
+          }
+          const uint32_t f = tile + (uint32_t)r * row_bytes + 8u * (uint32_t)fq;
+#pragma unroll
+          for (int q = 0; q < FPW; q += 2) {
             const double2 v = lds_f64x2(f + 8u * q);  // warp-uniform address: one broadcast
-            acc[q] = fma(wv, v.x, acc[q]);
-            acc[q + 1] = fma(wv, v.y, acc[q + 1]);
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+              acc[k][q] = fma(wv[k], v.x, acc[k][q]);
+              acc[k][q + 1] = fma(wv[k], v.y, acc[k][q + 1]);
+            }
           }
         }
       }
@@ -1211,17 +1247,21 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
                    : "=r"(old)
                    : "r"(smem_u32(cnt + s))
                    : "memory");
-      if (old == kFoWarps - 1) {
+      if (old == nwarps - 1) {
         cnt[s] = 0;
         if (t + kFoStages < ntiles) issue(t + kFoStages);
       }
     }
   }
-  if (!live) return;
-  double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
 #pragma unroll
-  for (int q = 0; q < CH; ++q)
-    if (q0 + q < nacc) out[q0 + q] = acc[q];
+  for (int k = 0; k < RPL; ++k) {
+    const uint64_t c = cbase + 32u * k;
+    if (c >= count) continue;
+    double *out = psum + ((uint64_t)sp * count + c) * (uint64_t)nacc;
+#pragma unroll
+    for (int q = 0; q < FPW; ++q)
+      if (q0 + fq + q < nacc) out[q0 + fq + q] = acc[k][q];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1364,23 +1404,30 @@ __global__ void __launch_bounds__(128)
 finalize_kernel(const double *__restrict__ psum, uint64_t N, int Dg, int second_order, uint64_t count,
                 int nsplit, const double *__restrict__ stats, double *__restrict__ est, int nacc, int nest) {
   const uint64_t c = blockIdx.x;
-  __shared__ double sc[5];
-  extern __shared__ double s1sh[];  // [Dg]
-  auto total = [&](int a) {
-    double v = 0.0;
-    for (int sp = 0; sp < nsplit; ++sp) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
-    return v;
-  };
-  const bool constant = !(stats[4] < stats[5]);  // ptp([A;B]) == 0 (or NaN)
-  if (threadIdx.x < 5) sc[threadIdx.x] = total(threadIdx.x);
+  extern __shared__ double fsh[];
+  double *s1sh = fsh;        // [Dg]
+  double *tot = fsh + Dg;    // [nacc] sums over the row splits (fixed order: deterministic)
+  if (nsplit == 1) {
+    for (int a = threadIdx.x; a < nacc; a += blockDim.x) tot[a] = psum[c * (uint64_t)nacc + a];
+  } else {
+    // one warp per accumulator, lanes stride over the splits: the loads of a sum are in flight together
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int a = threadIdx.x >> 5; a < nacc; a += nw) {
+      double v = 0.0;
+      for (int sp = lane; sp < nsplit; sp += 32) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
+      v = warp_sum(v);
+      if (lane == 0) tot[a] = v;
+    }
+  }
   __syncthreads();
+  const bool constant = !(stats[4] < stats[5]);  // ptp([A;B]) == 0 (or NaN)
   const double n = (double)N;
-  const double m = (sc[0] + sc[1]) / (2.0 * n);
-  const double V = (sc[2] + sc[3]) / (2.0 * n) - m * m;
+  const double m = (tot[0] + tot[1]) / (2.0 * n);
+  const double V = (tot[2] + tot[3]) / (2.0 * n) - m * m;
   double *o = est + c * (uint64_t)nest;
   for (int j = threadIdx.x; j < Dg; j += blockDim.x) {
-    const double s1 = constant ? 0.0 : (total(5 + j) / n) / V;
-    const double st = constant ? 0.0 : 0.5 * (total(5 + Dg + j) / n) / V;
+    const double s1 = constant ? 0.0 : (tot[5 + j] / n) / V;
+    const double st = constant ? 0.0 : 0.5 * (tot[5 + Dg + j] / n) / V;
     s1sh[j] = s1;
     o[j] = s1;
     o[Dg + j] = st;
@@ -1388,12 +1435,12 @@ finalize_kernel(const double *__restrict__ psum, uint64_t N, int Dg, int second_
   __syncthreads();
   if (second_order) {
     const int npairs = Dg * (Dg - 1) / 2;
-    const double mab = sc[4] / n;
+    const double mab = tot[4] / n;
     for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
       int q = p, j = 0;
       while (q >= Dg - 1 - j) { q -= Dg - 1 - j; ++j; }
       const int k = j + 1 + q;
-      const double vjk = (total(5 + 2 * Dg + p) / n - mab) / V;
+      const double vjk = (tot[5 + 2 * Dg + p] / n - mab) / V;
       o[2 * Dg + p] = constant ? 0.0 : vjk - s1sh[j] - s1sh[k];
     }
   }
@@ -1437,12 +1484,23 @@ using namespace sa;
 static int launch_feature_gemv(cudaStream_t st, const double *d_F, uint64_t N, int nfeat, const uint8_t *d_w,
                                uint64_t Npad, uint64_t count, int nsplit, uint64_t rps, double *d_psum) {
   const int ch = chunk_width(nfeat), nz = chunk_count(nfeat);
-  const uint64_t bx = ceil_div_u64(count, (uint64_t)kFoWarps * 32);
-  SA_REQUIRE(bx < (1ull << 31) && nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
-  dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-  auto kern = ch == 8 ? fo_gemv_kernel<8> : (ch == 16 ? fo_gemv_kernel<16> : (ch == 24 ? fo_gemv_kernel<24> : fo_gemv_kernel<32>));
+  SA_REQUIRE(nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
   const size_t smem = (size_t)kFoStages * kFoRows * ch * 8 + kFoStages * 12 + 16;
-  kern<<<grid, kFoWarps * 32, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+  if (count > (uint64_t)kFoWarps * 32) {
+    // <CH, 2, CH>: two resamples per lane; ~165 registers, so blocks of 4 warps (256 resamples), 3 per SM.
+    // (<CH, 4, 8> -- 4 per lane, CH/8 warps per resample group -- was measured slower, 3.55 vs 2.65 ms on cfg2:
+    // every warp of a group re-reads the group's weight bytes with lane-strided 16-byte loads.)
+    const uint64_t bx = ceil_div_u64(count, 256);
+    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
+    dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
+    auto kern = ch == 8 ? fo_gemv_kernel<8, 2, 8> : (ch == 16 ? fo_gemv_kernel<16, 2, 16> : (ch == 24 ? fo_gemv_kernel<24, 2, 24> : fo_gemv_kernel<32, 2, 32>));
+    kern<<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+  } else {
+    dim3 grid(1, (unsigned)nsplit, (unsigned)nz);
+    auto kern = ch == 8 ? fo_gemv_kernel<8, 1, 8> : (ch == 16 ? fo_gemv_kernel<16, 1, 16> : (ch == 24 ? fo_gemv_kernel<24, 1, 24> : fo_gemv_kernel<32, 1, 32>));
+    const unsigned threads = (unsigned)(32 * ceil_div_u64(count, 32));  // only warps that own a resample
+    kern<<<grid, threads, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+  }
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -1669,7 +1727,14 @@ extern "C" int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_
   SA_REQUIRE(d_psum && d_stats && d_est, SA_ERR_ARG, "sa_sobol_finalize_f64: null pointer");
   SA_REQUIRE(N >= 1 && Dg >= 1 && count >= 1 && nsplit >= 1, SA_ERR_ARG, "sa_sobol_finalize_f64: bad shape");
   SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
-  finalize_kernel<<<(unsigned)count, 128, (size_t)Dg * sizeof(double), (cudaStream_t)stream>>>(
+  const size_t fin_smem = ((size_t)Dg + SA_NACC(Dg, second_order)) * sizeof(double);
+  static size_t fin_attr = 48 * 1024;
+  if (fin_smem > fin_attr) {
+    SA_REQUIRE(fin_smem <= 200 * 1024, SA_ERR_UNSUPPORTED, "sa_sobol_finalize_f64: Dg too large");
+    SA_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    fin_attr = fin_smem;
+  }
+  finalize_kernel<<<(unsigned)count, 128, fin_smem, (cudaStream_t)stream>>>(
       d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
       SA_NEST(Dg, second_order));
   note_launches(1);
