@@ -232,6 +232,42 @@ int sa_discrepancy_f64(void *stream, const double *d_X, const double *d_Y, uint6
                        const double *d_lb, const double *d_ub, int method, int Dg, const int32_t *d_gcol,
                        double *d_out, double *d_disc, void *d_work, size_t work_bytes, int32_t *d_flag);
 
+/* ---- text output ---------------------------------------------------------------
+ * The reference's CLI writes samples with np.savetxt(fmt="%.<precision>e") (sample/common_args.py via
+ * sample/sobol.py:247-251, saltelli.py, finite_diff.py cli_action).  These two calls produce the same bytes
+ * on the device: every value is its exact binary value rounded half-to-even to precision+1 significant
+ * digits, as CPython/glibc print it ("nan", "inf", "-inf" for non-finite values).
+ *   sa_format_values_f64: d_x [rows, cols] -> d_slots [rows*cols][sa_text_slot_bytes()] (the characters of
+ *     each value), d_lens [rows*cols] (their count), d_rowlen [rows] (bytes of each text row including
+ *     delimiters and the newline).  0 <= precision <= 17.
+ *   sa_pack_text_rows: d_rowoff [rows] = exclusive prefix sum of d_rowlen (the caller scans); writes the rows
+ *     "v0<delim>v1...<delim>vn\n" at d_text + d_rowoff[r].                                               */
+int sa_text_slot_bytes(void);
+int sa_format_values_f64(void *stream, const double *d_x, uint64_t rows, int cols, int precision,
+                         uint8_t *d_slots, uint8_t *d_lens, int64_t *d_rowlen);
+int sa_pack_text_rows(void *stream, const uint8_t *d_slots, const uint8_t *d_lens, uint64_t rows, int cols,
+                      int delimiter, const int64_t *d_rowoff, uint8_t *d_text);
+
+/* ---- text input -----------------------------------------------------------------
+ * np.loadtxt as the reference's CLI uses it (analyze/sobol.py:476-491, dgsm.py:151-161, discrepancy.py:131-146):
+ * rectangular numeric text -> float64, every token converted as Python's float() does (correctly rounded;
+ * "nan", "inf", "infinity" in any case), '#' comments and blank lines skipped.
+ *   sa_text_count_newlines: d_blockcount[ceil(len / sa_text_parse_chunk_bytes())] = newlines per chunk.
+ *   sa_text_line_starts:    d_blockoff = exclusive prefix sum of d_blockcount (the caller scans);
+ *                           d_linestart[l] = byte offset of line l, l < nlines = newlines + 1.
+ *   sa_text_parse_lines:    one thread per line.  delimiter 0 = runs of blanks/tabs, else that byte.
+ *       mode 0: d_ntok[l] = number of fields on line l (0 for blank / comment lines);
+ *       mode 1: d_out[d_rowidx[l]][0..cols) = the converted fields (d_rowidx: index among non-blank lines).
+ *   d_flag (int32, zeroed by the caller): bit 0 a field is not a decimal float literal, bit 1 a line has a
+ *   different number of fields, bit 2 a field has more than 40 significant digits (not converted).        */
+int sa_text_parse_chunk_bytes(void);
+int sa_text_count_newlines(void *stream, const uint8_t *d_text, uint64_t len, int64_t *d_blockcount);
+int sa_text_line_starts(void *stream, const uint8_t *d_text, uint64_t len, const int64_t *d_blockoff,
+                        int64_t *d_linestart);
+int sa_text_parse_lines(void *stream, const uint8_t *d_text, uint64_t len, const int64_t *d_linestart,
+                        uint64_t nlines, int delimiter, int mode, int32_t *d_ntok, const int64_t *d_rowidx,
+                        int cols, double *d_out, int32_t *d_flag);
+
 /* ---- measurement helpers (bench.py only) ----------------------------------------------------
  * sa_launch_count: kernels enqueued by this library since the last reset (bench.py "gpu_launches").
  * sa_microbench_fp64 / sa_microbench_l2_read: the FP64-FMA and L2-read roofline denominators that

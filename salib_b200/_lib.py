@@ -29,6 +29,13 @@ SIGNATURES = {
                                                 _vp, _vp, _dbl, _dbl, _vp]),
     "sa_discrepancy_workspace_bytes": (_sz, [_u64, _i32]),
     "sa_discrepancy_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sa_text_slot_bytes": (C.c_int, []),
+    "sa_format_values_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]),
+    "sa_pack_text_rows": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _vp]),
+    "sa_text_parse_chunk_bytes": (C.c_int, []),
+    "sa_text_count_newlines": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "sa_text_line_starts": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
+    "sa_text_parse_lines": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "sa_moments_workspace_bytes": (_sz, []),
     "sa_moments_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _sz]),
     "sa_row_stride": (C.c_int, [_i32, _i32]),

@@ -18,6 +18,7 @@ import sys
 
 import numpy as np
 
+from ..util.textio import loadtxt, savetxt
 from ..util.util_funcs import read_param_file
 
 SAMPLERS = ("saltelli", "sobol", "finite_diff")
@@ -80,7 +81,7 @@ def run_sample(method, opts):
         from ..sample import finite_diff
 
         X = finite_diff.sample(problem, args.samples, args.delta, seed=args.seed)
-        np.savetxt(args.output, X, delimiter=args.delimiter, fmt="%." + str(args.precision) + "e")
+        savetxt(args.output, X, delimiter=args.delimiter, precision=args.precision)
         return
     second = args.max_order == 2
     if method == "saltelli":
@@ -93,7 +94,7 @@ def run_sample(method, opts):
         # like the reference's cli_action (sample/sobol.py:240-245), --skip-values and --seed are parsed
         # but not forwarded
         X = sobol.sample(problem, args.samples, calc_second_order=second, scramble=args.scramble)
-    np.savetxt(args.output, X, delimiter=args.delimiter, fmt="%." + str(args.precision) + "e")
+    savetxt(args.output, X, delimiter=args.delimiter, precision=args.precision)
 
 
 def run_analyze(method, opts):
@@ -101,17 +102,17 @@ def run_analyze(method, opts):
     from ..analyze import sobol
 
     problem = read_param_file(args.paramfile)
-    Y = np.loadtxt(args.model_output_file, delimiter=args.delimiter, usecols=(args.column,))
+    Y = loadtxt(args.model_output_file, delimiter=args.delimiter, usecols=(args.column,))
     if method == "discrepancy":
         from ..analyze import discrepancy
 
-        X = np.loadtxt(args.model_input_file, delimiter=args.delimiter)
+        X = loadtxt(args.model_input_file, delimiter=args.delimiter)
         discrepancy.analyze(problem, X, Y, print_to_console=True, seed=args.seed)
         return
     if method == "dgsm":
         from ..analyze import dgsm
 
-        X = np.loadtxt(args.model_input_file, delimiter=args.delimiter, ndmin=2)
+        X = loadtxt(args.model_input_file, delimiter=args.delimiter, ndmin=2)
         dgsm.analyze(problem, X, Y, num_resamples=args.resamples, print_to_console=True, seed=args.seed)
         return
     sobol.analyze(problem, Y, (args.max_order == 2), num_resamples=args.resamples, print_to_console=True,
