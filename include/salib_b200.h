@@ -136,6 +136,13 @@ int sa_row_stride(int Dg, int second_order);
  *     chunks of CW = 8/16/24/32 features as d_Yt[chunk][N][CW]; features in SA_NACC order
  *     { A, B, A^2, B^2, A*B, B*(AB_j - A) (j < Dg), (A - AB_j)^2 (j < Dg) }, zero padded.            */
 int sa_feature_count(int Dg);
+/* Feature matrix for either order (what algo 3 of sa_sobol_accumulate_ex_f64 consumes): SA_NACC(Dg,
+ * second_order) features per row in SA_NACC order -- for second order the list continues with the pair
+ * products BA_j * AB_k (j < k) -- chunked as above; sa_chunked_feature_doubles(SA_NACC) doubles per row.
+ * With it every sum of analyze/sobol.py:209-246 is one skinny GEMM w[R x N] * F[N x SA_NACC]; the Python
+ * side picks it for second order while Dg is small (the 8x8 register-tile kernel leaves lanes idle there).   */
+int sa_normalize_features_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                              const double *d_stats, double *d_F);
 uint64_t sa_pad_rows(uint64_t N);
 int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
                      const double *d_stats, double *d_Yn, double *d_Yt);
@@ -183,7 +190,7 @@ int sa_sobol_accumulate_f64(void *stream, const double *d_Yn, const double *d_Yt
                             int Dg, int second_order, const uint8_t *d_w, uint64_t count,
                             int nsplit, double *d_psum);
 /* Same, with an explicit kernel choice for tests: algo 0 = auto, 1 = generic (any shape),
- * 3 = first/total-order kernel, 4 = second-order 8x8 register-tile kernel with rows staged in
+ * 3 = feature-GEMV kernel (first/total order; second order with the pair-feature matrix), 4 = second-order 8x8 register-tile kernel with rows staged in
  * shared memory by cp.async.bulk (what "auto" picks for second order), 5 = EXPERIMENTAL FP64
  * tensor-core (mma.sync m8n8k4.f64) variant of 4, opt-in only (BASELINE rules tensor cores out).  */
 int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, const double *d_Yt, uint64_t N,

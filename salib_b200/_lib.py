@@ -36,6 +36,7 @@ SIGNATURES = {
     "sa_text_count_newlines": (C.c_int, [_vp, _vp, _u64, _vp]),
     "sa_text_line_starts": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "sa_text_parse_lines": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "sa_normalize_features_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _vp]),
     "sa_moments_workspace_bytes": (_sz, []),
     "sa_moments_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _sz]),
     "sa_row_stride": (C.c_int, [_i32, _i32]),

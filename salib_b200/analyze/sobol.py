@@ -45,7 +45,9 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
-_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "tile8": 4, "dmma": 5}
+_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5}
+PAIR_GEMV_MAX_DG = 40                 # second order through the feature GEMV up to this many groups ...
+PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
 
 def _nacc(Dg, c2):
@@ -156,12 +158,21 @@ class SobolAnalyzer:
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[algo]
-        # second order: tile kernel (Dg <= 512); first/total order only: GEMV kernel (any Dg)
-        kind = self.algo or (4 if (self.c2 and Dg <= 512) else (3 if not self.c2 else 1))
+        # first/total order only: feature-GEMV kernel (any Dg).  Second order: the same GEMV over pair-product
+        # features while Dg is small (the 8x8 register-tile kernel needs Dg >= 57 to occupy all 32 lanes) and
+        # the feature matrix fits PAIR_GEMV_MAX_BYTES; else the tile kernel (Dg <= 512); else the generic one.
+        L = _lib.lib()
+        if self.algo:
+            kind = self.algo
+        elif not self.c2:
+            kind = 3
+        elif Dg <= PAIR_GEMV_MAX_DG and 8 * N * int(L.sa_chunked_feature_doubles(self.nacc)) <= PAIR_GEMV_MAX_BYTES:
+            kind = 3
+        else:
+            kind = 4 if Dg <= 512 else 1
         self.kind = kind
         self.groups = tile_groups(Dg) if kind == 4 else 1
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
-        L = _lib.lib()
         self.stride = L.sa_row_stride(self.Dg, int(self.c2))
         self.Npad = int(L.sa_pad_rows(self.N))
         self.stats = rt.zeros((8,), torch.float64)
@@ -185,20 +196,22 @@ class SobolAnalyzer:
             self.moments(Yd)
         else:
             self.stats.copy_(rt.to_device(np.asarray(stats, dtype=np.float64), torch.float64))
-        need_rows = self.kind in (1, 4, 5)
-        need_cols = self.kind in (3, 4, 5)   # kinds 4, 5 only need the A and B columns
-        if need_rows:
+        if self.kind == 3:                   # feature matrix (first order, or second order with pair products)
+            self.Yt = rt.empty((self.N * int(L.sa_chunked_feature_doubles(self.nacc)),), torch.float64)
+        else:                                # analysis-layout rows (+ the A and B columns for kinds 4, 5)
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
-        if need_cols:
-            n_aux = 2 * self.Npad if self.c2 else self.N * int(L.sa_feature_count(self.Dg))
-            self.Yt = rt.empty((n_aux,), torch.float64)
-        _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
-                  rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
+            if self.kind in (4, 5):
+                self.Yt = rt.empty((2 * self.Npad,), torch.float64)
+        self.load_normalized(Yd)
 
     def load_normalized(self, Yd):
         """Re-run only the normalise/re-layout step with the current ``self.stats``."""
-        _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
-                  rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
+        if self.kind == 3:
+            _lib.call("sa_normalize_features_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
+                      rt.ptr(self.stats), rt.ptr(self.Yt))
+        else:
+            _lib.call("sa_normalize_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
+                      rt.ptr(self.stats), rt.ptr(self.Yn), rt.ptr(self.Yt))
 
     # -- work decomposition ----------------------------------------------------------------
     def _nsplit(self, count):

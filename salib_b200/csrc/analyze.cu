@@ -1084,11 +1084,15 @@ __host__ __device__ inline int chunk_count(int nfeat) {
 __host__ __device__ inline int feature_width(int Dg) { return chunk_width(5 + 2 * Dg); }
 __host__ __device__ inline int feature_chunks(int Dg) { return chunk_count(5 + 2 * Dg); }
 
+// second_order: the row also carries BA_j (columns 1+Dg+j) and the features continue with the Dg(Dg-1)/2 pair
+// products BA_j * AB_k (j < k, row-major over the strict upper triangle) -- SA_NACC order throughout, so the
+// GEMV output is exactly the accumulator vector finalize_kernel expects.
 __global__ void __launch_bounds__(256)
-normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step,
+normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int step, int second_order,
                           const double *__restrict__ stats, double *__restrict__ F) {
   const double mean = stats[0], sd = stats[1];
-  const int CW = feature_width(Dg), NZ = feature_chunks(Dg);
+  const int nfeat = 5 + 2 * Dg + (second_order ? Dg * (Dg - 1) / 2 : 0);
+  const int CW = chunk_width(nfeat), NZ = chunk_count(nfeat);
   const uint64_t per_chunk = N * (uint64_t)CW;
   const uint64_t total = per_chunk * NZ;
   for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1098,19 +1102,32 @@ normalize_features_kernel(const double *__restrict__ Y, uint64_t N, int Dg, int 
     const uint64_t i = rem / (uint64_t)CW;
     const int q = z * CW + (int)(rem - i * (uint64_t)CW);  // global feature index
     const double *row = Y + i * (uint64_t)step;
-    const double a = __ddiv_rn(__dsub_rn(row[0], mean), sd);
-    const double b = __ddiv_rn(__dsub_rn(row[step - 1], mean), sd);
     double v = 0.0;
-    if (q == 0) v = a;
-    else if (q == 1) v = b;
-    else if (q == 2) v = __dmul_rn(a, a);
-    else if (q == 3) v = __dmul_rn(b, b);
-    else if (q == 4) v = __dmul_rn(a, b);
-    else if (q < 5 + 2 * Dg) {
-      const int j = (q - 5 < Dg) ? q - 5 : q - 5 - Dg;
-      const double ab = __ddiv_rn(__dsub_rn(row[1 + j], mean), sd);
-      if (q - 5 < Dg) v = __dmul_rn(b, __dsub_rn(ab, a));          // B * (AB_j - A)
-      else { const double t = __dsub_rn(a, ab); v = __dmul_rn(t, t); }  // (A - AB_j)^2
+    if (q < 5 + 2 * Dg) {
+      const double a = __ddiv_rn(__dsub_rn(row[0], mean), sd);
+      const double b = __ddiv_rn(__dsub_rn(row[step - 1], mean), sd);
+      if (q == 0) v = a;
+      else if (q == 1) v = b;
+      else if (q == 2) v = __dmul_rn(a, a);
+      else if (q == 3) v = __dmul_rn(b, b);
+      else if (q == 4) v = __dmul_rn(a, b);
+      else {
+        const int j = (q - 5 < Dg) ? q - 5 : q - 5 - Dg;
+        const double ab = __ddiv_rn(__dsub_rn(row[1 + j], mean), sd);
+        if (q - 5 < Dg) v = __dmul_rn(b, __dsub_rn(ab, a));          // B * (AB_j - A)
+        else { const double t = __dsub_rn(a, ab); v = __dmul_rn(t, t); }  // (A - AB_j)^2
+      }
+    } else if (q < nfeat) {
+      // pair p -> (j, k): p = j*(2Dg - j - 1)/2 + (k - j - 1)
+      const int p = q - 5 - 2 * Dg;
+      const double t = 2.0 * Dg - 1.0;
+      int j = (int)((t - sqrt(t * t - 8.0 * p)) * 0.5);
+      while (j > 0 && j * (2 * Dg - j - 1) / 2 > p) --j;
+      while ((j + 1) * (2 * Dg - j - 2) / 2 <= p) ++j;
+      const int k = j + 1 + (p - j * (2 * Dg - j - 1) / 2);
+      const double ba = __ddiv_rn(__dsub_rn(row[1 + Dg + j], mean), sd);
+      const double ab = __ddiv_rn(__dsub_rn(row[1 + k], mean), sd);
+      v = __dmul_rn(ba, ab);
     }
     F[idx] = v;
   }
@@ -1556,10 +1573,27 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
       const uint64_t total = N * (uint64_t)feature_width(Dg) * feature_chunks(Dg);
       uint64_t blocks = ceil_div_u64(total, 256);
       if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
-      normalize_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, d_stats, d_Yt);
+      normalize_features_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_Y, N, Dg, step, 0, d_stats, d_Yt);
     }
     note_launches(1);
   }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// Feature matrix of the GEMV kernel for either order: SA_NACC(Dg, second_order) features per row, chunked.
+extern "C" int sa_normalize_features_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                                         const double *d_stats, double *d_F) {
+  SA_REQUIRE(d_Y && d_stats && d_F, SA_ERR_ARG, "sa_normalize_features_f64: null pointer");
+  SA_REQUIRE(N >= 1 && Dg >= 1 && Dg <= 2048, SA_ERR_ARG, "sa_normalize_features_f64: bad N/Dg");
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  const int nfeat = SA_NACC(Dg, second_order);
+  const uint64_t total = N * (uint64_t)chunk_width(nfeat) * chunk_count(nfeat);
+  uint64_t blocks = ceil_div_u64(total, 256);
+  if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
+  normalize_features_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_Y, N, Dg, step, second_order,
+                                                                               d_stats, d_F);
+  note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -1699,7 +1733,7 @@ extern "C" int sa_sobol_accumulate_ex_f64(void *stream, const double *d_Yn, cons
         d_Yn, stride, Dp, N, Dg, d_w, Npad, count, rps, d_psum, nacc);
     note_launches(1);
   } else if (algo == 3) {
-    SA_REQUIRE(!second_order, SA_ERR_UNSUPPORTED, "first-order kernel cannot do second order");
+    // second order: d_Yt must be the pair-feature matrix of sa_normalize_features_f64(second_order = 1)
     SA_REQUIRE(d_Yt, SA_ERR_ARG, "sa_sobol_accumulate_f64: d_Yt (feature matrix) is null");
     return launch_feature_gemv(st, d_Yt, N, nacc, d_w, Npad, count, nsplit, rps, d_psum);
   } else if (algo == 1) {

@@ -47,7 +47,9 @@ def test_matches_frozen_reference(name):
                                        ("g8_n512_c1_r64", "generic"), ("g64_n128_r16", "generic"),
                                        ("grp3_n512_r40", "generic"), ("g64_n128_r16", "dmma"),
                                        ("g16_n256_r32", "dmma"), ("g8_n512_r64", "dmma"),
-                                       ("ishigami_n1024_r100", "dmma")])
+                                       ("ishigami_n1024_r100", "dmma"), ("g8_n512_r64", "tile8"),
+                                       ("g16_n256_r32", "tile8"), ("ishigami_n1024_r100", "tile8"),
+                                       ("grp3_n512_r40", "tile8"), ("g64_n128_r16", "gemv")])
 def test_generic_kernel_matches_frozen_reference(name, algo):
     """The fallback kernel is an independent implementation of the same sums; "dmma" is the experimental
     opt-in FP64 tensor-core variant of the tile kernel."""
@@ -84,7 +86,8 @@ def test_cli_golden_table():
                                       (200, 70, True, 3), (95, 128, False, 7), (300, 40, False, 3)])
 def test_matches_oracle_over_shapes(D, N, c2, R):
     """Ragged N (not a multiple of 32), Dg not a multiple of 8, Dg > 64 (tile groups, 16/8-row ring tiles;
-    chunked feature matrix of the first-order kernel), row splits."""
+    chunked feature matrix of the GEMV kernel), row splits.  Second order with Dg <= 40 defaults to the
+    pair-feature GEMV; the register-tile kernel is run on the same inputs as well."""
     from oracle import analyze as o_analyze
     from salib_b200.analyze import sobol
 
@@ -97,6 +100,10 @@ def test_matches_oracle_over_shapes(D, N, c2, R):
     S = sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r)
     So = o_analyze.analyze(D, Y, c2, R, keep_resamples=True, r=r)
     _cmp(S, So, D, c2, rtol=1e-9, atol=1e-12)
+    if c2 and D <= 100:
+        other = "tile8" if D <= sobol.PAIR_GEMV_MAX_DG else "gemv"
+        S2 = sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r, algo=other)
+        _cmp(S2, So, D, c2, rtol=1e-9, atol=1e-12)
 
 
 def test_estimator_functions():
@@ -284,14 +291,16 @@ def test_edge_shapes_match_oracle(D, N, c2, R):
     p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0, 1]] * D}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        S = sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r)
         So = o_analyze.analyze(D, Y, c2, R, keep_resamples=True, r=r)
-    for k in ("S1", "ST", "S1_conf_all", "ST_conf_all", "S1_conf", "ST_conf"):
-        np.testing.assert_allclose(S[k], So[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
-    if c2 and D > 1:
-        iu = np.triu_indices(D, 1)
-        np.testing.assert_allclose(S["S2"][iu], So["S2"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
-        np.testing.assert_allclose(S["S2_conf"][iu], So["S2_conf"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
+        runs = [sobol.analyze_device(p, Y, calc_second_order=c2, keep_resamples=True, r=r, algo=a)
+                for a in (("auto", "tile8") if c2 else ("auto",))]
+    for S in runs:
+        for k in ("S1", "ST", "S1_conf_all", "ST_conf_all", "S1_conf", "ST_conf"):
+            np.testing.assert_allclose(S[k], So[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+        if c2 and D > 1:
+            iu = np.triu_indices(D, 1)
+            np.testing.assert_allclose(S["S2"][iu], So["S2"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(S["S2_conf"][iu], So["S2_conf"][iu], rtol=1e-9, atol=1e-12, equal_nan=True)
 
 
 def test_row_window_multiplicities_tile_the_full_ones():
