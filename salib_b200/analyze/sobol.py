@@ -46,7 +46,7 @@ RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
 _ALGO = {"auto": 0, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5}
-PAIR_GEMV_MAX_DG = 40                 # second order through the feature GEMV up to this many groups ...
+PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
 
@@ -120,12 +120,17 @@ def plan_row_splits(kind, count, N, sms, nacc, groups=1):
     max_split = max(1, min(4096, N // 32))
     if kind in (4, 5):   # tile kernels: `groups` warps per resample, 8 warps per block, one block per SM
         blocks = -(-count // 8) * groups
-    elif kind == 3:      # first-order GEMV kernel (launch_feature_gemv in analyze.cu)
-        if count > 256:  # two resamples per lane, blocks of 4 warps = 256 resamples, 3 resident per SM
-            blocks, resident = -(-count // 256) * -(-nacc // 32), 3
-        else:            # one resample per lane, one block of up to 8 warps
-            blocks, resident = -(-nacc // 32), 4
-        return max(1, min(max_split, (resident * sms) // blocks))
+    elif kind == 3:      # feature GEMV kernel (launch_feature_gemv in analyze.cu)
+        chunks = 1 if nacc <= 24 else -(-nacc // 16)     # chunk_width() in analyze.cu
+        four = nacc > 24 or 8 < nacc <= 16
+        if count > 256 and four:      # 4 resamples per lane: 512 per block of 4 warps, 2 blocks/SM
+            blocks, resident = -(-count // 512) * chunks, 2
+        elif count > 256:             # 2 per lane: 256 per block, 3 blocks/SM
+            blocks, resident = -(-count // 256) * chunks, 3
+        else:                         # one resample per lane, one block of up to 8 warps
+            blocks, resident = chunks, 4
+        slots = resident * sms        # aim at three full waves of blocks
+        return max(1, min(max_split, -(-3 * slots // blocks) if blocks < 3 * slots else 1))
     else:                # generic kernel: one block per resample
         blocks = count
     return max(1, min(max_split, sms // blocks if blocks <= sms else 1))

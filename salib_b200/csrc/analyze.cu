@@ -19,6 +19,8 @@
 //     for Dg > 64 with second order and an independent cross-check of the two fast kernels.
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sa {
@@ -1072,11 +1074,15 @@ s2_accum_dmma_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 // row, read 32 rows at a time.  One DFMA per (resample, row, feature): 5 + 2*Dg flop-pairs instead of
 // the 7 + 8*Dg operations of evaluating the estimator terms per resample.
 constexpr int kFoWarps = 8;
+#ifndef SA_MULTI_CHUNK
+#define SA_MULTI_CHUNK 16
+#endif
+constexpr int kMultiChunk = SA_MULTI_CHUNK;  // chunk width when the features do not fit one chunk of <= 24
 constexpr int kFoRows = 32;   // rows per weight fetch (32 bytes per resample)
 
 // Feature matrix layout: chunks of CW features, F[chunk][row][CW] (each chunk is what one grid.z slice of
 // fo_gemv_kernel streams).  CW = 8/16/24 when all 5 + 2*Dg features fit one chunk, else 32.
-__host__ __device__ inline int chunk_width(int nfeat) { return nfeat <= 24 ? ((nfeat + 7) & ~7) : 32; }
+__host__ __device__ inline int chunk_width(int nfeat) { return nfeat <= 24 ? ((nfeat + 7) & ~7) : kMultiChunk; }
 __host__ __device__ inline int chunk_count(int nfeat) {
   const int cw = chunk_width(nfeat);
   return (nfeat + cw - 1) / cw;
@@ -1233,6 +1239,8 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
         cur[k] = wreg[k][0];
         wreg[k][0] = wreg[k][1]; wreg[k][1] = wreg[k][2]; wreg[k][2] = wreg[k][3];
       }
+      // (an explicit two-buffer software pipeline over the rows was measured slower: +35 registers, fewer
+      // resident blocks; ptxas already hoists the next rows' broadcasts within the 4-row body)
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
         const int r = 4 * wi + bb;
@@ -1503,14 +1511,23 @@ static int launch_feature_gemv(cudaStream_t st, const double *d_F, uint64_t N, i
   const int ch = chunk_width(nfeat), nz = chunk_count(nfeat);
   SA_REQUIRE(nz <= 65535, SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
   const size_t smem = (size_t)kFoStages * kFoRows * ch * 8 + kFoStages * 12 + 16;
-  if (count > (uint64_t)kFoWarps * 32) {
+  if (count > (uint64_t)kFoWarps * 32 && ch == 16) {
+    // <16, 4, 16>: 4 resamples per lane on a 16-wide chunk -- 8 warp-uniform LDS.128 (16 wavefronts) feed 64
+    // DFMAs (32 SM-clocks): FP64-bound.  (The same tile with the two halves of a 32-wide chunk on two warps
+    // was no faster than <32, 2, 32>: a warp-dependent offset turns the broadcast into a per-lane address,
+    // 4 wavefronts instead of 2.)
+    const uint64_t bx = ceil_div_u64(count, 512);
+    SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
+    dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
+    fo_gemv_kernel<16, 4, 16><<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+  } else if (count > (uint64_t)kFoWarps * 32) {
     // <CH, 2, CH>: two resamples per lane; ~165 registers, so blocks of 4 warps (256 resamples), 3 per SM.
     // (<CH, 4, 8> -- 4 per lane, CH/8 warps per resample group -- was measured slower, 3.55 vs 2.65 ms on cfg2:
     // every warp of a group re-reads the group's weight bytes with lane-strided 16-byte loads.)
     const uint64_t bx = ceil_div_u64(count, 256);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
     dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-    auto kern = ch == 8 ? fo_gemv_kernel<8, 2, 8> : (ch == 16 ? fo_gemv_kernel<16, 2, 16> : (ch == 24 ? fo_gemv_kernel<24, 2, 24> : fo_gemv_kernel<32, 2, 32>));
+    auto kern = ch == 8 ? fo_gemv_kernel<8, 2, 8> : (ch == 24 ? fo_gemv_kernel<24, 2, 24> : fo_gemv_kernel<32, 2, 32>);
     kern<<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
   } else {
     dim3 grid(1, (unsigned)nsplit, (unsigned)nz);

@@ -249,7 +249,7 @@ def test_work_decomposition_plans():
     assert plan_row_splits(4, 1, 1 << 20, sms, 2149) == 148           # point estimate: one block per SM
     assert plan_row_splits(4, 528, 1 << 20, sms, 2149) == 2
     assert plan_row_splits(4, 16, 100, sms, 11) == 3                  # never fewer than 32 rows per split
-    assert plan_row_splits(3, 1000, 1 << 20, sms, 21) == 111             # 4 blocks of 256 resamples x 111 = 3 per SM
+    assert plan_row_splits(3, 1000, 1 << 20, sms, 21) == 333             # 4 blocks of 256 resamples -> three waves of 3 per SM
     assert plan_row_splits(1, 1000, 4096, sms, 50) == 1
 
 
