@@ -1148,7 +1148,7 @@ constexpr int kFoStages = 4;
 // crossbar-bound at half the FP64 rate (measured 89 % of that bound; used for launches of <= 256
 // resamples).  <CH, 2, CH> reuses every broadcast for 4 DFMAs, which balances the two pipes (cfg2: 3.1 -> 2.65
 // ms; FP64 pipe 55 %, crossbar 55 % -- the rest is the lane-strided weight fetch, see launch_feature_gemv).
-template <int CH, int RPL, int FPW>
+template <int CH, int RPL, int FPW, bool WEIGHTED>
 __global__ void __launch_bounds__(kFoWarps * 32)
 fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__restrict__ w, uint64_t Npad,
                uint64_t count, uint64_t rows_per_split, double *__restrict__ psum, int nacc) {
@@ -1200,8 +1200,8 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
 #pragma unroll
     for (int q = 0; q < FPW; ++q) acc[k][q] = 0.0;
     const uint64_t c = cbase + 32u * k;
-    wrow[k] = (w && c < count) ? w + c * Npad : nullptr;
-    ones[k] = (!w && c < count) ? 1.0 : 0.0;  // point estimate: weight 1 for every row
+    wrow[k] = (WEIGHTED && c < count) ? w + c * Npad : nullptr;
+    ones[k] = (!WEIGHTED && c < count) ? 1.0 : 0.0;  // point estimate: weight 1 for every row
   }
   // this lane's weights, 16 rows (one uint4 per resample) at a time: half-tile u covers rows [16u, 16u+16) of
   // the split (rows_per_split is a multiple of 32, Npad of 128: in bounds); fetched one half-tile ahead
@@ -1222,35 +1222,22 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
     }
     const uint32_t tile = sm_base + s * stage_bytes;
     // 4 rows per iteration; the loop is kept rolled (the weight words rotate through wreg[k][0]) so that the
-    // body stays in the instruction cache
+    // body stays in the instruction cache.  Full tiles run a branch-free body (WEIGHTED is a template
+    // parameter, no per-row bounds test), so the 4 rows are one basic block and ptxas issues the next rows'
+    // broadcasts ahead of the DFMAs that consume the current ones; only the last tile of a split is checked.
     uint32_t wreg[RPL][4];
-#pragma unroll 1
-    for (int wi = 0; wi < 8; ++wi) {
-      if ((wi & 3) == 0) {  // uniform: start of a half-tile
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-          wreg[k][0] = wn[k].x; wreg[k][1] = wn[k].y; wreg[k][2] = wn[k].z; wreg[k][3] = wn[k].w;
-        }
-        load_w(2 * t + (wi >> 2) + 1, wn);
-      }
-      uint32_t cur[RPL];
-#pragma unroll
-      for (int k = 0; k < RPL; ++k) {
-        cur[k] = wreg[k][0];
-        wreg[k][0] = wreg[k][1]; wreg[k][1] = wreg[k][2]; wreg[k][2] = wreg[k][3];
-      }
-      // (an explicit two-buffer software pipeline over the rows was measured slower: +35 registers, fewer
-      // resident blocks; ptxas already hoists the next rows' broadcasts within the 4-row body)
+    auto four_rows = [&](int wi, uint32_t (&cur)[RPL], auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
         const int r = 4 * wi + bb;
-        if (r < nrows) {  // uniform; false only in the last tile of a split
+        if (FULL || r < nrows) {
           double wv[RPL];
 #pragma unroll
           for (int k = 0; k < RPL; ++k) {
             const uint32_t byte = (cur[k] >> (8 * bb)) & 0xffu;
             // small integer -> double without the conversion pipe: 2^52 + n has n in the low mantissa bits
-            wv[k] = w ? (__hiloint2double(0x43300000, (int)byte) - 4503599627370496.0) : ones[k];
+            wv[k] = WEIGHTED ? (__hiloint2double(0x43300000, (int)byte) - 4503599627370496.0) : ones[k];
           }
           const uint32_t f = tile + (uint32_t)r * row_bytes + 8u * (uint32_t)fq;
 #pragma unroll
@@ -1264,6 +1251,26 @@ fo_gemv_kernel(const double *__restrict__ Fall, uint64_t N, const uint8_t *__res
           }
         }
       }
+    };
+#pragma unroll 1
+    for (int wi = 0; wi < 8; ++wi) {
+      if (WEIGHTED && (wi & 3) == 0) {  // uniform: start of a half-tile
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          wreg[k][0] = wn[k].x; wreg[k][1] = wn[k].y; wreg[k][2] = wn[k].z; wreg[k][3] = wn[k].w;
+        }
+        load_w(2 * t + (wi >> 2) + 1, wn);
+      }
+      uint32_t cur[RPL];
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        cur[k] = WEIGHTED ? wreg[k][0] : 0u;
+        if (WEIGHTED) {
+          wreg[k][0] = wreg[k][1]; wreg[k][1] = wreg[k][2]; wreg[k][2] = wreg[k][3];
+        }
+      }
+      if (nrows == kFoRows) four_rows(wi, cur, std::true_type{});
+      else four_rows(wi, cur, std::false_type{});
     }
     __syncwarp();
     if (lane == 0) {
@@ -1519,7 +1526,7 @@ static int launch_feature_gemv(cudaStream_t st, const double *d_F, uint64_t N, i
     const uint64_t bx = ceil_div_u64(count, 512);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
     dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-    fo_gemv_kernel<16, 4, 16><<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+    fo_gemv_kernel<16, 4, 16, true><<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
   } else if (count > (uint64_t)kFoWarps * 32) {
     // <CH, 2, CH>: two resamples per lane; ~165 registers, so blocks of 4 warps (256 resamples), 3 per SM.
     // (<CH, 4, 8> -- 4 per lane, CH/8 warps per resample group -- was measured slower, 3.55 vs 2.65 ms on cfg2:
@@ -1527,13 +1534,18 @@ static int launch_feature_gemv(cudaStream_t st, const double *d_F, uint64_t N, i
     const uint64_t bx = ceil_div_u64(count, 256);
     SA_REQUIRE(bx < (1ull << 31), SA_ERR_UNSUPPORTED, "shape too large for the feature GEMV kernel");
     dim3 grid((unsigned)bx, (unsigned)nsplit, (unsigned)nz);
-    auto kern = ch == 8 ? fo_gemv_kernel<8, 2, 8> : (ch == 24 ? fo_gemv_kernel<24, 2, 24> : fo_gemv_kernel<32, 2, 32>);
+    auto kern = ch == 8 ? fo_gemv_kernel<8, 2, 8, true> : (ch == 24 ? fo_gemv_kernel<24, 2, 24, true> : fo_gemv_kernel<32, 2, 32, true>);
     kern<<<grid, 128, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
   } else {
     dim3 grid(1, (unsigned)nsplit, (unsigned)nz);
-    auto kern = ch == 8 ? fo_gemv_kernel<8, 1, 8> : (ch == 16 ? fo_gemv_kernel<16, 1, 16> : (ch == 24 ? fo_gemv_kernel<24, 1, 24> : fo_gemv_kernel<32, 1, 32>));
     const unsigned threads = (unsigned)(32 * ceil_div_u64(count, 32));  // only warps that own a resample
-    kern<<<grid, threads, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+    if (d_w) {
+      auto kern = ch == 8 ? fo_gemv_kernel<8, 1, 8, true> : (ch == 16 ? fo_gemv_kernel<16, 1, 16, true> : (ch == 24 ? fo_gemv_kernel<24, 1, 24, true> : fo_gemv_kernel<32, 1, 32, true>));
+      kern<<<grid, threads, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+    } else {
+      auto kern = ch == 8 ? fo_gemv_kernel<8, 1, 8, false> : (ch == 16 ? fo_gemv_kernel<16, 1, 16, false> : (ch == 24 ? fo_gemv_kernel<24, 1, 24, false> : fo_gemv_kernel<32, 1, 32, false>));
+      kern<<<grid, threads, smem, st>>>(d_F, N, d_w, Npad, count, rps, d_psum, nfeat);
+    }
   }
   note_launches(1);
   SA_LAUNCH_CHECK();
