@@ -8,6 +8,11 @@ All arithmetic runs in the CUDA library through the C ABI (include/salib_b200.h)
             -> per batch of resamples: multiplicities -> weighted sums -> estimator algebra
             -> Z * std(ddof=1) over resamples
 
+Weighted sums: every sum is linear in the multiplicities.  First/total order, and second order while
+Dg <= PAIR_GEMV_MAX_DG, run as one skinny GEMM  w[R x N] * F[N x SA_NACC]  over per-row features (for second
+order the pair products BA_j * AB_k are features too); larger second-order problems use the 8x8
+register-tile kernel, which skips rows of multiplicity 0.
+
 Resample indices.  The reference draws ``r = rng.integers(N, size=(N, R))`` on the host
 (:113-117,144).  ``RESAMPLE_MODE``:
   * ``"numpy"``  -- draw exactly that matrix on the host (same seed semantics, ``seed`` falsy -> legacy
@@ -550,7 +555,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
     ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
-    ``algo``: force an accumulate kernel ("generic" | "tile8" | "first_order"); ``distributed``: shard the
+    ``algo``: force an accumulate kernel ("generic" | "tile8" | "gemv" | "dmma"); ``distributed``: shard the
     resamples over the initialised torch.distributed job; ``shard``: "resamples" (default: every rank holds
     Y, resample ids are split) or "rows" (every rank keeps only its base-row range of Y and all resamples'
     partial sums are all-reduced -- ``analyze_row_sharded``).

@@ -56,6 +56,8 @@ def gprob(D):
 
 def cfg1():
     p = {"num_vars": 3, "names": ["x1", "x2", "x3"], "bounds": [[-np.pi, np.pi]] * 3}
+    for _ in range(3):   # warm-up: CUDA context, library load, allocator
+        an.analyze(p, Ishigami.evaluate(saltelli.sample(dict(p), 1024)), num_resamples=100, seed=100)
     t0 = time.perf_counter()
     for _ in range(20):
         X = saltelli.sample(dict(p), 1024)
