@@ -477,10 +477,16 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     const size_t row_bytes = 2 * (size_t)D * sizeof(double);
     SA_REQUIRE(row_bytes <= 200 * 1024, SA_ERR_UNSUPPORTED,
                "sa_saltelli_sample_f64: D=%d needs %zu B of shared memory per base row", D, row_bytes);
-    int BR = (int)((48 * 1024) / row_bytes);
-    if (BR < 1) BR = 1;
-    if (BR > 32) BR = 32;
     const uint64_t rowlen = (uint64_t)step * D;
+    // base rows per chunk: 32 for wide rows; for short rows (small D) enough of them that a chunk writes
+    // ~24 K values -- with 32 the per-chunk closed-form start and the two barriers capped every D <= 5 at
+    // 84 Grows/s (20-50 % of the HBM roofline)
+    int BR = (int)((48 * 1024) / row_bytes);
+    int cap = (int)(24576 / rowlen);
+    if (cap < 32) cap = 32;
+    if (cap > 1024) cap = 1024;
+    if (BR < 1) BR = 1;
+    if (BR > cap) BR = cap;
     while (BR > 1 && (uint64_t)BR * rowlen >= (1ull << 31)) BR >>= 1;
     SA_REQUIRE((uint64_t)BR * rowlen < (1ull << 31), SA_ERR_UNSUPPORTED,
                "sa_saltelli_sample_f64: row of %llu values too long", (unsigned long long)rowlen);
