@@ -349,28 +349,58 @@ saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restri
   if (flag && bad) atomicOr(flag, bad);
 }
 
+// One thread per run of kIshRun consecutive base rows: closed form once, then one XOR per coordinate and row.
+// Every output row of a base row combines coordinates of A_i and B_i only, so the three terms of the model are
+// evaluated once per source (4 sines per base row instead of 2 per output row) and combined per row in exactly
+// the order of ishigami_value: (s0 + A*s1^2) + (B*x2^4)*s0 -- bit-identical to evaluating the rows one by one.
+constexpr int kIshRun = 8;
 template <bool GROUPED>
 __global__ void __launch_bounds__(256)
 saltelli_eval_ishigami_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                               uint64_t first_index, uint64_t n, int Dg,
                               const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
                               double A, double B, double *__restrict__ Y) {
-  // one thread per base row: 6 Sobol' values, `step` outputs
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    double xa[3], xb[3];
-    int g[3];
+  const uint64_t nruns = ceil_div_u64(n, kIshRun);
+  int g[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      xa[j] = scale_col(sobol_point(sv, shift ? shift[j] : 0u, j, first_index + i), j, cs);
-      xb[j] = scale_col(sobol_point(sv, shift ? shift[3 + j] : 0u, 3 + j, first_index + i), j, cs);
-      g[j] = GROUPED ? gcol[j] : j;
-    }
-    for (int s = 0; s < step; ++s) {
-      double x[3];
+  for (int j = 0; j < 3; ++j) g[j] = GROUPED ? gcol[j] : j;
+  for (uint64_t run = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; run < nruns;
+       run += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i0 = run * kIshRun;
+    const int len = (int)((n - i0 < (uint64_t)kIshRun) ? (n - i0) : kIshRun);
+    uint64_t k = first_index + i0;
+    uint32_t x[6];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) x[j] = slot_uses_b(s, g[j], Dg, step, second_order) ? xb[j] : xa[j];
-      Y[i * (uint64_t)step + s] = ishigami_value(x[0], x[1], x[2], A, B);
+    for (int d = 0; d < 6; ++d) x[d] = sobol_point(sv, shift ? shift[d] : 0u, d, k);
+    for (int r = 0; r < len; ++r) {
+      double s0[2], t1[2], q[2];  // [0]: from A_i, [1]: from B_i
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double x0 = scale_col(x[3 * h + 0], 0, cs);
+        const double x1 = scale_col(x[3 * h + 1], 1, cs);
+        const double x2 = scale_col(x[3 * h + 2], 2, cs);
+        const double s1 = sin(x1);
+        const double x2sq = __dmul_rn(x2, x2);
+        s0[h] = sin(x0);
+        t1[h] = __dmul_rn(A, __dmul_rn(s1, s1));
+        q[h] = __dmul_rn(B, __dmul_rn(x2sq, x2sq));
+      }
+      double *dst = Y + (i0 + r) * (uint64_t)step;
+      for (int s = 0; s < step; ++s) {
+        const int c0 = slot_uses_b(s, g[0], Dg, step, second_order) ? 1 : 0;
+        const int c1 = slot_uses_b(s, g[1], Dg, step, second_order) ? 1 : 0;
+        const int c2 = slot_uses_b(s, g[2], Dg, step, second_order) ? 1 : 0;
+        const double u0 = c0 ? s0[1] : s0[0];
+        const double u1 = c1 ? t1[1] : t1[0];
+        const double u2 = c2 ? q[1] : q[0];
+        dst[s] = __dadd_rn(__dadd_rn(u0, u1), __dmul_rn(u2, u0));
+      }
+      ++k;
+      const int c = __ffsll((long long)k) - 1;
+      if (c < SA_SOBOL_BITS) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) x[d] ^= __ldg(sv + (size_t)d * SA_SOBOL_BITS + c);
+      }
     }
   }
 }
@@ -619,7 +649,7 @@ extern "C" int sa_saltelli_eval_ishigami_f64(void *stream, const uint32_t *d_sv,
   if (rc) return rc;
   if (n == 0) return SA_OK;
   const int step = second_order ? 2 * Dg + 2 : Dg + 2;
-  uint64_t blocks = ceil_div_u64(n, 256);
+  uint64_t blocks = ceil_div_u64(ceil_div_u64(n, kIshRun), 256);
   if (blocks > (uint64_t)sm_count() * 32) blocks = (uint64_t)sm_count() * 32;
   if (d_group_of_col)
     saltelli_eval_ishigami_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
