@@ -338,9 +338,24 @@ saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restri
       const double *fa = sa + (size_t)r * D;
       const double *fb = sb + (size_t)r * D;
       double p = 1.0;
-      for (int j = 0; j < D; ++j) {
-        const bool ub = slot_uses_b(s, sg[j], Dg, step, second_order);
-        p = __dmul_rn(p, ub ? fb[j] : fa[j]);
+      if (GROUPED || D < 32) {  // (short rows: the slot test per factor is cheaper than three divergent runs)
+        for (int j = 0; j < D; ++j) {
+          const bool ub = slot_uses_b(s, sg[j], Dg, step, second_order);
+          p = __dmul_rn(p, ub ? fb[j] : fa[j]);
+        }
+      } else {
+        // no groups: slot s takes every factor from one matrix except column k from the other
+        // (A: k = -1; AB_k; BA_k; B) -- three plain runs, no per-factor slot test, same product order
+        const bool from_b = (s == step - 1) || (second_order && s > D);
+        const int k = (s == 0 || s == step - 1) ? -1 : (s <= D ? s - 1 : s - 1 - D);
+        const double *main_f = from_b ? fb : fa;
+        const double *other_f = from_b ? fa : fb;
+        const int kk = k < 0 ? D : k;
+        for (int j = 0; j < kk; ++j) p = __dmul_rn(p, main_f[j]);
+        if (k >= 0) {
+          p = __dmul_rn(p, other_f[k]);
+          for (int j = k + 1; j < D; ++j) p = __dmul_rn(p, main_f[j]);
+        }
       }
       __stcs(Y + base * (uint64_t)step + o, p);
     }
