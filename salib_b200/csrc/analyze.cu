@@ -1432,34 +1432,46 @@ accum_generic_kernel(const double *__restrict__ Yn, int stride, int Dp, uint64_t
 // ------------------------------------------------------------------------------------------
 // finalize: sums -> S1, ST, S2 per resample
 // ------------------------------------------------------------------------------------------
+template <bool STAGE>  // STAGE: sums over the row splits staged in shared memory (Dg + nacc doubles fit)
 __global__ void __launch_bounds__(128)
 finalize_kernel(const double *__restrict__ psum, uint64_t N, int Dg, int second_order, uint64_t count,
                 int nsplit, const double *__restrict__ stats, double *__restrict__ est, int nacc, int nest) {
   const uint64_t c = blockIdx.x;
   extern __shared__ double fsh[];
-  double *s1sh = fsh;        // [Dg]
-  double *tot = fsh + Dg;    // [nacc] sums over the row splits (fixed order: deterministic)
-  if (nsplit == 1) {
-    for (int a = threadIdx.x; a < nacc; a += blockDim.x) tot[a] = psum[c * (uint64_t)nacc + a];
-  } else {
-    // one warp per accumulator, lanes stride over the splits: the loads of a sum are in flight together
-    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int a = threadIdx.x >> 5; a < nacc; a += nw) {
-      double v = 0.0;
-      for (int sp = lane; sp < nsplit; sp += 32) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
-      v = warp_sum(v);
-      if (lane == 0) tot[a] = v;
+  double *s1sh = fsh;                          // [Dg]
+  double *tot_sh = STAGE ? fsh + Dg : nullptr; // [nacc] sums over the row splits (fixed order: deterministic)
+  __shared__ double head[5];
+  auto direct = [&](int a) {
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
+    return v;
+  };
+  if (STAGE) {
+    if (nsplit == 1) {
+      for (int a = threadIdx.x; a < nacc; a += blockDim.x) tot_sh[a] = psum[c * (uint64_t)nacc + a];
+    } else {
+      // one warp per accumulator, lanes stride over the splits: the loads of a sum are in flight together
+      const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+      for (int a = threadIdx.x >> 5; a < nacc; a += nw) {
+        double v = 0.0;
+        for (int sp = lane; sp < nsplit; sp += 32) v += psum[((uint64_t)sp * count + c) * (uint64_t)nacc + a];
+        v = warp_sum(v);
+        if (lane == 0) tot_sh[a] = v;
+      }
     }
+    __syncthreads();
   }
+  auto tot = [&](int a) { return STAGE ? tot_sh[a] : direct(a); };
+  if (threadIdx.x < 5) head[threadIdx.x] = tot(threadIdx.x);
   __syncthreads();
   const bool constant = !(stats[4] < stats[5]);  // ptp([A;B]) == 0 (or NaN)
   const double n = (double)N;
-  const double m = (tot[0] + tot[1]) / (2.0 * n);
-  const double V = (tot[2] + tot[3]) / (2.0 * n) - m * m;
+  const double m = (head[0] + head[1]) / (2.0 * n);
+  const double V = (head[2] + head[3]) / (2.0 * n) - m * m;
   double *o = est + c * (uint64_t)nest;
   for (int j = threadIdx.x; j < Dg; j += blockDim.x) {
-    const double s1 = constant ? 0.0 : (tot[5 + j] / n) / V;
-    const double st = constant ? 0.0 : 0.5 * (tot[5 + Dg + j] / n) / V;
+    const double s1 = constant ? 0.0 : (tot(5 + j) / n) / V;
+    const double st = constant ? 0.0 : 0.5 * (tot(5 + Dg + j) / n) / V;
     s1sh[j] = s1;
     o[j] = s1;
     o[Dg + j] = st;
@@ -1467,12 +1479,12 @@ finalize_kernel(const double *__restrict__ psum, uint64_t N, int Dg, int second_
   __syncthreads();
   if (second_order) {
     const int npairs = Dg * (Dg - 1) / 2;
-    const double mab = tot[4] / n;
+    const double mab = head[4] / n;
     for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
       int q = p, j = 0;
       while (q >= Dg - 1 - j) { q -= Dg - 1 - j; ++j; }
       const int k = j + 1 + q;
-      const double vjk = (tot[5 + 2 * Dg + p] / n - mab) / V;
+      const double vjk = (tot(5 + 2 * Dg + p) / n - mab) / V;
       o[2 * Dg + p] = constant ? 0.0 : vjk - s1sh[j] - s1sh[k];
     }
   }
@@ -1791,15 +1803,21 @@ extern "C" int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_
   SA_REQUIRE(N >= 1 && Dg >= 1 && count >= 1 && nsplit >= 1, SA_ERR_ARG, "sa_sobol_finalize_f64: bad shape");
   SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
   const size_t fin_smem = ((size_t)Dg + SA_NACC(Dg, second_order)) * sizeof(double);
-  static size_t fin_attr = 48 * 1024;
-  if (fin_smem > fin_attr) {
-    SA_REQUIRE(fin_smem <= 200 * 1024, SA_ERR_UNSUPPORTED, "sa_sobol_finalize_f64: Dg too large");
-    SA_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    fin_attr = fin_smem;
+  if (fin_smem <= 200 * 1024) {
+    static size_t fin_attr = 48 * 1024;
+    if (fin_smem > fin_attr) {
+      SA_CUDA(cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+      fin_attr = fin_smem;
+    }
+    finalize_kernel<true><<<(unsigned)count, 128, fin_smem, (cudaStream_t)stream>>>(
+        d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
+        SA_NEST(Dg, second_order));
+  } else {  // very wide problems: read the partial sums in place
+    SA_REQUIRE((size_t)Dg * sizeof(double) <= 48 * 1024, SA_ERR_UNSUPPORTED, "sa_sobol_finalize_f64: Dg too large");
+    finalize_kernel<false><<<(unsigned)count, 128, (size_t)Dg * sizeof(double), (cudaStream_t)stream>>>(
+        d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
+        SA_NEST(Dg, second_order));
   }
-  finalize_kernel<<<(unsigned)count, 128, fin_smem, (cudaStream_t)stream>>>(
-      d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
-      SA_NEST(Dg, second_order));
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

@@ -83,7 +83,8 @@ def test_cli_golden_table():
                                       (24, 200, True, 12), (40, 96, True, 9), (64, 300, True, 40),
                                       (70, 64, True, 6), (70, 64, False, 6), (20, 5000, False, 50),
                                       (8, 20000, True, 8), (100, 300, True, 5), (130, 96, True, 4),
-                                      (200, 70, True, 3), (95, 128, False, 7), (300, 40, False, 3)])
+                                      (200, 70, True, 3), (95, 128, False, 7), (300, 40, False, 3),
+                                      (260, 40, True, 2)])
 def test_matches_oracle_over_shapes(D, N, c2, R):
     """Ragged N (not a multiple of 32), Dg not a multiple of 8, Dg > 64 (tile groups, 16/8-row ring tiles;
     chunked feature matrix of the GEMV kernel), row splits.  Second order with Dg <= 40 defaults to the
