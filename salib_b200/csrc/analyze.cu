@@ -1626,7 +1626,8 @@ extern "C" int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int
 extern "C" int sa_normalize_features_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
                                          const double *d_stats, double *d_F) {
   SA_REQUIRE(d_Y && d_stats && d_F, SA_ERR_ARG, "sa_normalize_features_f64: null pointer");
-  SA_REQUIRE(N >= 1 && Dg >= 1 && Dg <= 2048, SA_ERR_ARG, "sa_normalize_features_f64: bad N/Dg");
+  SA_REQUIRE(N >= 1 && Dg >= 1 && Dg <= (second_order ? 2048 : (1 << 24)), SA_ERR_ARG,
+             "sa_normalize_features_f64: bad N/Dg (second order: Dg <= 2048)");
   const int step = second_order ? 2 * Dg + 2 : Dg + 2;
   const int nfeat = SA_NACC(Dg, second_order);
   const uint64_t total = N * (uint64_t)chunk_width(nfeat) * chunk_count(nfeat);
