@@ -174,7 +174,8 @@ saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
 // Stage the scaled A/B values of base rows [base, base+nv) in shared memory: sa/sb [BR][D].
 __device__ __forceinline__ void stage_rows(const uint32_t *__restrict__ sv,
                                            const uint32_t *__restrict__ shift, uint64_t k0, int nv,
-                                           int D, const ColScale &cs, double *sa, double *sb) {
+                                           int D, const ColScale &cs, double *sa, double *sb, int ld = 0) {
+  if (ld == 0) ld = D;  // row pitch of sa / sb in doubles
   const int dims = 2 * D;
   int nseg = blockDim.x / dims;
   if (nseg < 1) nseg = 1;
@@ -192,7 +193,7 @@ __device__ __forceinline__ void stage_rows(const uint32_t *__restrict__ sv,
     uint64_t k = k0 + rs;
     uint32_t x = sobol_point(sv, shift ? shift[d] : 0u, d, k);
     for (int r = rs; r < re; ++r) {
-      dst[(size_t)r * D + col] = scale_col(x, col, cs);
+      dst[(size_t)r * ld + col] = scale_col(x, col, cs);
       ++k;
       const int c = __ffsll((long long)k) - 1;
       if (c < SA_SOBOL_BITS) x ^= __ldg(v + c);
@@ -358,6 +359,95 @@ saltelli_eval_g_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restri
         }
       }
       __stcs(Y + base * (uint64_t)step + o, p);
+    }
+    __syncthreads();
+  }
+  if (flag && bad) atomicOr(flag, bad);
+}
+
+// Ungrouped problems: slot AB_k is row A with column k taken from B (BA_k the other way round), so the
+// reference's left-to-right product of slot AB_k starts with the prefix product of A up to column k -- shared by
+// all slots and bit-identical to the sequential loop -- and only the tail after the exchanged column is
+// specific.  A thread takes the slot pair (k, D-1-k) (tails of D-k-1 and k factors: the same work for every
+// thread) for kGRows base rows side by side (independent dependency chains).  Half the multiplications of the
+// slot-by-slot loop and no slot test per factor.
+constexpr int kGRows = 4;
+__global__ void __launch_bounds__(256)
+saltelli_eval_g_pairs_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
+                             uint64_t first_index, uint64_t n, int D, int step, int second_order,
+                             const ColScale cs, const double *__restrict__ a, const double *__restrict__ delta,
+                             const double *__restrict__ alpha, double *__restrict__ Y, int32_t *flag, int BR) {
+  extern __shared__ double smem[];
+  const int LD = D | 1;  // odd row pitch: the row-per-lane prefix pass is free of bank conflicts
+  double *fa = smem;
+  double *fb = fa + (size_t)BR * LD;
+  double *pa = fb + (size_t)BR * LD;
+  double *pb = pa + (size_t)BR * LD;
+  const uint64_t nchunks = ceil_div_u64(n, BR);
+  const int nm = second_order ? 2 : 1;
+  const int npair = (D + 1) / 2;
+  int bad = 0;
+  for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const uint64_t base = chunk * (uint64_t)BR;
+    const int nv = (int)((n - base < (uint64_t)BR) ? (n - base) : BR);
+    stage_rows(sv, shift, first_index + base, nv, D, cs, fa, fb, LD);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nv * D; e += blockDim.x) {
+      const int r = e / D, j = e - r * D;
+      const int pos = r * LD + j;
+      const double aj = a[j], dj = delta ? delta[j] : 0.0, al = alpha ? alpha[j] : 1.0;
+      const double va = fa[pos], vb = fb[pos];
+      bad |= (va < 0.0 || vb < 0.0) ? 1 : 0;
+      bad |= (va > 1.0 || vb > 1.0) ? 2 : 0;
+      fa[pos] = g_factor(va, aj, dj, al);
+      fb[pos] = g_factor(vb, aj, dj, al);
+    }
+    __syncthreads();
+    // prefix products p[j] = f[0] * ... * f[j-1] (left to right) and the A / B rows themselves
+    for (int e = threadIdx.x; e < 2 * nv; e += blockDim.x) {
+      const int m = e / nv, r = e - m * nv;  // lanes of a warp: consecutive rows of one matrix
+      const double *f = (m ? fb : fa) + (size_t)r * LD;
+      double *pp = (m ? pb : pa) + (size_t)r * LD;
+      double p = 1.0;
+      for (int j = 0; j < D; ++j) {
+        pp[j] = p;
+        p = __dmul_rn(p, f[j]);
+      }
+      __stcs(Y + (base + r) * (uint64_t)step + (m ? step - 1 : 0), p);
+    }
+    __syncthreads();
+    const int ngrp = (nv + kGRows - 1) / kGRows;
+    const int items = ngrp * nm * npair;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int q = it % npair;
+      const int t = it / npair;
+      const int m = t % nm, grp = t / nm;
+      const double *main_f = m ? fb : fa;
+      const double *other_f = m ? fa : fb;
+      const double *pm = m ? pb : pa;
+      int rc[kGRows];
+#pragma unroll
+      for (int u = 0; u < kGRows; ++u) {
+        const int r = grp * kGRows + u;
+        rc[u] = (r < nv ? r : nv - 1) * LD;  // clamp: rows past the chunk repeat the last one (not stored)
+      }
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const int k = which ? D - 1 - q : q;
+        if (which && k == q) break;  // odd D: the middle column pairs with itself
+        double p[kGRows];
+#pragma unroll
+        for (int u = 0; u < kGRows; ++u) p[u] = __dmul_rn(pm[rc[u] + k], other_f[rc[u] + k]);
+        for (int j = k + 1; j < D; ++j) {
+#pragma unroll
+          for (int u = 0; u < kGRows; ++u) p[u] = __dmul_rn(p[u], main_f[rc[u] + j]);
+        }
+#pragma unroll
+        for (int u = 0; u < kGRows; ++u) {
+          const int r = grp * kGRows + u;
+          if (r < nv) __stcs(Y + (base + r) * (uint64_t)step + 1 + m * D + k, p[u]);
+        }
+      }
     }
     __syncthreads();
   }
@@ -636,17 +726,36 @@ extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, 
   const size_t row_bytes = 2 * (size_t)D * sizeof(double);
   SA_REQUIRE(row_bytes + D * sizeof(int) <= 200 * 1024, SA_ERR_UNSUPPORTED,
              "sa_saltelli_eval_sobol_g_f64: D=%d too large", D);
-  int BR = (int)((32 * 1024) / row_bytes);
-  if (BR < 1) BR = 1;
-  if (BR > 64) BR = 64;
-  const size_t smem = (size_t)BR * row_bytes + (size_t)D * sizeof(int);
-  uint64_t blocks = ceil_div_u64(n, BR);
-  if (blocks > (uint64_t)sm_count() * 16) blocks = (uint64_t)sm_count() * 16;
-  auto kern = d_group_of_col ? saltelli_eval_g_kernel<true> : saltelli_eval_g_kernel<false>;
-  if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, D, Dg,
-                                                             d_group_of_col, step, second_order, cs, d_a,
-                                                             d_delta, d_alpha, d_Y, d_flag, BR);
+  if (!d_group_of_col && D >= 32 && 4 * (size_t)(D | 1) * sizeof(double) * kGRows <= 96 * 1024) {
+    // prefix-sharing kernel: A/B factors and their prefix products of BR base rows in shared memory
+    const size_t pitch_bytes = 4 * (size_t)(D | 1) * sizeof(double);  // fa, fb, pa, pb rows
+    int BR = (int)((64 * 1024) / pitch_bytes);
+    BR -= BR % kGRows;
+    if (BR < kGRows) BR = kGRows;
+    if (BR > 64) BR = 64;
+    const size_t smem = (size_t)BR * pitch_bytes;
+    uint64_t blocks = ceil_div_u64(n, BR);
+    if (blocks > (uint64_t)sm_count() * 16) blocks = (uint64_t)sm_count() * 16;
+    static size_t pairs_attr = 48 * 1024;
+    if (smem > pairs_attr) {
+      SA_CUDA(cudaFuncSetAttribute(saltelli_eval_g_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      pairs_attr = 96 * 1024;
+    }
+    saltelli_eval_g_pairs_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+        d_sv, d_shift, first_index, n, D, step, second_order, cs, d_a, d_delta, d_alpha, d_Y, d_flag, BR);
+  } else {
+    int BR = (int)((32 * 1024) / row_bytes);
+    if (BR < 1) BR = 1;
+    if (BR > 64) BR = 64;
+    const size_t smem = (size_t)BR * row_bytes + (size_t)D * sizeof(int);
+    uint64_t blocks = ceil_div_u64(n, BR);
+    if (blocks > (uint64_t)sm_count() * 16) blocks = (uint64_t)sm_count() * 16;
+    auto kern = d_group_of_col ? saltelli_eval_g_kernel<true> : saltelli_eval_g_kernel<false>;
+    if (smem > 48 * 1024) SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d_sv, d_shift, first_index, n, D, Dg,
+                                                               d_group_of_col, step, second_order, cs, d_a,
+                                                               d_delta, d_alpha, d_Y, d_flag, BR);
+  }
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
