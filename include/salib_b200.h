@@ -206,6 +206,37 @@ int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg
 int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
                       double *d_conf);
 
+/* ---- analyze: opt-in exact-integer tensor-core engine ("digits", csrc/digits.cu) ---------------------
+ * The sums of sa_sobol_accumulate_f64 by another route: psum[c][q] = sum_i w[c][i] * F[i][q] with integer
+ * w is split error-free.  Each feature column F[:, q] (SA_NACC order, the features of
+ * sa_normalize_features_f64) is scaled by a power of two taken from its exact max |F|, rounded ONCE to an
+ * (8*ndigits-2)-bit integer and stored as `ndigits` balanced radix-256 digits (int8); the digit sums
+ * sum_i w_i * d_i are u8 x s8 dot products accumulated exactly in int32 by tcgen05.mma kind::i8 (N <= 2^24),
+ * recombined in 128-bit integers and rounded to float64 once.  Never selected automatically (BASELINE's
+ * north star rules tensor cores out for the default path); Python: analyze_device(..., algo="digits").
+ *   sa_digit_row_pitch(N)   bytes of one digit column (rows of Y padded to 128)
+ *   sa_digit_features_i8    d_Y [N*step] reference order + d_stats -> d_Q [nfeat*ndigits][pitch] int8,
+ *                           column q*ndigits+s = digit s of feature q, K-major; d_inv [nfeat] = the power of
+ *                           two that maps the integer sums back.  nfeat = SA_NACC(Dg, second_order).
+ *   sa_digit_sums_f64       d_psum [count][nfeat] (the nsplit = 1 layout sa_sobol_finalize_f64 reads) from
+ *                           d_w [count][w_pitch] uint8 multiplicities; workspace = int32 digit sums
+ *                           [ksplit][count][ldc], ksplit = sa_digit_ksplit(...), ldc = sa_digit_ldc(...).
+ *   sa_digit_gemm_i32       the GEMM alone (tests): d_C[ks][count][ldc] = d_w [count][K] * d_Q[ncols][K]^T over
+ *                           the ks-th of `ksplit` ranges of K.                                              */
+uint64_t sa_digit_row_pitch(uint64_t N);
+uint64_t sa_digit_ldc(int nfeat, int ndigits);
+int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count);
+size_t sa_digit_features_workspace_bytes(int nfeat);
+size_t sa_digit_sums_workspace_bytes(uint64_t N, int nfeat, int ndigits, uint64_t count);
+int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                         const double *d_stats, int ndigits, int8_t *d_Q, double *d_inv, void *d_work,
+                         size_t work_bytes);
+int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat, int ndigits,
+                      const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work, size_t work_bytes,
+                      double *d_psum);
+int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, const int8_t *d_Q,
+                      uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit, int32_t *d_C, uint64_t ldc);
+
 /* ---- DGSM on the same machinery ------------------------------------------------
  * sa_finite_diff_expand_f64: rows of sample/finite_diff.py:76-91 from scaled Sobol' points d_base [n, D]:
  *   d_out [n*(D+1), D]; row 1+j moves column j by base_j*delta, clipped to [d_lo[j], d_hi[j]].

@@ -56,6 +56,14 @@ SIGNATURES = {
     "sa_dgsm_features_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "sa_feature_sums_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _u64, _i32, _vp]),
     "sa_reduce_splits_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _dbl, _vp]),
+    "sa_digit_row_pitch": (_u64, [_u64]),
+    "sa_digit_ldc": (_u64, [_i32, _i32]),
+    "sa_digit_ksplit": (C.c_int, [_u64, _i32, _i32, _u64]),
+    "sa_digit_features_workspace_bytes": (_sz, [_i32]),
+    "sa_digit_sums_workspace_bytes": (_sz, [_u64, _i32, _i32, _u64]),
+    "sa_digit_features_i8": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _sz]),
+    "sa_digit_sums_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _u64, _vp, _sz, _vp]),
+    "sa_digit_gemm_i32": (C.c_int, [_vp, _vp, _u64, _u64, _vp, _u64, _u64, _u64, _i32, _vp, _u64]),
     "sa_launch_count": (C.c_longlong, [_i32]),
     "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),
     "sa_microbench_fp64_outer": (C.c_int, [_vp, _i32, _vp, _vp]),

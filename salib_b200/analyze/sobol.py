@@ -50,7 +50,11 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
-_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5}
+_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5, "digits": 6}
+# SALIB_B200_ALGO: engine used when the caller does not name one ("auto" = the FP64 engines; "digits" = the
+# opt-in exact-integer tensor-core engine, csrc/digits.cu).  DIGITS: radix-256 digits per feature value.
+DEFAULT_ALGO = os.environ.get("SALIB_B200_ALGO", "auto")
+DIGITS = int(os.environ.get("SALIB_B200_DIGITS", "7"))
 PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
@@ -146,6 +150,9 @@ def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None, groups=1):
     one-warp-per-resample tile kernel sized in whole waves (8 * sms), the remainder being its own
     (row-split) launch.  Pure host logic."""
     cap = max(1, (max_bytes or MAX_COUNT_BYTES) // Npad)
+    if kind == 6:        # integer GEMM: tiles of 128 resamples, one batch as large as the buffer allows
+        cap = cap // 128 * 128 or cap
+        return [(c, min(c + cap, hi)) for c in range(lo, hi, cap)]
     wave = max(8, 8 * sms // groups) if kind in (4, 5) else 256 * sms
     out, c = [], lo
     while c < hi:
@@ -167,7 +174,8 @@ class SobolAnalyzer:
         self.Dg, self.N, self.c2 = int(Dg), int(N), bool(calc_second_order)
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
-        self.algo = _ALGO[algo]
+        self.algo = _ALGO[DEFAULT_ALGO if algo == "auto" else algo]
+        self.ndigits = DIGITS
         # first/total order only: feature-GEMV kernel (any Dg).  Second order: the same GEMV over pair-product
         # features while Dg is small (the 8x8 register-tile kernel needs Dg >= 57 to occupy all 32 lanes) and
         # the feature matrix fits PAIR_GEMV_MAX_BYTES; else the tile kernel (Dg <= 512); else the generic one.
@@ -206,7 +214,10 @@ class SobolAnalyzer:
             self.moments(Yd)
         else:
             self.stats.copy_(rt.to_device(np.asarray(stats, dtype=np.float64), torch.float64))
-        if self.kind == 3:                   # feature matrix (first order, or second order with pair products)
+        if self.kind == 6:                   # digit columns of the features (int8, K-major) + their scales
+            self.Q = rt.empty((self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N)),), torch.int8)
+            self.inv = rt.empty((self.nacc,), torch.float64)
+        elif self.kind == 3:                 # feature matrix (first order, or second order with pair products)
             self.Yt = rt.empty((self.N * int(L.sa_chunked_feature_doubles(self.nacc)),), torch.float64)
         else:                                # analysis-layout rows (+ the A and B columns for kinds 4, 5)
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
@@ -216,7 +227,12 @@ class SobolAnalyzer:
 
     def load_normalized(self, Yd):
         """Re-run only the normalise/re-layout step with the current ``self.stats``."""
-        if self.kind == 3:
+        if self.kind == 6:
+            work = rt.empty((int(_lib.lib().sa_digit_features_workspace_bytes(self.nacc)),), torch.uint8)
+            _lib.call("sa_digit_features_i8", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
+                      rt.ptr(self.stats), self.ndigits, rt.ptr(self.Q), rt.ptr(self.inv), rt.ptr(work),
+                      int(work.numel()))
+        elif self.kind == 3:
             _lib.call("sa_normalize_features_f64", rt.stream_ptr(), rt.ptr(Yd), self.N, self.Dg, int(self.c2),
                       rt.ptr(self.stats), rt.ptr(self.Yt))
         else:
@@ -229,14 +245,23 @@ class SobolAnalyzer:
 
     def _partial_sums(self, w, count):
         """psum [nsplit, count, nacc] of this engine's rows; returns (psum, nsplit)."""
-        nsplit = self._nsplit(count)
+        nsplit = 1 if self.kind == 6 else self._nsplit(count)
         psum = rt.empty((nsplit * count * self.nacc,), torch.float64)
+        if self.kind == 6:
+            if w is None:                    # point estimate: every row once
+                w = torch.ones((self.Npad,), dtype=torch.uint8, device=rt.device())
+            work = rt.empty((int(_lib.lib().sa_digit_sums_workspace_bytes(self.N, self.nacc, self.ndigits,
+                                                                           int(count))),), torch.uint8)
         ev = None
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(self.Yn), rt.ptr(self.Yt), self.N,
-                  self.Dg, int(self.c2), rt.ptr(w), int(count), int(nsplit), rt.ptr(psum), self.kind)
+        if self.kind == 6:
+            _lib.call("sa_digit_sums_f64", rt.stream_ptr(), rt.ptr(self.Q), rt.ptr(self.inv), self.N, self.nacc,
+                      self.ndigits, rt.ptr(w), self.Npad, int(count), rt.ptr(work), int(work.numel()), rt.ptr(psum))
+        else:
+            _lib.call("sa_sobol_accumulate_ex_f64", rt.stream_ptr(), rt.ptr(self.Yn), rt.ptr(self.Yt), self.N,
+                      self.Dg, int(self.c2), rt.ptr(w), int(count), int(nsplit), rt.ptr(psum), self.kind)
         if ev is not None:
             ev[1].record()
             self.kernel_events.append((int(count), ev[0], ev[1]))
@@ -555,7 +580,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
     ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
-    ``algo``: force an accumulate kernel ("generic" | "tile8" | "gemv" | "dmma"); ``distributed``: shard the
+    ``algo``: force an accumulate kernel ("generic" | "tile8" | "gemv" | "dmma" | "digits"); ``distributed``: shard the
     resamples over the initialised torch.distributed job; ``shard``: "resamples" (default: every rank holds
     Y, resample ids are split) or "rows" (every rank keeps only its base-row range of Y and all resamples'
     partial sums are all-reduced -- ``analyze_row_sharded``).

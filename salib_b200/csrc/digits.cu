@@ -1,0 +1,576 @@
+// Opt-in "digits" engine of sobol.analyze: the bootstrap sums as an EXACT integer GEMM on the
+// 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM, operands by TMA).
+//
+// Reference behaviour replaced: the gathers + reductions of src/SALib/analyze/sobol.py:209-246 for all
+// resamples at once -- the same sums sa_sobol_accumulate_f64 produces (analyze.cu), by another route.
+//
+// Why this is not "reshaping a gather into a GEMM": with multiplicities the sums ARE
+//     psum[c][q] = sum_i w[c][i] * F[i][q]          w: small non-negative integers (uint8), F: float64
+// and the integer operand makes an error-free split possible.  Every feature column is scaled by a power of
+// two (from its exact max |F[:, q]|) and rounded once to a (8*S-2)-bit integer t, which is written as S
+// balanced radix-256 digits  t = sum_s d_s * 256^s,  d_s in [-128, 127]  (int8).  Then
+//     sum_i w_i * t_i = sum_s 256^s * (sum_i w_i * d_{s,i})
+// and each inner sum is a u8 x s8 dot product accumulated in int32 WITHOUT ANY ROUNDING: |sum| <= 128 *
+// sum_i w_i = 128 * N < 2^31 for N <= 2^24.  The digit sums are recombined in 128-bit integers and rounded
+// to float64 once.  The only error is the one rounding of each feature value to 8*S-2 bits relative to its
+// column maximum (S = 6: 2^-47 of the column max per element, unbiased) -- the summation itself is exact,
+// which FP64 accumulation is not.
+//
+// Kernels
+//   feature_table_kernel / feature_max_kernel / feature_scale_kernel / digit_split_kernel
+//       Y -> Q[nfeat*S][Kp] int8, K-major (rows of Y contiguous), column q*S+s = digit s of feature q
+//   digit_gemm_kernel     C[ks][count][ldc] int32 = W[count][K] (u8) * Q[ncols][K]^T (s8) per K split
+//       warp 0: TMA producer (128-byte-swizzled 128 x 128 B and BN x 128 B boxes, STAGES-deep mbarrier ring)
+//       warp 1: allocates TMEM, one lane issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=BN, K=32)
+//       warps 2-5: epilogue, tcgen05.ld 32x32b -> int32 rows to global
+//   digit_combine_kernel  psum[count][nfeat] float64 from the digit sums
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sa {
+namespace dg {
+
+constexpr int BM = 128;        // resamples per tile = UMMA M (TMEM lanes)
+constexpr int BK = 128;        // rows of Y per pipeline stage = bytes per swizzle row
+constexpr int UK = 32;         // K of one tcgen05.mma kind::i8
+constexpr int kThreads = 192;  // 6 warps
+constexpr int kMaxDigits = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A barrier that never completes would hang the GPU: give up after ~10 s of polling and trap instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 30)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Arrives on `bar` once every tcgen05.mma this thread has issued so far has completed.
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x s8 -> s32, shapes from the instruction descriptor.
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major operand whose rows are 128 bytes,
+// 128-byte swizzle, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4)  // start address, 16-byte units          bits [0,14)
+         | (1ull << 16)                      // leading byte offset (unused, K-major)  bits [16,30)
+         | ((uint64_t)(1024 >> 4) << 32)     // stride byte offset: 8 rows * 128 B     bits [32,46)
+         | (1ull << 46)                      // descriptor version (sm_100)            bits [46,48)
+         | (2ull << 61);                     // layout: SWIZZLE_128B                   bits [61,64)
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = s32, A = u8, B = s8, both K-major.
+__host__ __device__ constexpr uint32_t instr_desc_i8(int M, int N) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+digit_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
+                  int32_t *__restrict__ C, uint32_t count, uint32_t ldc, uint32_t tiles_m, uint32_t tiles_n,
+                  uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_sh;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
+  constexpr uint32_t kABytes = BM * BK, kBBytes = BN * BK;
+  auto sA = [&](uint32_t s) { return tiles_base + s * kABytes; };
+  auto sB = [&](uint32_t s) { return tiles_base + STAGES * kABytes + s * kBBytes; };
+  auto full = [&](uint32_t s) { return smem_u32(&bars[s]); };
+  auto empty = [&](uint32_t s) { return smem_u32(&bars[STAGES + s]); };
+  const uint32_t tmem_full = smem_u32(&bars[2 * STAGES]);
+
+  // tile of this block: K split outermost, then bands of `band` m-tiles swept over all n-tiles, so the
+  // blocks resident at the same time share their W rows and Q columns in L2
+  const uint32_t per_split = tiles_m * tiles_n;
+  const uint32_t ks = blockIdx.x / per_split;
+  const uint32_t t = blockIdx.x - ks * per_split;
+  const uint32_t b = t / (band * tiles_n);
+  const uint32_t in_band = t - b * band * tiles_n;
+  const uint32_t bm = min(band, tiles_m - b * band);
+  const uint32_t tile_m = b * band + in_band % bm, tile_n = in_band / bm;
+  const uint32_t k0 = ks * ksteps_per_split;
+  const uint32_t nk = min(ksteps_per_split, ksteps - k0);
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {  // TMA producer
+      for (uint32_t i = 0; i < nk; ++i) {
+        const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        mbar_arrive_expect_tx(full(s), kABytes + kBBytes);
+        const int32_t kbyte = (int32_t)((k0 + i) * BK);
+        tma_load_2d(sA(s), &tmW, kbyte, (int32_t)(tile_m * BM), full(s));
+        tma_load_2d(sB(s), &tmQ, kbyte, (int32_t)(tile_n * BN), full(s));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {  // MMA issuer
+      constexpr uint32_t idesc = instr_desc_i8(BM, BN);
+      for (uint32_t i = 0; i < nk; ++i) {
+        const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(full(s), ph);
+        tc_fence_after();
+        const uint64_t ad = smem_desc_sw128(sA(s)), bd = smem_desc_sw128(sB(s));
+#pragma unroll
+        for (uint32_t k = 0; k < BK / UK; ++k)  // +32 bytes along K inside the swizzle row: +2 in 16-byte units
+          umma_i8(tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) != 0);
+        tc_commit(empty(s));  // frees the stage when these MMAs have read it
+      }
+      tc_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane = resample row of the tile
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t quarter = warp & 3;
+    const uint32_t row = tile_m * BM + quarter * 32 + lane;
+    int32_t *crow = C + ((uint64_t)ks * count + row) * ldc + (uint64_t)tile_n * BN;
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < BN; c0 += 32) {
+      if (tile_n * BN + c0 >= ldc) break;  // warp-uniform
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(tmem + ((quarter * 32u) << 16) + c0)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < count) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4 *>(crow + c0 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)BN) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// features -> digits
+// ------------------------------------------------------------------------------------------
+// Feature q of a normalised row x[0..step) in the reference order [A, AB_0.., (BA_0..,) B], SA_NACC order:
+//   type 0: x[u]          type 1: x[u] * x[v]          type 2: x[u] * (x[v] - x[w])          type 3: (x[u] - x[v])^2
+struct FeatDesc {
+  uint16_t type, u, v, w;
+};
+
+__global__ void __launch_bounds__(256)
+feature_table_kernel(int Dg, int step, int nfeat, FeatDesc *__restrict__ tab) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nfeat) return;
+  FeatDesc d{0, 0, 0, 0};
+  const int A = 0, B = step - 1;
+  if (q == 0) d = {0, (uint16_t)A, 0, 0};
+  else if (q == 1) d = {0, (uint16_t)B, 0, 0};
+  else if (q == 2) d = {1, (uint16_t)A, (uint16_t)A, 0};
+  else if (q == 3) d = {1, (uint16_t)B, (uint16_t)B, 0};
+  else if (q == 4) d = {1, (uint16_t)A, (uint16_t)B, 0};
+  else if (q < 5 + Dg) d = {2, (uint16_t)B, (uint16_t)(1 + q - 5), (uint16_t)A};       // B * (AB_j - A)
+  else if (q < 5 + 2 * Dg) d = {3, (uint16_t)A, (uint16_t)(1 + q - 5 - Dg), 0};        // (A - AB_j)^2
+  else {
+    int p = q - 5 - 2 * Dg, j = 0;  // pair p -> (j, k), row-major over the strict upper triangle
+    while (p >= Dg - 1 - j) {
+      p -= Dg - 1 - j;
+      ++j;
+    }
+    const int k = j + 1 + p;
+    d = {1, (uint16_t)(1 + Dg + j), (uint16_t)(1 + k), 0};                             // BA_j * AB_k
+  }
+  tab[q] = d;
+}
+
+// Same operations, in the same order, as normalize_features_kernel (analyze.cu).
+template <class X>
+__device__ __forceinline__ double feature_value(const FeatDesc d, X x) {
+  const double a = x(d.u);
+  if (d.type == 0) return a;
+  const double b = x(d.v);
+  if (d.type == 1) return __dmul_rn(a, b);
+  if (d.type == 2) return __dmul_rn(a, __dsub_rn(b, x(d.w)));
+  const double t = __dsub_rn(a, b);
+  return __dmul_rn(t, t);
+}
+
+// Normalised rows [i0, i0 + rows) of Y -> xs[col * pitch + r] (column-major in shared memory); rows >= N are 0.
+__device__ __forceinline__ void load_tile(const double *__restrict__ Y, uint64_t N, int step, uint64_t i0, int rows,
+                                          int pitch, double mean, double sd, double *xs) {
+  const int total = rows * step;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int r = e / step, c = e - r * step;
+    const uint64_t i = i0 + r;
+    xs[c * pitch + r] = i < N ? __ddiv_rn(__dsub_rn(Y[i * (uint64_t)step + c], mean), sd) : 0.0;
+  }
+}
+
+// fmax_bits[q] (bit pattern of a non-negative double, zeroed by the caller) = max_i |F[i][q]|
+__global__ void __launch_bounds__(256)
+feature_max_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat, const FeatDesc *__restrict__ tab,
+                   const double *__restrict__ stats, int tile_rows, unsigned long long *__restrict__ fmax_bits) {
+  extern __shared__ double dsm[];
+  const int pitch = tile_rows + 1;
+  double *xs = dsm;                       // [step][pitch]
+  double *best = dsm + step * pitch;      // [nfeat], entry q owned by thread q % 256
+  const double mean = stats[0], sd = stats[1];
+  for (int q = threadIdx.x; q < nfeat; q += blockDim.x) best[q] = 0.0;
+  const uint64_t tiles = ceil_div_u64(N, tile_rows);
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __syncthreads();
+    load_tile(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
+    __syncthreads();
+    for (int q = threadIdx.x; q < nfeat; q += blockDim.x) {
+      const FeatDesc d = tab[q];
+      double m = best[q];
+      for (int r = 0; r < tile_rows; ++r)
+        m = fmax(m, fabs(feature_value(d, [&](int c) { return xs[c * pitch + r]; })));
+      best[q] = m;
+    }
+  }
+  for (int q = threadIdx.x; q < nfeat; q += blockDim.x)
+    atomicMax(fmax_bits + q, (unsigned long long)__double_as_longlong(best[q]));
+}
+
+// scale[q] = 2^(bits - e), inv[q] = 2^(e - bits) with max |F[:, q]| < 2^e: |F * scale| < 2^bits
+__global__ void __launch_bounds__(256)
+feature_scale_kernel(const unsigned long long *__restrict__ fmax, int nfeat, int bits, double *__restrict__ scale,
+                     double *__restrict__ inv) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nfeat) return;
+  const double m = __longlong_as_double((long long)fmax[q]);
+  int e = 0;
+  if (m > 0.0 && m < INFINITY) e = ilogb(m) + 1;
+  e = max(-900, min(900, e));
+  scale[q] = ldexp(1.0, bits - e);
+  inv[q] = ldexp(1.0, e - bits);
+}
+
+// Q[(q*S + s) * Kp + i] = digit s of rint(F[i][q] * scale[q]).  Blocks take tiles of TR rows; LPF = TR/4 lanes
+// share a feature (4 consecutive rows each -> one 32-bit store per digit, TR contiguous bytes per column).
+template <int S>
+__global__ void __launch_bounds__(256)
+digit_split_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat, const FeatDesc *__restrict__ tab,
+                   const double *__restrict__ stats, const double *__restrict__ scale, int tile_rows, uint64_t Kp,
+                   int8_t *__restrict__ Q) {
+  extern __shared__ double dsm[];
+  const int pitch = tile_rows + 1;
+  double *xs = dsm;
+  const double mean = stats[0], sd = stats[1];
+  const int lpf = tile_rows >> 2, fpw = 32 / lpf;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int sub = lane % lpf, fsel = lane / lpf;
+  const uint64_t tiles = Kp / tile_rows;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __syncthreads();
+    load_tile(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
+    __syncthreads();
+    for (int q = warp * fpw + fsel; q < nfeat; q += nwarps * fpw) {
+      const FeatDesc d = tab[q];
+      const double sc = scale[q];
+      uint32_t packed[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) packed[s] = 0;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = 4 * sub + rr;
+        const double f = feature_value(d, [&](int c) { return xs[c * pitch + r]; });
+        long long t = __double2ll_rn(__dmul_rn(f, sc));
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const long long dgt = (long long)(int8_t)(t & 0xff);
+          packed[s] |= ((uint32_t)dgt & 0xffu) << (8 * rr);
+          t = (t - dgt) >> 8;
+        }
+      }
+      int8_t *dst = Q + (uint64_t)q * S * Kp + tile * tile_rows + 4 * sub;
+#pragma unroll
+      for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t *>(dst + (uint64_t)s * Kp) = packed[s];
+    }
+  }
+}
+
+__device__ __forceinline__ double i128_to_double(__int128 v) {
+  const bool neg = v < 0;
+  const unsigned __int128 a = neg ? (unsigned __int128)0 - (unsigned __int128)v : (unsigned __int128)v;
+  const uint64_t hi = (uint64_t)(a >> 64), lo = (uint64_t)a;
+  double r;
+  if (hi == 0) {
+    r = __ull2double_rn(lo);
+  } else {
+    const int sh = 64 - __clzll((long long)hi);  // 1..64 bits above the low word
+    uint64_t top = (uint64_t)(a >> sh);
+    if ((a & (((unsigned __int128)1 << sh) - 1)) != 0) top |= 1;  // sticky bit: one correct rounding
+    r = ldexp(__ull2double_rn(top), sh);
+  }
+  return neg ? -r : r;
+}
+
+// psum[c][q] = inv[q] * sum_s 256^s * sum_ks C[ks][c][q*S + s]
+__global__ void __launch_bounds__(256)
+digit_combine_kernel(const int32_t *__restrict__ C, uint64_t count, uint64_t ldc, int ksplit, int nfeat, int S,
+                     const double *__restrict__ inv, double *__restrict__ psum) {
+  const uint64_t total = count * (uint64_t)nfeat;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = idx / nfeat;
+    const int q = (int)(idx - c * nfeat);
+    __int128 acc = 0;
+    for (int s = S - 1; s >= 0; --s) {
+      long long part = 0;
+      for (int ks = 0; ks < ksplit; ++ks) part += C[((uint64_t)ks * count + c) * ldc + (uint64_t)q * S + s];
+      acc = acc * 256 + part;
+    }
+    psum[idx] = __dmul_rn(i128_to_double(acc), inv[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Byte matrix [rows][K] with row pitch `pitch`: boxes of box_rows x 128 bytes, 128-byte swizzle, zero fill
+// outside [0, K) x [0, rows).
+static int make_map(CUtensorMap *map, const void *base, uint64_t K, uint64_t rows, uint64_t pitch, int box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  SA_REQUIRE(fn, SA_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {K, rows};
+  const cuuint64_t strides[1] = {pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SA_REQUIRE(r == CUDA_SUCCESS, SA_ERR_ARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SA_OK;
+}
+
+static uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// K splits so that small launches still fill the GPU (at least ~2 blocks per SM, at least 8 K-steps each).
+static int choose_ksplit(uint64_t count, uint64_t ncols, uint64_t K, int bn) {
+  const uint64_t tiles = ceil_div_u64(count, BM) * ceil_div_u64(ncols, bn);
+  const uint64_t ksteps = ceil_div_u64(K, BK);
+  const uint64_t want = 2 * (uint64_t)sm_count();
+  uint64_t ks = tiles >= want ? 1 : ceil_div_u64(want, tiles);
+  const uint64_t cap = ksteps / 8 ? ksteps / 8 : 1;
+  if (ks > cap) ks = cap;
+  const uint64_t per = ceil_div_u64(ksteps, ks);
+  return (int)ceil_div_u64(ksteps, per);  // no empty split
+}
+
+static int pick_bn(uint64_t ncols) { return ncols > 128 ? 256 : 128; }
+
+template <int BN, int STAGES>
+static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C, uint64_t count,
+                       uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit) {
+  const uint64_t tm = ceil_div_u64(count, BM), tn = ceil_div_u64(ncols, BN);
+  const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
+  const uint64_t blocks = tm * tn * (uint64_t)ksplit;
+  SA_REQUIRE(blocks < (1ull << 31), SA_ERR_UNSUPPORTED, "digit GEMM: too many tiles");
+  const size_t smem = (size_t)STAGES * (BM + BN) * BK + 1024;
+  auto kern = digit_gemm_kernel<BN, STAGES>;
+  SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, (uint32_t)tm,
+                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 16u);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+static int feature_tile_rows(int step, int nfeat) {
+  // shared memory: step * (rows + 1) doubles (+ nfeat doubles in the max kernel), at most ~200 KB
+  for (int rows = 128; rows >= 8; rows >>= 1)
+    if (((size_t)step * (rows + 1) + nfeat) * 8 <= 200 * 1024) return rows;
+  return 0;
+}
+
+}  // namespace dg
+}  // namespace sa
+
+using namespace sa;
+using namespace sa::dg;
+
+extern "C" uint64_t sa_digit_row_pitch(uint64_t N) { return round_up(N, 128); }
+
+extern "C" uint64_t sa_digit_ldc(int nfeat, int ndigits) { return round_up((uint64_t)nfeat * ndigits, 32); }
+
+extern "C" int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count) {
+  const uint64_t ncols = (uint64_t)nfeat * ndigits;
+  return choose_ksplit(count, ncols, N, pick_bn(ncols));
+}
+
+extern "C" size_t sa_digit_features_workspace_bytes(int nfeat) {
+  return (size_t)round_up((uint64_t)nfeat * (sizeof(FeatDesc) + 8 + 8), 256);
+}
+
+extern "C" size_t sa_digit_sums_workspace_bytes(uint64_t N, int nfeat, int ndigits, uint64_t count) {
+  return (size_t)sa_digit_ksplit(N, nfeat, ndigits, count) * count * sa_digit_ldc(nfeat, ndigits) * sizeof(int32_t);
+}
+
+extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count,
+                                 const int8_t *d_Q, uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit,
+                                 int32_t *d_C, uint64_t ldc) {
+  SA_REQUIRE(d_w && d_Q && d_C, SA_ERR_ARG, "sa_digit_gemm_i32: null pointer");
+  SA_REQUIRE(count >= 1 && ncols >= 1 && K >= 1 && ksplit >= 1, SA_ERR_ARG, "sa_digit_gemm_i32: bad shape");
+  SA_REQUIRE(K <= (1ull << 24), SA_ERR_UNSUPPORTED, "sa_digit_gemm_i32: more than 2^24 rows could overflow int32");
+  SA_REQUIRE(w_pitch % 16 == 0 && q_pitch % 16 == 0 && w_pitch >= K && q_pitch >= K, SA_ERR_ARG,
+             "sa_digit_gemm_i32: row pitches must be multiples of 16 bytes and >= K");
+  SA_REQUIRE(((uintptr_t)d_w & 15) == 0 && ((uintptr_t)d_Q & 15) == 0 && ((uintptr_t)d_C & 15) == 0, SA_ERR_ARG,
+             "sa_digit_gemm_i32: pointers must be 16-byte aligned");
+  SA_REQUIRE(ldc % 32 == 0 && ldc >= ncols, SA_ERR_ARG, "sa_digit_gemm_i32: ldc must be a multiple of 32 >= ncols");
+  SA_REQUIRE((uint64_t)ksplit <= ceil_div_u64(K, BK), SA_ERR_ARG, "sa_digit_gemm_i32: more K splits than K steps");
+  {
+    const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
+    SA_REQUIRE(per * (uint64_t)(ksplit - 1) < ksteps, SA_ERR_ARG, "sa_digit_gemm_i32: ksplit leaves an empty split");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bn = pick_bn(ncols);
+  CUtensorMap mw, mq;
+  int rc = make_map(&mw, d_w, K, count, w_pitch, BM);
+  if (rc) return rc;
+  rc = make_map(&mq, d_Q, K, ncols, q_pitch, bn);
+  if (rc) return rc;
+  if (bn == 256) return launch_gemm<256, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
+  return launch_gemm<128, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
+}
+
+extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
+                                    const double *d_stats, int ndigits, int8_t *d_Q, double *d_inv, void *d_work,
+                                    size_t work_bytes) {
+  SA_REQUIRE(d_Y && d_stats && d_Q && d_inv && d_work, SA_ERR_ARG, "sa_digit_features_i8: null pointer");
+  SA_REQUIRE(N >= 1 && Dg >= 1 && Dg <= 16000, SA_ERR_ARG, "sa_digit_features_i8: bad shape");
+  SA_REQUIRE(ndigits >= 2 && ndigits <= kMaxDigits, SA_ERR_ARG, "sa_digit_features_i8: 2 <= ndigits <= 8");
+  SA_REQUIRE(N <= (1ull << 24), SA_ERR_UNSUPPORTED, "sa_digit_features_i8: N > 2^24");
+  const int nfeat = SA_NACC(Dg, second_order);
+  const int step = second_order ? 2 * Dg + 2 : Dg + 2;
+  SA_REQUIRE(work_bytes >= sa_digit_features_workspace_bytes(nfeat), SA_ERR_WORKSPACE,
+             "sa_digit_features_i8: workspace too small");
+  const int rows = feature_tile_rows(step, nfeat);
+  SA_REQUIRE(rows >= 8, SA_ERR_UNSUPPORTED, "sa_digit_features_i8: %d outputs per base row do not fit shared memory",
+             step);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t Kp = sa_digit_row_pitch(N);
+  unsigned long long *fmax = (unsigned long long *)d_work;
+  double *scale = (double *)(fmax + nfeat);
+  FeatDesc *tab = (FeatDesc *)(scale + nfeat);
+  const int fb = (nfeat + 255) / 256;
+  SA_CUDA(cudaMemsetAsync(fmax, 0, (size_t)nfeat * 8, st));
+  feature_table_kernel<<<fb, 256, 0, st>>>(Dg, step, nfeat, tab);
+  const size_t smem_max = ((size_t)step * (rows + 1) + nfeat) * 8;
+  const size_t smem_split = (size_t)step * (rows + 1) * 8;
+  SA_CUDA(cudaFuncSetAttribute(feature_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  const uint64_t tiles = ceil_div_u64(N, rows);
+  const unsigned grid = (unsigned)(tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count());
+  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows, fmax);
+  feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv);
+  const uint64_t tiles2 = Kp / rows;
+  const unsigned grid2 = (unsigned)(tiles2 < (uint64_t)sm_count() ? tiles2 : (uint64_t)sm_count());
+#define SA_SPLIT(S)                                                                                               \
+  case S:                                                                                                         \
+    SA_CUDA(cudaFuncSetAttribute(digit_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                 (int)smem_split));                                                               \
+    digit_split_kernel<S><<<grid2, 256, smem_split, st>>>(d_Y, N, step, nfeat, tab, d_stats, scale, rows, Kp, d_Q); \
+    break;
+  switch (ndigits) {
+    SA_SPLIT(2) SA_SPLIT(3) SA_SPLIT(4) SA_SPLIT(5) SA_SPLIT(6) SA_SPLIT(7) SA_SPLIT(8)
+  }
+#undef SA_SPLIT
+  note_launches(4);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat,
+                                 int ndigits, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work,
+                                 size_t work_bytes, double *d_psum) {
+  SA_REQUIRE(d_Q && d_inv && d_w && d_work && d_psum, SA_ERR_ARG, "sa_digit_sums_f64: null pointer");
+  SA_REQUIRE(N >= 1 && nfeat >= 1 && count >= 1, SA_ERR_ARG, "sa_digit_sums_f64: bad shape");
+  SA_REQUIRE(ndigits >= 2 && ndigits <= kMaxDigits, SA_ERR_ARG, "sa_digit_sums_f64: 2 <= ndigits <= 8");
+  SA_REQUIRE(work_bytes >= sa_digit_sums_workspace_bytes(N, nfeat, ndigits, count), SA_ERR_WORKSPACE,
+             "sa_digit_sums_f64: workspace too small");
+  const uint64_t ncols = (uint64_t)nfeat * ndigits, ldc = sa_digit_ldc(nfeat, ndigits);
+  const int ksplit = sa_digit_ksplit(N, nfeat, ndigits, count);
+  int32_t *C = (int32_t *)d_work;
+  const int rc = sa_digit_gemm_i32(stream, d_w, w_pitch, count, d_Q, sa_digit_row_pitch(N), ncols, N, ksplit, C, ldc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t total = count * (uint64_t)nfeat;
+  const unsigned grid = (unsigned)(ceil_div_u64(total, 256) < 148ull * 16 ? ceil_div_u64(total, 256) : 148ull * 16);
+  digit_combine_kernel<<<grid, 256, 0, st>>>(C, count, ldc, ksplit, nfeat, ndigits, d_inv, d_psum);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

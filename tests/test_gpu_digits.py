@@ -1,0 +1,142 @@
+"""GPU parity of the opt-in exact-integer tensor-core engine (csrc/digits.cu, ``algo="digits"``).
+
+The int8 GEMM must be bit-exact against an integer matmul; the engine must meet the same 1e-10 bar against the
+frozen reference outputs as the FP64 engines (tests/test_gpu_analyze.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden, problem_from
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-10, 1e-13
+
+
+def _gemm(W, Q, ksplit):
+    """C[ks][count][ldc] through sa_digit_gemm_i32 for host arrays W uint8 [count, K], Q int8 [ncols, K]."""
+    import torch
+    from salib_b200 import _lib, _runtime as rt
+
+    count, K = W.shape
+    ncols = Q.shape[0]
+    pitch = (K + 127) // 128 * 128
+    ldc = (ncols + 31) // 32 * 32
+    Wd = torch.full((count, pitch), 7, dtype=torch.uint8, device="cuda")      # junk in the pad columns:
+    Qd = torch.full((ncols, pitch), -3, dtype=torch.int8, device="cuda")      # TMA must zero-fill beyond K
+    Wd[:, :K] = torch.from_numpy(W).cuda()
+    Qd[:, :K] = torch.from_numpy(Q).cuda()
+    Cd = torch.full((ksplit, count, ldc), -1, dtype=torch.int32, device="cuda")
+    _lib.call("sa_digit_gemm_i32", rt.stream_ptr(), rt.ptr(Wd), pitch, count, rt.ptr(Qd), pitch, ncols, K, ksplit,
+              rt.ptr(Cd), ldc)
+    torch.cuda.synchronize()
+    return Cd.cpu().numpy()[:, :, :ncols]
+
+
+@pytest.mark.parametrize("count,ncols,K,ksplit", [(1, 7, 100, 1), (5, 40, 128, 1), (130, 129, 1000, 1),
+                                                  (130, 129, 1000, 3), (300, 600, 5000, 1), (257, 300, 4097, 5),
+                                                  (128, 256, 16384, 2), (64, 128, 777, 1), (200, 100, 3000, 2)])
+def test_digit_gemm_is_exact(count, ncols, K, ksplit):
+    rng = np.random.default_rng(count * 1000 + ncols + K)
+    W = rng.integers(0, 256, size=(count, K), dtype=np.uint8)            # full uint8 range: A is unsigned
+    Q = rng.integers(-128, 128, size=(ncols, K), dtype=np.int8)          # full int8 range: B is signed
+    got = _gemm(W, Q, ksplit)
+    ksteps = -(-K // 128)
+    per = -(-ksteps // ksplit)
+    for ks in range(ksplit):
+        lo, hi = ks * per * 128, min(K, (ks + 1) * per * 128)
+        want = W[:, lo:hi].astype(np.int64) @ Q[:, lo:hi].astype(np.int64).T
+        assert np.array_equal(got[ks].astype(np.int64), want), f"K split {ks}"
+
+
+def test_digit_gemm_one_hot_layout():
+    """Each output picks exactly one (row of W, column of Q, k) product: any operand-layout error shows up
+    as a misplaced value rather than as noise."""
+    count, ncols, K = 128, 256, 512
+    W = np.zeros((count, K), dtype=np.uint8)
+    Q = np.zeros((ncols, K), dtype=np.int8)
+    for m in range(count):
+        W[m, (m * 5) % K] = 1 + m % 100
+    for n in range(ncols):
+        Q[n, (n * 5) % K] = (n % 120) - 60
+    got = _gemm(W, Q, 1)[0]
+    want = W.astype(np.int64) @ Q.astype(np.int64).T
+    assert np.array_equal(got, want)
+
+
+CASES = ["ishigami_n1024_r100", "ishigami_n256_c1_r50", "g8_n512_r64", "g8_n512_c1_r64", "g16_n256_r32",
+         "grp3_n512_r40", "g64_n128_r16"]
+
+
+def _cmp(S, ref, D, c2, rtol=RTOL, atol=ATOL):
+    for k in ["S1", "S1_conf", "ST", "ST_conf", "S1_conf_all", "ST_conf_all"]:
+        np.testing.assert_allclose(S[k], ref[k], rtol=rtol, atol=atol, err_msg=k)
+    if c2:
+        iu = np.triu_indices(D, 1)
+        for k in ("S2", "S2_conf"):
+            np.testing.assert_allclose(S[k][iu], np.asarray(ref[k])[iu], rtol=rtol, atol=atol, err_msg=k)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_digits_engine_matches_frozen_reference(name):
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_" + name)
+    D = z["S1"].shape[0]
+    S = sobol.analyze_device(problem_from(z), z["Y"], calc_second_order=bool(z["c2"]), conf_level=float(z["conf"]),
+                             keep_resamples=True, r=z["r"].astype(np.int64), algo="digits")
+    _cmp(S, z, D, bool(z["c2"]))
+
+
+@pytest.mark.parametrize("digits,rtol", [(5, 1e-7), (6, 1e-9), (8, 1e-10)])
+def test_digit_count_sets_the_precision(digits, rtol, monkeypatch):
+    from salib_b200.analyze import sobol
+
+    monkeypatch.setattr(sobol, "DIGITS", digits)
+    z = golden("analyze_g16_n256_r32")
+    S = sobol.analyze_device(problem_from(z), z["Y"], calc_second_order=True, conf_level=float(z["conf"]),
+                             keep_resamples=True, r=z["r"].astype(np.int64), algo="digits")
+    _cmp(S, z, 16, True, rtol=rtol, atol=rtol * 1e-2)
+
+
+def test_digits_engine_matches_fp64_engine_philox():
+    """Same device Philox multiplicities through both engines, a shape with several resample tiles and K
+    splits: D = 24, N = 8192, R = 300."""
+    from salib_b200.analyze import sobol
+    from salib_b200.sample import sobol as sample
+    from salib_b200.test_functions import Sobol_G
+
+    D = 24
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+    X = sample.sample(p, 8192, scramble=False)
+    Y = Sobol_G.evaluate(X, a=np.linspace(0.0, 30.0, D))
+    a = sobol.analyze_device(p, Y, num_resamples=300, seed=7, resample="philox", keep_resamples=True)
+    b = sobol.analyze_device(p, Y, num_resamples=300, seed=7, resample="philox", keep_resamples=True,
+                             algo="digits")
+    _cmp(b, a, D, True, rtol=1e-9, atol=1e-12)
+
+
+def test_digits_row_sharded_single_process():
+    """Two row shards in one process (partial sums added, then the estimator algebra) through the digits engine."""
+    from salib_b200.analyze import sobol
+
+    z = golden("analyze_g8_n512_r64")
+    p = problem_from(z)
+    Y = np.asarray(z["Y"])
+    step = 2 * 8 + 2
+    cut = 200
+    S = sobol.analyze_row_sharded(p, [(0, Y[:cut * step]), (cut, Y[cut * step:])], 512, calc_second_order=True,
+                                  conf_level=float(z["conf"]), keep_resamples=True, r=z["r"].astype(np.int64),
+                                  algo="digits", distributed=False)
+    _cmp(S, z, 8, True)
+
+
+def test_exports():
+    from salib_b200 import _lib
+
+    L = _lib.lib()
+    assert L.sa_digit_row_pitch(1000) == 1024
+    assert L.sa_digit_ldc(10, 6) == 64
+    assert L.sa_digit_ksplit(1 << 20, 2149, 6, 10000) == 1
+    assert isinstance(L.sa_digit_sums_workspace_bytes(1 << 14, 100, 6, 50), int)
+    assert C.sizeof(C.c_size_t) == 8
