@@ -49,6 +49,24 @@ def test_digit_gemm_is_exact(count, ncols, K, ksplit):
         assert np.array_equal(got[ks].astype(np.int64), want), f"K split {ks}"
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("count,ncols,K,ksplit", [(3, 7, 300, 1), (130, 129, 1000, 2), (300, 600, 5000, 1),
+                                                  (513, 1030, 2500, 3)])
+def test_digit_gemm_variants_are_exact(variant, count, ncols, K, ksplit, monkeypatch):
+    """Every tile shape (one CTA 128 x 128 / 128 x 256, CTA pair 256 x 256 / 256 x 512) on ragged problems."""
+    monkeypatch.setenv("SALIB_B200_DIGIT_GEMM", str(variant))
+    rng = np.random.default_rng(variant + count + ncols + K)
+    W = rng.integers(0, 256, size=(count, K), dtype=np.uint8)
+    Q = rng.integers(-128, 128, size=(ncols, K), dtype=np.int8)
+    got = _gemm(W, Q, ksplit)
+    ksteps = -(-K // 128)
+    per = -(-ksteps // ksplit)
+    for ks in range(ksplit):
+        lo, hi = ks * per * 128, min(K, (ks + 1) * per * 128)
+        want = W[:, lo:hi].astype(np.int64) @ Q[:, lo:hi].astype(np.int64).T
+        assert np.array_equal(got[ks].astype(np.int64), want), f"variant {variant}, K split {ks}"
+
+
 def test_digit_gemm_one_hot_layout():
     """Each output picks exactly one (row of W, column of Q, k) product: any operand-layout error shows up
     as a misplaced value rather than as noise."""
