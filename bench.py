@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--resamples", type=int, default=10000)
     ap.add_argument("--first-order-only", action="store_true")
+    ap.add_argument("--algo", default="auto", help="analyze engine of the measured arm: auto | digits | fp64")
+    ap.add_argument("--no-fp64-leg", action="store_true", help="skip the extra FP64-engine measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample", action="store_true", help="skip the 70 GB sample-generation leg")
     ap.add_argument("--ref-log2n", type=int, default=10, help="bounded sample of the reference arm")
@@ -284,59 +286,130 @@ def main():
     fused = {"value": step_rows * N * a.steps / t_eval / 1e9, "unit": "Grows/s", "ms_per_pass": t_eval / a.steps * 1e3}
 
     # ---- leg 2 (the metric): sobol.analyze on resident Y
-    events = []
-
-    def analyze_step():
-        return analyze_sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100,
-                                            resample="philox", kernel_events=events)
-
-    for _ in range(a.warmup):
-        analyze_step()
-    events.clear()
-    L.sa_launch_count(1)
-    with ClockSampler(local_rank) as clocks:
-        t_an = timed(analyze_step, a.steps, 0)
-    launches = int(L.sa_launch_count(1))
-    S = analyze_step()
-    # dominant kernel: the accumulate launches of the timed steps
-    timed_events = events[: len(events) * a.steps // (a.steps + 1)] if events else []
-    k_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in timed_events)
-    k_rows = sum(c for c, _, _ in timed_events) * N
-    k_ms = max_over_ranks(k_ms)
-
-    # roofline denominator: FP64 FMA pipe, measured here
-    out = rt.zeros((1,), torch.float64)
     import ctypes
 
-    nthreads = ctypes.c_uint64(0)
-    best = 0.0
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.call("sa_microbench_fp64", rt.stream_ptr(), 40000, rt.ptr(out), ctypes.addressof(nthreads))
-        e1.record()
-        torch.cuda.synchronize()
-        best = max(best, 32.0 * 40000 * nthreads.value / (e0.elapsed_time(e1) / 1e3) / 1e12)
-    fp64_peak = best
-    if c2:
-        flop_per_row = 2 * (D * (D - 1) // 2) + 6 * D + 6
-        kernel = "s2_accum_smem_kernel (+ scalar_sums_kernel)" if D <= 64 else "accum_generic_kernel"
-    else:
-        flop_per_row = 6 * D + 6
-        kernel = "fo_accum_kernel"
-    achieved = flop_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
-    # DRAM bytes of one tile-kernel launch from the committed ncu capture (1184 resamples = one wave at
-    # N = 2^20: Y in analysis layout 1.36 GB + multiplicities 1.24 GB, each read once)
-    traffic = 2.635e9 if (c2 and D == 64 and a.log2n == 20) else None
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_final_ncu_full_summary.csv (dram read+write per 1184-resample launch)"
-                if traffic else None, "kernel": kernel,
-                "kernel_ms_per_step": k_ms / a.steps, "kernel_share_of_step": (k_ms / 1e3) / t_an,
+    def measure(algo, steps, warmup, sample_clocks):
+        """Times `steps` analyze calls; returns (seconds per step, accumulate-kernel ms per step, resample-rows the
+        accumulate launches covered per step, launches in the timed region, last result, clocks)."""
+        events = []
+
+        def analyze_step():
+            return analyze_sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100,
+                                                resample="philox", kernel_events=events, algo=algo)
+
+        for _ in range(warmup):
+            analyze_step()
+        events.clear()
+        L.sa_launch_count(1)
+        if sample_clocks:
+            with ClockSampler(local_rank) as clk:
+                t = timed(analyze_step, steps, 0)
+        else:
+            clk = None
+            t = timed(analyze_step, steps, 0)
+        n_launch = int(L.sa_launch_count(1))
+        timed_events = list(events)
+        S_ = analyze_step()
+        ms = max_over_ranks(sum(e0.elapsed_time(e1) for _, e0, e1 in timed_events)) / steps
+        rows = sum(c for c, _, _ in timed_events) * N / steps
+        return t / steps, ms, rows, n_launch, S_, clk
+
+    t_step, k_ms, k_rows, launches, S, clocks = measure(a.algo, a.steps, a.warmup, True)
+    t_an = t_step * a.steps
+    engine = getattr(S, "engine", "?")
+    nacc = analyze_sobol._nacc(D, c2)
+
+    def fp64_peak_tflops():
+        out = rt.zeros((1,), torch.float64)
+        nthreads = ctypes.c_uint64(0)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("sa_microbench_fp64", rt.stream_ptr(), 40000, rt.ptr(out), ctypes.addressof(nthreads))
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 32.0 * 40000 * nthreads.value / (e0.elapsed_time(e1) / 1e3) / 1e12)
+        return best
+
+    def i8_peak_tops():
+        """The digits GEMM's own MMA mix with the operand ring filled once: burst (best short run) and sustained
+        (one ~0.1 s run, power-limited clocks like the real kernel)."""
+        pairs = torch.cuda.get_device_properties(local_rank).multi_processor_count // 2
+        w = torch.ones((pairs * 256, 1024), dtype=torch.uint8, device="cuda")
+        q = torch.ones((512, 1024), dtype=torch.int8, device="cuda")
+        c = torch.empty((pairs * 256, 512), dtype=torch.int32, device="cuda")
+        ops = ctypes.c_double(0.0)
+
+        def run(ksteps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("sa_microbench_i8_tensor", rt.stream_ptr(), rt.ptr(w), rt.ptr(q), rt.ptr(c), ksteps,
+                      ctypes.addressof(ops))
+            e1.record()
+            torch.cuda.synchronize()
+            return ops.value / (e0.elapsed_time(e1) / 1e3) / 1e12
+
+        run(2000)
+        burst = max(run(4000) for _ in range(3))
+        sustained = run(130000)
+        return burst, sustained
+
+    def fp64_roofline(ms, rows, t_step_):
+        if c2:
+            flop_per_row = 2 * (D * (D - 1) // 2) + 6 * D + 6   # SURVEY 8(d)
+            kernel = "s2_accum_smem_kernel (+ scalar_sums_kernel)" if D > 48 else "fo_gemv_kernel (pair features)"
+        else:
+            flop_per_row = 6 * D + 6
+            kernel = "fo_gemv_kernel"
+        peak = fp64_peak_tflops()
+        achieved = flop_per_row * rows / (ms / 1e3) / 1e12 if ms > 0 else None
+        # DRAM bytes of one tile-kernel launch from the committed ncu capture (1184 resamples = one wave at
+        # N = 2^20: Y in analysis layout 1.36 GB + multiplicities 1.24 GB, each read once)
+        traffic = 2.635e9 if (c2 and D == 64 and a.log2n == 20) else None
+        return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r01_final_ncu_full_summary.csv (dram read+write per 1184-resample "
+                                  "launch)" if traffic else None,
+                "kernel": kernel, "kernel_ms_per_step": ms, "kernel_share_of_step": (ms / 1e3) / t_step_,
                 "algorithmic_flop_per_resample_row": flop_per_row,
                 "peak_source": "measured here: sa_microbench_fp64 (16 independent DFMA chains/thread)",
-                "note": "FP64-FMA-pipe bound (no tensor cores by design); rows with multiplicity 0 are skipped, "
-                        "so achieved counts algorithmic flop of all N*R resample-rows"}
+                "note": "FP64-FMA-pipe bound; rows with multiplicity 0 are skipped, so achieved counts "
+                        "algorithmic flop of all N*R resample-rows"}
+
+    if engine == "digits":
+        S_dig = analyze_sobol.DIGITS
+        ops_per_row = 2 * nacc * S_dig        # int8 multiply-adds x 2 per (resample, row)
+        burst, sustained = i8_peak_tops()
+        achieved = ops_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
+        traffic = 436.6e9 if (c2 and D == 64 and a.log2n == 20 and R == 10000 and world == 1) else None
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TOP/s (int8)",
+                    "frac": (achieved / sustained) if achieved else None, "peak_burst": burst,
+                    "traffic": traffic,
+                    "traffic_source": "profiles/r01_digits_pair_gemm_ncu_summary.csv (dram read+write of the "
+                                      "10^4-resample launch)" if traffic else None,
+                    "kernel": "digit_gemm_pair_kernel<2,4> (tcgen05.mma.cta_group::2.kind::i8)",
+                    "kernel_ms_per_step": k_ms, "kernel_share_of_step": (k_ms / 1e3) / t_step,
+                    "algorithmic_int8_ops_per_resample_row": ops_per_row, "digits": S_dig,
+                    "equivalent_fp64_tflops": (2 * (D * (D - 1) // 2) + 6 * D + 6 if c2 else 6 * D + 6) * k_rows
+                    / (k_ms / 1e3) / 1e12 if k_ms > 0 else None,
+                    "peak_source": "measured here: sa_microbench_i8_tensor (the kernel's own MMA mix, operand ring "
+                                   "filled once, ~0.1 s run at power-limited clocks); MEASURED_PEAKS.json has no "
+                                   "int8 figure (2 x its bf16 numbers: 3282 burst / 2771 sustained)",
+                    "note": "exact integer GEMM of the multiplicities with the int8 digits of the features; "
+                            "tensor pipe 94 % active at the 1.36 GHz the 1000 W cap allows (ncu)"}
+    else:
+        roofline = fp64_roofline(k_ms, k_rows, t_step)
+
+    fp64_leg = None
+    if engine == "digits" and not a.no_fp64_leg:
+        t2, k2, rows2, launches2, S2, _ = measure("fp64", 1, 1, False)
+        fp64_leg = {"analyze_s": t2, "value": N * R / t2, "unit": "resample-rows/s", "engine": S2.engine,
+                    "gpu_launches": launches2, "roofline": fp64_roofline(k2, rows2, t2),
+                    "max_abs_diff_vs_default": {k: float(np.nanmax(np.abs(np.asarray(S[k]) - np.asarray(S2[k]))))
+                                                for k in S if k in S2},
+                    "note": "the north-star design (no tensor cores) measured in the same run: 1 step after 1 "
+                            "warm-up, same Philox multiplicities"}
 
     # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region
     Yh = torch.empty(Yd.shape, dtype=torch.float64, pin_memory=True)
@@ -345,7 +418,7 @@ def main():
 
     def e2e_step():
         return analyze_sobol.analyze_device(problem, Yh, calc_second_order=c2, num_resamples=R, seed=100,
-                                            resample="philox")
+                                            resample="philox", algo=a.algo)
 
     t_e2e = timed(e2e_step, a.steps, 1)
     nest = analyze_sobol._nest(D, c2)
@@ -368,12 +441,15 @@ def main():
             "metric": "sobol.analyze resample-rows/s (N*R/s)", "value": N * R * a.steps / t_an,
             "unit": "resample-rows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t_an / a.steps * 1e3, "analyze_s": t_an / a.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 (sums: exact u8 x s8 -> s32 digit GEMM)" if engine == "digits" else "f64",
+            "data": "synthetic", "engine": engine,
             "config": {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
                        "skip_values": skip, "resample": "philox seed 100", "parallelism": f"resample-id x{world}",
                        "l2": f"Y is {Yd.numel() * 8 / 1e6:.0f} MB (> 126 MB L2), no explicit flush"
                        if Yd.numel() * 8 > 126e6 else "Y fits L2 (resident by design)"},
-            "sample": sample, "fused_sample_eval": fused, "roofline": roofline, "cpu_baseline": cpu,
+            "sample": sample, "fused_sample_eval": fused, "roofline": roofline, "fp64_engine": fp64_leg,
+            "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
             "result_check": {"S1_0": float(S["S1"][0]), "ST_0": float(S["ST"][0]), "S1_conf_0": float(S["S1_conf"][0]),
                              "ST_conf_0": float(S["ST_conf"][0]), "analytic_S1_0": analytic[0], "analytic_ST_0": analytic[1]},

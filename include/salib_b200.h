@@ -315,6 +315,11 @@ int sa_microbench_fp64(void *stream, int iters, double *d_out, uint64_t *h_threa
 /* 8x8 register outer-product DFMA mix of the tile kernel, no memory: flop = 128 * iters * (*h_threads). */
 int sa_microbench_fp64_outer(void *stream, int iters, double *d_out, uint64_t *h_threads);
 int sa_microbench_l2_read(void *stream, const void *d_buf, uint64_t bytes, int reps, double *d_out);
+/* int8 tensor-core rate of the digits engine's MMA mix with no operand traffic (ring filled once):
+ * d_w [pairs*256][1024] u8, d_Q [512][1024] s8, d_C [pairs*256][512] int32, pairs = SMs / 2;
+ * *h_ops = integer operations (2 per multiply-add) of the launch.                                       */
+int sa_microbench_i8_tensor(void *stream, const uint8_t *d_w, const int8_t *d_Q, int32_t *d_C, int ksteps,
+                            double *h_ops);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),
     "sa_microbench_fp64_outer": (C.c_int, [_vp, _i32, _vp, _vp]),
     "sa_microbench_l2_read": (C.c_int, [_vp, _vp, _u64, _i32, _vp]),
+    "sa_microbench_i8_tensor": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
 }
 
 

@@ -8,10 +8,13 @@ All arithmetic runs in the CUDA library through the C ABI (include/salib_b200.h)
             -> per batch of resamples: multiplicities -> weighted sums -> estimator algebra
             -> Z * std(ddof=1) over resamples
 
-Weighted sums: every sum is linear in the multiplicities.  First/total order, and second order while
-Dg <= PAIR_GEMV_MAX_DG, run as one skinny GEMM  w[R x N] * F[N x SA_NACC]  over per-row features (for second
-order the pair products BA_j * AB_k are features too); larger second-order problems use the 8x8
-register-tile kernel, which skips rows of multiplicity 0.
+Weighted sums: every sum is linear in the multiplicities, i.e. all of them together are one GEMM
+w[R x N] * F[N x SA_NACC] over per-row features (for second order the pair products BA_j * AB_k are features
+too) whose left operand holds small integers.  Two families of engines compute it:
+  * "digits" (large problems): F is split error-free into int8 radix-256 digits and the GEMM runs exactly on
+    the tensor cores (tcgen05 u8 x s8 -> s32 in TMEM), see csrc/digits.cu;
+  * "fp64": FP64-pipe kernels -- the skinny feature GEMV (first/total order, second order while
+    Dg <= PAIR_GEMV_MAX_DG) and the 8x8 register-tile kernel, which skips rows of multiplicity 0.
 
 Resample indices.  The reference draws ``r = rng.integers(N, size=(N, R))`` on the host
 (:113-117,144).  ``RESAMPLE_MODE``:
@@ -50,11 +53,17 @@ CONST_RESULT_MSG = (
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
 NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
-_ALGO = {"auto": 0, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5, "digits": 6}
-# SALIB_B200_ALGO: engine used when the caller does not name one ("auto" = the FP64 engines; "digits" = the
-# opt-in exact-integer tensor-core engine, csrc/digits.cu).  DIGITS: radix-256 digits per feature value.
+_ALGO = {"auto": 0, "fp64": -1, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5, "digits": 6}
+# Engines.  "digits": the bootstrap sums as an exact integer GEMM on the tensor cores (csrc/digits.cu);
+# "fp64": the FP64-pipe engines (feature GEMV / 8x8 register-tile kernel / generic).  "auto" takes "digits"
+# from DIGITS_MIN_WORK multiply-adds on (there it is ~10x faster and its sums carry no accumulation error),
+# "fp64" below (launch-latency territory) and whenever the integer engine does not apply (N > 2^24, digit
+# matrix over DIGITS_MAX_BYTES, non-finite or constant Y).  SALIB_B200_ALGO overrides "auto".
 DEFAULT_ALGO = os.environ.get("SALIB_B200_ALGO", "auto")
-DIGITS = int(os.environ.get("SALIB_B200_DIGITS", "7"))
+DIGITS = int(os.environ.get("SALIB_B200_DIGITS", "7"))   # radix-256 digits per feature value (54 bits)
+ENGINE_NAMES = {1: "fp64-generic", 3: "fp64-gemv", 4: "fp64-tile8", 5: "fp64-dmma", 6: "digits"}
+DIGITS_MIN_WORK = 1 << 31
+DIGITS_MAX_BYTES = 80 << 30
 PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
@@ -169,34 +178,49 @@ def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None, groups=1):
 class SobolAnalyzer:
     """Device state of one ``analyze`` call; also usable directly with a device-resident Y."""
 
-    def __init__(self, Dg, N, calc_second_order, algo="auto"):
+    def __init__(self, Dg, N, calc_second_order, algo="auto", resamples=0):
         rt.require_cuda()
         self.Dg, self.N, self.c2 = int(Dg), int(N), bool(calc_second_order)
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[DEFAULT_ALGO if algo == "auto" else algo]
         self.ndigits = DIGITS
-        # first/total order only: feature-GEMV kernel (any Dg).  Second order: the same GEMV over pair-product
-        # features while Dg is small (the 8x8 register-tile kernel needs Dg >= 57 to occupy all 32 lanes) and
-        # the feature matrix fits PAIR_GEMV_MAX_BYTES; else the tile kernel (Dg <= 512); else the generic one.
         L = _lib.lib()
-        if self.algo:
+        self.auto_digits = False
+        if self.algo > 0:
             kind = self.algo
-        elif not self.c2:
-            kind = 3
-        elif Dg <= PAIR_GEMV_MAX_DG and 8 * N * int(L.sa_chunked_feature_doubles(self.nacc)) <= PAIR_GEMV_MAX_BYTES:
-            kind = 3
+        elif self.algo == 0 and self._digits_pays(int(resamples)):
+            kind, self.auto_digits = 6, True
         else:
-            kind = 4 if Dg <= 512 else 1
-        self.kind = kind
-        self.groups = tile_groups(Dg) if kind == 4 else 1
+            kind = self._fp64_kind()
         self.sms = torch.cuda.get_device_properties(rt.device()).multi_processor_count
+        self._set_kind(kind)
         self.stride = L.sa_row_stride(self.Dg, int(self.c2))
         self.Npad = int(L.sa_pad_rows(self.N))
         self.stats = rt.zeros((8,), torch.float64)
         self.Yn = None
         self.Yt = None
         self.kernel_events = None   # bench.py sets this to a list to time the accumulate launches
+
+    def _fp64_kind(self):
+        """First/total order only: feature-GEMV kernel (any Dg).  Second order: the same GEMV over pair-product
+        features while Dg is small (the 8x8 register-tile kernel needs Dg >= 57 to occupy all 32 lanes) and the
+        feature matrix fits PAIR_GEMV_MAX_BYTES; else the tile kernel (Dg <= 512); else the generic one."""
+        if not self.c2:
+            return 3
+        feat = 8 * self.N * int(_lib.lib().sa_chunked_feature_doubles(self.nacc))
+        if self.Dg <= PAIR_GEMV_MAX_DG and feat <= PAIR_GEMV_MAX_BYTES:
+            return 3
+        return 4 if self.Dg <= 512 else 1
+
+    def _digits_pays(self, resamples):
+        q_bytes = self.nacc * self.ndigits * int(_lib.lib().sa_digit_row_pitch(self.N))
+        return (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.N <= 1 << 24
+                and q_bytes <= DIGITS_MAX_BYTES and self.step <= 2048)
+
+    def _set_kind(self, kind):
+        self.kind = kind
+        self.groups = tile_groups(self.Dg) if kind == 4 else 1
 
     # -- normalisation ---------------------------------------------------------------------
     def moments(self, Yd):
@@ -214,6 +238,13 @@ class SobolAnalyzer:
             self.moments(Yd)
         else:
             self.stats.copy_(rt.to_device(np.asarray(stats, dtype=np.float64), torch.float64))
+        if self.auto_digits:
+            # the integer engine needs finite, non-degenerate values to scale; NaN/inf/constant outputs keep the
+            # reference's NaN propagation through the FP64 engines
+            st = self.stats[:4].cpu().numpy()
+            if not (np.all(np.isfinite(st)) and st[1] > 0.0):
+                self.auto_digits = False
+                self._set_kind(self._fp64_kind())
         if self.kind == 6:                   # digit columns of the features (int8, K-major) + their scales
             self.Q = rt.empty((self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N)),), torch.int8)
             self.inv = rt.empty((self.nacc,), torch.float64)
@@ -389,7 +420,8 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
         if size % step or size == 0:
             raise RuntimeError("row shard size is not a multiple of the Saltelli block length")
-        eng = SobolAnalyzer(Dg, size // step, c2, algo=algo)
+        eng = SobolAnalyzer(Dg, size // step, c2, algo=algo,
+                            resamples=np.shape(r)[1] if r is not None else num_resamples)
         eng.kernel_events = kernel_events
         eng.row0 = int(row0)
         Yd = rt.to_device(Y, torch.float64).reshape(-1)
@@ -523,7 +555,8 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
     rt.require_cuda()
     engines = []
     for Y in Ys:
-        eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo)
+        eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo,
+                            resamples=np.shape(r)[1] if r is not None else num_resamples)
         eng.kernel_events = kernel_events
         # multi-GPU: a host Y is uploaded as one shard per rank and all-gathered over NVLink
         Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
@@ -569,6 +602,7 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         S = _assemble(Dg, bool(calc_second_order), keep, point[0].cpu().numpy(), conf.cpu().numpy(), kept, const_y)
         S.problem = problem
         S.to_df = MethodType(to_df, S)
+        S.engine = ENGINE_NAMES[eng.kind]
         out.append(S)
     return out
 
@@ -580,7 +614,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
     ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
-    ``algo``: force an accumulate kernel ("generic" | "tile8" | "gemv" | "dmma" | "digits"); ``distributed``: shard the
+    ``algo``: "auto" | "fp64" | "digits", or one kernel ("generic" | "tile8" | "gemv" | "dmma"); ``distributed``: shard the
     resamples over the initialised torch.distributed job; ``shard``: "resamples" (default: every rank holds
     Y, resample ids are split) or "rows" (every rank keeps only its base-row range of Y and all resamples'
     partial sums are all-reduced -- ``analyze_row_sharded``).

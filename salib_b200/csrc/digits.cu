@@ -263,7 +263,9 @@ template <int NACC, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
                        int32_t *__restrict__ C, uint32_t count, uint32_t ldc, uint32_t tiles_m, uint32_t tiles_n,
-                       uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band) {
+                       uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band, uint32_t no_reload) {
+  // no_reload (sa_microbench_i8_tensor only): the ring is filled once and the MMAs keep re-reading it -- the
+  // tensor-core rate of this instruction mix with no operand traffic, i.e. the roofline denominator.
   constexpr uint32_t PM = 256, PN = 256 * NACC;          // pair tile
   constexpr uint32_t kABytes = 128 * BK, kBBytes = NACC * 128 * BK;  // per CTA and stage
   constexpr uint32_t kCols = NACC * 256;                  // TMEM columns per CTA
@@ -312,7 +314,7 @@ digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
   if (warp == 0) {
     if (lane == 0) {  // TMA producer of this CTA's halves
       const int32_t wrow = (int32_t)(tile_m * PM + rank * 128);
-      for (uint32_t i = 0; i < nk; ++i) {
+      for (uint32_t i = 0; i < (no_reload ? min(nk, (uint32_t)STAGES) : nk); ++i) {
         const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(empty(s), ph ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(full(s), 2 * (kABytes + kBBytes));
@@ -330,7 +332,7 @@ digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
       constexpr uint32_t idesc = instr_desc_i8(256, 256);
       for (uint32_t i = 0; i < nk; ++i) {
         const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(full(s), ph);
+        if (!no_reload || i < STAGES) mbar_wait(full(s), ph);
         tc_fence_after();
         const uint64_t ad = smem_desc_sw128(sA(s));
 #pragma unroll
@@ -623,7 +625,8 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap
 
 template <int NACC, int STAGES>
 static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
-                            uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit) {
+                            uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
+                            uint32_t no_reload = 0) {
   const uint64_t tm = ceil_div_u64(count, 256), tn = ceil_div_u64(ncols, 256 * NACC);
   const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
   const uint64_t blocks = 2 * tm * tn * (uint64_t)ksplit;
@@ -632,7 +635,7 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtens
   auto kern = digit_gemm_pair_kernel<NACC, STAGES>;
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, (uint32_t)tm,
-                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u);
+                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u, no_reload);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -649,10 +652,13 @@ static int pick_variant(uint64_t count, uint64_t ncols) {
 static int variant_bm(int v) { return v >= 2 ? 256 : 128; }
 static int variant_bn(int v) { return v == 0 ? 128 : (v == 3 ? 512 : 256); }
 
-static int feature_tile_rows(int step, int nfeat) {
-  // shared memory: step * (rows + 1) doubles (+ nfeat doubles in the max kernel), at most ~200 KB
-  for (int rows = 128; rows >= 8; rows >>= 1)
-    if (((size_t)step * (rows + 1) + nfeat) * 8 <= 200 * 1024) return rows;
+// Rows per shared-memory tile of the feature kernels: step * (rows + 1) doubles (+ `extra` doubles) within
+// `budget` bytes, so that several blocks are resident per SM (the kernels are latency bound otherwise).
+static int feature_tile_rows(int step, int extra, size_t budget, int max_rows) {
+  for (int rows = max_rows; rows >= 8; rows >>= 1)
+    if (((size_t)step * (rows + 1) + extra) * 8 <= budget) return rows;
+  for (int rows = max_rows; rows >= 8; rows >>= 1)  // long rows: one block per SM
+    if (((size_t)step * (rows + 1) + extra) * 8 <= 200 * 1024) return rows;
   return 0;
 }
 
@@ -723,9 +729,10 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
   const int step = second_order ? 2 * Dg + 2 : Dg + 2;
   SA_REQUIRE(work_bytes >= sa_digit_features_workspace_bytes(nfeat), SA_ERR_WORKSPACE,
              "sa_digit_features_i8: workspace too small");
-  const int rows = feature_tile_rows(step, nfeat);
-  SA_REQUIRE(rows >= 8, SA_ERR_UNSUPPORTED, "sa_digit_features_i8: %d outputs per base row do not fit shared memory",
-             step);
+  const int rows_max = feature_tile_rows(step, nfeat, 54 * 1024, 32);   // 4 blocks per SM
+  const int rows = feature_tile_rows(step, 0, 72 * 1024, 64);          // 3 blocks per SM
+  SA_REQUIRE(rows >= 8 && rows_max >= 8, SA_ERR_UNSUPPORTED,
+             "sa_digit_features_i8: %d outputs per base row do not fit shared memory", step);
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t Kp = sa_digit_row_pitch(N);
   unsigned long long *fmax = (unsigned long long *)d_work;
@@ -734,15 +741,15 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
   const int fb = (nfeat + 255) / 256;
   SA_CUDA(cudaMemsetAsync(fmax, 0, (size_t)nfeat * 8, st));
   feature_table_kernel<<<fb, 256, 0, st>>>(Dg, step, nfeat, tab);
-  const size_t smem_max = ((size_t)step * (rows + 1) + nfeat) * 8;
+  const size_t smem_max = ((size_t)step * (rows_max + 1) + nfeat) * 8;
   const size_t smem_split = (size_t)step * (rows + 1) * 8;
   SA_CUDA(cudaFuncSetAttribute(feature_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  const uint64_t tiles = ceil_div_u64(N, rows);
-  const unsigned grid = (unsigned)(tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count());
-  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows, fmax);
+  const uint64_t tiles = ceil_div_u64(N, rows_max), slots = 4 * (uint64_t)sm_count();
+  const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax);
   feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv);
-  const uint64_t tiles2 = Kp / rows;
-  const unsigned grid2 = (unsigned)(tiles2 < (uint64_t)sm_count() ? tiles2 : (uint64_t)sm_count());
+  const uint64_t tiles2 = Kp / rows, slots2 = 3 * (uint64_t)sm_count();
+  const unsigned grid2 = (unsigned)(tiles2 < slots2 ? tiles2 : slots2);
 #define SA_SPLIT(S)                                                                                               \
   case S:                                                                                                         \
     SA_CUDA(cudaFuncSetAttribute(digit_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
@@ -777,5 +784,30 @@ extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *
   digit_combine_kernel<<<grid, 256, 0, st>>>(C, count, ldc, ksplit, nfeat, ndigits, d_inv, d_psum);
   note_launches(1);
   SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// Tensor-core roofline denominator: the CTA-pair kernel on one 256 x 512 tile per SM pair with the operand ring
+// filled once (no TMA / L2 / HBM traffic in the loop).  ops = 2 * 256 * 512 * 128 * ksteps per pair.
+extern "C" int sa_microbench_i8_tensor(void *stream, const uint8_t *d_w, const int8_t *d_Q, int32_t *d_C,
+                                       int ksteps, double *h_ops) {
+  SA_REQUIRE(d_w && d_Q && d_C && h_ops && ksteps >= 8, SA_ERR_ARG, "sa_microbench_i8_tensor: bad arguments");
+  // buffers: d_w [pairs*256][1024] u8, d_Q [512][1024] s8, d_C [pairs*256][512] int32
+  const uint64_t pairs = (uint64_t)sm_count() / 2, K = 1024;
+  CUtensorMap mw, mq;
+  int rc = make_map(&mw, d_w, K, pairs * 256, K, BM);
+  if (rc) return rc;
+  rc = make_map(&mq, d_Q, K, 512, K, 128);
+  if (rc) return rc;
+  // the K coordinate runs past the 1024-byte rows after 8 steps: those boxes are zero-filled, and never loaded
+  // anyway (no_reload stops the producer after the first ring fill)
+  const size_t smem = (size_t)4 * (128 + 256) * BK + 1024;
+  auto kern = digit_gemm_pair_kernel<2, 4>;
+  SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(2 * pairs), kThreads, smem, (cudaStream_t)stream>>>(mw, mq, d_C, (uint32_t)(pairs * 256), 512u,
+                                                                        (uint32_t)pairs, 1u, (uint32_t)ksteps,
+                                                                        (uint32_t)ksteps, 8u, 1u);
+  SA_LAUNCH_CHECK();
+  *h_ops = 2.0 * 256 * 512 * 128 * (double)ksteps * (double)pairs;
   return SA_OK;
 }

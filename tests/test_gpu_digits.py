@@ -134,6 +134,68 @@ def test_digits_engine_matches_fp64_engine_philox():
     _cmp(b, a, D, True, rtol=1e-9, atol=1e-12)
 
 
+def test_digits_invariances_d64():
+    """The properties tests/test_gpu_properties.py checks for the FP64 engines, for the integer engine at
+    D = 64, N = 2^16: "auto" picks it at this size and agrees with the FP64 engines; affine invariance; resample
+    sharding (two halves == one call, bit for bit: integer sums do not depend on the batch); an all-ones
+    multiplicity row reproduces the point estimate bit for bit."""
+    import torch
+
+    from salib_b200 import _runtime as rt
+    from salib_b200.analyze import sobol
+    from salib_b200.sample import sobol as sample
+    from salib_b200.test_functions import Sobol_G
+
+    D, N, R = 64, 1 << 16, 300
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+    plan, first = sample._plan(p, N, True, False, N, None)
+    Y = rt.empty(((2 * D + 2) * N,), torch.float64)
+    Sobol_G.evaluate_sample(plan, first, N, a=np.resize([0, 1, 4.5, 9, 99, 99, 99, 99.0], D), out=Y, check=False)
+    S = sobol.analyze_device(p, Y, num_resamples=R, seed=100, resample="philox", keep_resamples=True)
+    assert S.engine == "digits"
+    F = sobol.analyze_device(p, Y, num_resamples=R, seed=100, resample="philox", keep_resamples=True, algo="fp64")
+    assert F.engine == "fp64-tile8"
+    _cmp(S, F, D, True, rtol=1e-9, atol=1e-12)
+    T = sobol.analyze_device(p, 3.0 * Y + 7.0, num_resamples=R, seed=100, resample="philox", keep_resamples=True)
+    _cmp(S, T, D, True, rtol=1e-9, atol=1e-12)
+
+    eng = sobol.SobolAnalyzer(D, N, True, algo="digits")
+    eng.load(Y)
+    rs = sobol._Resampler(N, R, 100, "philox")
+    whole = eng.bootstrap(rs, 0, R)
+    halves = torch.cat([eng.bootstrap(rs, 0, 100), eng.bootstrap(rs, 100, R)])
+    assert torch.equal(whole, halves)
+    np.testing.assert_array_equal(whole[:, :D].cpu().numpy(), S["S1_conf_all"])
+    ones = torch.ones((eng.Npad,), dtype=torch.uint8, device="cuda")
+    est1 = rt.empty((1, eng.nest), torch.float64)
+    eng._accumulate(ones, 1, est1)
+    assert torch.equal(est1, eng.point())
+
+
+def test_auto_falls_back_to_fp64_for_degenerate_outputs():
+    """NaN / constant outputs keep the reference's NaN propagation through the FP64 engines even at
+    sizes where "auto" would take the integer engine."""
+    import warnings
+
+    from salib_b200.analyze import sobol
+
+    D, N = 8, 1 << 16
+    p = {"num_vars": D, "names": [f"x{i}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+    Y = np.random.default_rng(0).normal(size=(2 * D + 2) * N)
+    S = sobol.analyze_device(p, Y, num_resamples=1000, seed=3, resample="philox")
+    assert S.engine == "digits" and np.isfinite(S["S1"]).all()
+    Ynan = Y.copy()
+    Ynan[12345] = np.nan
+    for bad in (Ynan, np.full_like(Y, 0.5)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = sobol.analyze_device(p, bad, num_resamples=1000, seed=3, resample="philox")
+            F = sobol.analyze_device(p, bad, num_resamples=1000, seed=3, resample="philox", algo="fp64")
+        assert S.engine.startswith("fp64")
+        for k in F:
+            np.testing.assert_array_equal(S[k], F[k])
+
+
 def test_digits_row_sharded_single_process():
     """Two row shards in one process (partial sums added, then the estimator algebra) through the digits engine."""
     from salib_b200.analyze import sobol

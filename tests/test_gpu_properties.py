@@ -78,12 +78,14 @@ def test_analyze_invariances_d64():
 
     p, Y = _headline_y(18)
     N, R = 1 << 18, 296
-    S = sobol.analyze_device(p, Y, num_resamples=R, seed=100, resample="philox", keep_resamples=True)
-    T = sobol.analyze_device(p, 3.0 * Y + 7.0, num_resamples=R, seed=100, resample="philox", keep_resamples=True)
+    S = sobol.analyze_device(p, Y, num_resamples=R, seed=100, resample="philox", keep_resamples=True, algo="fp64")
+    T = sobol.analyze_device(p, 3.0 * Y + 7.0, num_resamples=R, seed=100, resample="philox", keep_resamples=True,
+                             algo="fp64")
     _close(S, T, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(S["S1_conf_all"], T["S1_conf_all"], rtol=1e-9, atol=1e-12)
+    assert S.engine == "fp64-tile8"
 
-    eng = sobol.SobolAnalyzer(64, N, True)
+    eng = sobol.SobolAnalyzer(64, N, True, algo="fp64")
     eng.load(Y)
     rs = sobol._Resampler(N, R, 100, "philox")
     whole = eng.bootstrap(rs, 0, R)

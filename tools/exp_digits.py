@@ -29,6 +29,7 @@ ap.add_argument("--digits", type=int, default=7)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--skip-fp64", action="store_true")
 ap.add_argument("--first-order-only", action="store_true")
+ap.add_argument("--trace", action="store_true", help="torch.profiler timeline of one digits call (device ops, gaps)")
 a = ap.parse_args()
 
 D, N, R = a.dim, 1 << a.log2n, a.resamples
@@ -63,6 +64,24 @@ def run(algo):
 
 
 out = {"D": D, "N": N, "R": R, "digits": a.digits, "second_order": c2}
+if a.trace:
+    from torch.profiler import ProfilerActivity, profile
+
+    run("digits")
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100, resample="philox",
+                             algo="digits")
+        torch.cuda.synchronize()
+    dev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                 key=lambda e: e.time_range.start)
+    t0 = dev[0].time_range.start
+    prev_end = t0
+    for e in dev:
+        gap = (e.time_range.start - prev_end) / 1e3
+        print(f"{(e.time_range.start - t0) / 1e3:9.3f} ms  dur {(e.time_range.end - e.time_range.start) / 1e3:9.3f} ms  "
+              f"gap {gap:7.3f} ms  {e.name[:70]}", file=sys.stderr)
+        prev_end = max(prev_end, e.time_range.end)
+    print(f"device span {(prev_end - t0) / 1e3:.3f} ms", file=sys.stderr)
 Sd, ms_d, k_d = run("digits")
 nacc = sobol._nacc(D, c2)
 ops = 2.0 * (R + 1) * N * nacc * a.digits          # +1: the point estimate runs the same GEMM over one row of ones
