@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--first-order-only", action="store_true")
     ap.add_argument("--algo", default="auto", help="analyze engine of the measured arm: auto | digits | fp64")
     ap.add_argument("--no-fp64-leg", action="store_true", help="skip the extra FP64-engine measurement")
+    ap.add_argument("--shard", default="auto", choices=["auto", "rows", "resamples"],
+                    help="multi-GPU decomposition of analyze: base-row ranges (all-reduce of partial sums; what "
+                         "the integer engine scales with) or resample ids (all-gather of estimates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample", action="store_true", help="skip the 70 GB sample-generation leg")
     ap.add_argument("--ref-log2n", type=int, default=10, help="bounded sample of the reference arm")
@@ -276,7 +279,10 @@ def main():
     Ypart = rt.empty((step_rows * (hi - lo),), torch.float64)
     t_eval = timed(lambda: Sobol_G.evaluate_sample(plan, first + lo, hi - lo, a=avec, out=Ypart, check=False),
                    a.steps, a.warmup)
-    if world > 1:
+    # multi-GPU analyze: by base-row range for the integer engine (features, multiplicities and GEMM all shrink
+    # with the shard; one all-reduce of [R, SA_NACC] partial sums), by resample id for the FP64 engines
+    row_mode = world > 1 and (a.shard == "rows" or (a.shard == "auto" and a.algo in ("auto", "digits")))
+    if world > 1 and not row_mode:
         sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0]) for g in range(world)]
         parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
         dist.all_gather(parts, Ypart)
@@ -293,7 +299,16 @@ def main():
         accumulate launches covered per step, launches in the timed region, last result, clocks)."""
         events = []
 
+        rows_mode = row_mode and algo != "fp64"
+
         def analyze_step():
+            if rows_mode:
+                return analyze_sobol.analyze_row_sharded(problem, [(lo, Yd)], N, calc_second_order=c2,
+                                                         num_resamples=R, seed=100, resample="philox",
+                                                         kernel_events=events, algo=algo)
+            if row_mode:    # FP64 leg of a row-sharded run: every rank needs all of Y
+                return analyze_sobol.analyze_device(problem, full_y(), calc_second_order=c2, num_resamples=R,
+                                                    seed=100, resample="philox", kernel_events=events, algo=algo)
             return analyze_sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100,
                                                 resample="philox", kernel_events=events, algo=algo)
 
@@ -311,8 +326,19 @@ def main():
         timed_events = list(events)
         S_ = analyze_step()
         ms = max_over_ranks(sum(e0.elapsed_time(e1) for _, e0, e1 in timed_events)) / steps
-        rows = sum(c for c, _, _ in timed_events) * N / steps
+        rows = sum(c for c, _, _ in timed_events) * ((hi - lo) if rows_mode else N) / steps
         return t / steps, ms, rows, n_launch, S_, clk
+
+    _full = []
+
+    def full_y():
+        if not _full:
+            sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0])
+                     for g in range(world)]
+            parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
+            dist.all_gather(parts, Ypart)
+            _full.append(torch.cat(parts))
+        return _full[0]
 
     t_step, k_ms, k_rows, launches, S, clocks = measure(a.algo, a.steps, a.warmup, True)
     t_an = t_step * a.steps
@@ -417,13 +443,16 @@ def main():
     torch.cuda.synchronize()
 
     def e2e_step():
+        if row_mode:   # every rank uploads only its own base-row range
+            return analyze_sobol.analyze_row_sharded(problem, [(lo, Yh)], N, calc_second_order=c2, num_resamples=R,
+                                                     seed=100, resample="philox", algo=a.algo)
         return analyze_sobol.analyze_device(problem, Yh, calc_second_order=c2, num_resamples=R, seed=100,
                                             resample="philox", algo=a.algo)
 
     t_e2e = timed(e2e_step, a.steps, 1)
     nest = analyze_sobol._nest(D, c2)
     e2e = {"value": N * R * a.steps / t_e2e, "unit": "resample-rows/s", "analyze_s": t_e2e / a.steps,
-           "h2d_bytes_per_step": int(Yh.numel() * 8), "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4)}
+           "h2d_bytes_per_step": int(Yh.numel() * 8) * (world if row_mode else 1), "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4)}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -445,7 +474,8 @@ def main():
             "dtype": "f64 (sums: exact u8 x s8 -> s32 digit GEMM)" if engine == "digits" else "f64",
             "data": "synthetic", "engine": engine,
             "config": {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
-                       "skip_values": skip, "resample": "philox seed 100", "parallelism": f"resample-id x{world}",
+                       "skip_values": skip, "resample": "philox seed 100", "parallelism": (f"base-row range x{world} (all-reduce of partial sums)" if row_mode
+                                       else f"resample-id x{world}"),
                        "l2": f"Y is {Yd.numel() * 8 / 1e6:.0f} MB (> 126 MB L2), no explicit flush"
                        if Yd.numel() * 8 > 126e6 else "Y fits L2 (resident by design)"},
             "sample": sample, "fused_sample_eval": fused, "roofline": roofline, "fp64_engine": fp64_leg,

@@ -492,6 +492,7 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     S.problem = problem
     S.to_df = MethodType(to_df, S)
     S.rows_here = rows_here
+    S.engine = ENGINE_NAMES[lead.kind]
     return S
 
 
