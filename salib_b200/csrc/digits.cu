@@ -600,6 +600,7 @@ static int choose_ksplit(uint64_t count, uint64_t ncols, uint64_t K, int bm, int
   const uint64_t ksteps = ceil_div_u64(K, BK);
   const uint64_t want = 2 * (uint64_t)sm_count();
   uint64_t ks = tiles >= want ? 1 : ceil_div_u64(want, tiles);
+  if (const char *e = getenv("SALIB_B200_DIGIT_KSPLIT")) ks = (uint64_t)atoi(e) > ks ? (uint64_t)atoi(e) : ks;
   const uint64_t cap = ksteps / 8 ? ksteps / 8 : 1;
   if (ks > cap) ks = cap;
   const uint64_t per = ceil_div_u64(ksteps, ks);

@@ -134,6 +134,45 @@ def test_digits_engine_matches_fp64_engine_philox():
     _cmp(b, a, D, True, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("Dg,N,c2,S", [(3, 1000, True, 7), (8, 517, False, 6), (16, 300, True, 7), (5, 4096, True, 8),
+                                         (64, 130, True, 7)])
+def test_digit_matrix_and_sums_match_the_oracle_bit_for_bit(Dg, N, c2, S):
+    """Device digit columns == oracle digits (int8, every byte); device sums == the oracle's exact integer sums
+    (Python integers, one rounding).  Y has a wide dynamic range so that columns get very different scales."""
+    import torch
+    from oracle import digits as o_digits
+    from salib_b200 import _lib, _runtime as rt
+    from salib_b200.analyze import sobol
+
+    rng = np.random.default_rng(Dg * 1000 + N)
+    step = 2 * Dg + 2 if c2 else Dg + 2
+    Y = rng.normal(size=(N, step)) * np.exp(rng.normal(size=(1, step)) * 2.0) + rng.normal(size=(1, step))
+    Y = Y.reshape(-1)
+    eng = sobol.SobolAnalyzer(Dg, N, c2, algo="digits")
+    eng.ndigits = S
+    Yd = rt.to_device(Y, torch.float64)
+    eng.load(Yd)
+    stats = eng.stats.cpu().numpy()
+    F = o_digits.features(Y, Dg, c2, stats[0], stats[1])
+    dig, inv, _ = o_digits.split(F, S)
+    pitch = int(_lib.lib().sa_digit_row_pitch(N))
+    Q = eng.Q.cpu().numpy().reshape(eng.nacc * S, pitch)
+    assert np.array_equal(Q[:, :N], dig)
+    assert not Q[:, N:].any()
+    assert np.array_equal(eng.inv.cpu().numpy(), inv)
+
+    count = 37
+    w = rng.multinomial(N, np.full(N, 1.0 / N), size=count).astype(np.uint8)
+    w[0, :] = 0
+    w[0, 0] = 200                                                   # a heavy row: multiplicities beyond 127
+    wd = torch.zeros((count, eng.Npad), dtype=torch.uint8, device="cuda")
+    wd[:, :N] = torch.from_numpy(w).cuda()
+    psum, nsplit = eng._partial_sums(wd.reshape(-1), count)
+    assert nsplit == 1
+    got = psum.cpu().numpy().reshape(count, eng.nacc)
+    assert np.array_equal(got, o_digits.sums(w, dig, inv, S))
+
+
 def test_digits_invariances_d64():
     """The properties tests/test_gpu_properties.py checks for the FP64 engines, for the integer engine at
     D = 64, N = 2^16: "auto" picks it at this size and agrees with the FP64 engines; affine invariance; resample

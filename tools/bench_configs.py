@@ -103,6 +103,7 @@ def cfg2():
     Vi = 1.0 / (3.0 * (1.0 + np.array([0, 1, 4.5, 9, 99, 99, 99, 99.0])) ** 2)
     var = np.prod(1 + Vi) - 1
     print(json.dumps({"config": "cfg2 G-function D=8 N=2^20 first+total order R=1000 (Y resident, philox)",
+                      "engine": getattr(S, "engine", None),
                       "analyze_s": t, "resample_rows_per_s": N * R / t, "accumulate_kernel_s": k_s,
                       "roofline": {"bound": "l2", "achieved": gather_bytes / k_s / 1e9, "peak": l2, "unit": "GB/s",
                                    "frac": gather_bytes / k_s / 1e9 / l2,

@@ -89,7 +89,7 @@ out["digits_ms"] = ms_d
 out["digits_accumulate_ms"] = k_d
 out["digits_int8_TOPS"] = ops / (k_d / 1e3) / 1e12
 if not a.skip_fp64:
-    Sf, ms_f, k_f = run("auto")
+    Sf, ms_f, k_f = run("fp64")
     out["fp64_ms"] = ms_f
     out["fp64_accumulate_ms"] = k_f
     out["speedup"] = ms_f / ms_d
