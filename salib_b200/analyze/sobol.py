@@ -326,7 +326,32 @@ class SobolAnalyzer:
         return out
 
 
-def bootstrap_shared(engines, resampler, lo, hi):
+class _CountsPrefetch:
+    """Multiplicities of the first resample batch, drawn on a side stream while the main stream is still busy
+    with Y (host-to-device copy, moments, feature kernels): they depend on the seed only, not on Y."""
+
+    def __init__(self, resampler, batch, targets):
+        """batch = (c0, c1); targets = [(row pitch, (row0, nrows) or None)]: one buffer per row shard."""
+        self.c0, self.n = batch[0], batch[1] - batch[0]
+        self.ws = [rt.empty((self.n * npad,), torch.uint8) for npad, _ in targets]
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)          # the cached blocks may still be read by earlier work on the main stream
+        with torch.cuda.stream(side):
+            for w, (_, rows) in zip(self.ws, targets):
+                resampler.counts(self.c0, self.n, w, rows=rows)
+            self.done = torch.cuda.Event()
+            self.done.record(side)
+
+    def take(self, c0, n):
+        """The buffers if they hold exactly batch [c0, c0+n), after making the current stream wait for them."""
+        if (c0, n) != (self.c0, self.n):
+            return None
+        torch.cuda.current_stream().wait_event(self.done)
+        return self.ws
+
+
+def bootstrap_shared(engines, resampler, lo, hi, prefetch=None):
     """Estimates of resamples [lo, hi) for several model outputs of the same design (same N, Dg, order):
     the multiplicities of each batch are built once and every output's rows are accumulated against them."""
     lead = engines[0]
@@ -334,11 +359,17 @@ def bootstrap_shared(engines, resampler, lo, hi):
     w = None
     for c0, c1 in lead._batches(lo, hi):
         n = c1 - c0
-        if w is None or w.numel() < n * lead.Npad:
-            w = rt.empty((n * lead.Npad,), torch.uint8)
-        resampler.counts(c0, n, w)
+        ready = prefetch.take(c0, n) if prefetch is not None else None
+        if ready is not None:
+            w = ready[0]
+        else:
+            if w is None or w.numel() < n * lead.Npad:
+                w = rt.empty((n * lead.Npad,), torch.uint8)
+            resampler.counts(c0, n, w)
         for e, est in zip(engines, ests):
             e._accumulate(w, n, est[c0 - lo:c1 - lo])
+    if prefetch is not None:
+        torch.cuda.current_stream().wait_event(prefetch.done)   # never leave the side stream unjoined
     return ests
 
 
@@ -424,19 +455,10 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
                             resamples=np.shape(r)[1] if r is not None else num_resamples)
         eng.kernel_events = kernel_events
         eng.row0 = int(row0)
-        Yd = rt.to_device(Y, torch.float64).reshape(-1)
-        eng.moments(Yd)
-        engines.append((eng, Yd))
-        local.append((float(size), eng.stats.cpu().numpy().copy()))
-    rows_here = sum(e.N for e, _ in engines)
-    parts = allgather_moments(local, world)
-    if int(round(sum(c for c, _ in parts))) != N * step:
-        raise RuntimeError(f"row shards hold {int(sum(c for c, _ in parts)) // step} base rows, expected {N}")
-    stats = combine_moments(parts)
-    for eng, Yd in engines:
-        eng.load(Yd, stats=stats)
-    engines = [e for e, _ in engines]
+        engines.append(eng)
+    rows_here = sum(e.N for e in engines)
     lead = engines[0]
+    big = max(engines, key=lambda e: e.Npad)
     Z = norm.ppf(0.5 + conf_level / 2)
 
     if r is not None:
@@ -447,6 +469,24 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     else:
         R = int(num_resamples)
         rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
+    # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of the shards
+    prefetch = None
+    if R > 0 and rs.mode == "philox":
+        prefetch = _CountsPrefetch(rs, big._batches(0, R)[0], [(e.Npad, (e.row0, e.N)) for e in engines])
+
+    loaded = []
+    for eng, (_, Y) in zip(engines, shards):
+        Yd = rt.to_device(Y, torch.float64).reshape(-1)
+        eng.moments(Yd)
+        loaded.append(Yd)
+        local.append((float(Yd.numel()), eng.stats.cpu().numpy().copy()))
+    parts = allgather_moments(local, world)
+    if int(round(sum(c for c, _ in parts))) != N * step:
+        raise RuntimeError(f"row shards hold {int(sum(c for c, _ in parts)) // step} base rows, expected {N}")
+    stats = combine_moments(parts)
+    for eng, Yd in zip(engines, loaded):
+        eng.load(Yd, stats=stats)
+    del loaded
 
     def totals(ws, count, est_out):
         tot = rt.zeros((count * lead.nacc,), torch.float64)
@@ -465,17 +505,22 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     est = None
     if R > 0:
         est = rt.empty((R, lead.nest), torch.float64)
-        big = max(engines, key=lambda e: e.Npad)
         wbuf = {}
         for c0, c1 in big._batches(0, R):
             n = c1 - c0
-            ws = []
-            for i, eng in enumerate(engines):
-                if i not in wbuf or wbuf[i].numel() < n * eng.Npad:
-                    wbuf[i] = rt.empty((n * eng.Npad,), torch.uint8)
-                rs.counts(c0, n, wbuf[i], rows=(eng.row0, eng.N))
-                ws.append(wbuf[i])
+            ws = prefetch.take(c0, n) if prefetch is not None else None
+            if ws is not None:
+                wbuf = dict(enumerate(ws))
+            else:
+                ws = []
+                for i, eng in enumerate(engines):
+                    if i not in wbuf or wbuf[i].numel() < n * eng.Npad:
+                        wbuf[i] = rt.empty((n * eng.Npad,), torch.uint8)
+                    rs.counts(c0, n, wbuf[i], rows=(eng.row0, eng.N))
+                    ws.append(wbuf[i])
             totals(ws, n, est[c0:c1])
+        if prefetch is not None:
+            torch.cuda.current_stream().wait_event(prefetch.done)
         conf = lead.conf(est, Z)
         rs.check()
     else:
@@ -559,9 +604,6 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo,
                             resamples=np.shape(r)[1] if r is not None else num_resamples)
         eng.kernel_events = kernel_events
-        # multi-GPU: a host Y is uploaded as one shard per rank and all-gathered over NVLink
-        Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
-        eng.load(Yd.reshape(-1))
         engines.append(eng)
     Z = norm.ppf(0.5 + conf_level / 2)
 
@@ -573,13 +615,22 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
     else:
         R = int(num_resamples)
         rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
+    rank, world = rt.world() if distributed else (0, 1)
+    lo, hi = rt.shard_range(R, rank, world)
+    # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of Y
+    prefetch = None
+    if hi > lo and rs.mode == "philox":
+        prefetch = _CountsPrefetch(rs, engines[0]._batches(lo, hi)[0], [(engines[0].Npad, None)])
+
+    for eng, Y in zip(engines, Ys):
+        # multi-GPU: a host Y is uploaded as one shard per rank and all-gathered over NVLink
+        Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
+        eng.load(Yd.reshape(-1))
 
     points = [eng.point() for eng in engines]
-    rank, world = rt.world() if distributed else (0, 1)
     ests = [None] * len(engines)
     if R > 0:
-        lo, hi = rt.shard_range(R, rank, world)
-        ests = bootstrap_shared(engines, rs, lo, hi)
+        ests = bootstrap_shared(engines, rs, lo, hi, prefetch)
         if world > 1:
             ests = [allgather_estimates(e, R, rank, world) for e in ests]
         confs = [eng.conf(e, Z) for eng, e in zip(engines, ests)]
