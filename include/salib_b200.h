@@ -215,14 +215,16 @@ int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, 
  * recombined in 128-bit integers and rounded to float64 once.  Never selected automatically (BASELINE's
  * north star rules tensor cores out for the default path); Python: analyze_device(..., algo="digits").
  *   sa_digit_row_pitch(N)   bytes of one digit column (rows of Y padded to 128)
- *   sa_digit_features_i8    d_Y [N*step] reference order + d_stats -> d_Q [nfeat*ndigits][pitch] int8,
- *                           column q*ndigits+s = digit s of feature q, K-major; d_inv [nfeat] = the power of
- *                           two that maps the integer sums back.  nfeat = SA_NACC(Dg, second_order).
+ *   sa_digit_features_i8    d_Y [N*step] reference order + d_stats -> d_Q int8, nfeat*ndigits columns (column
+ *                           q*ndigits+s = digit s of feature q) of sa_digit_row_pitch(N) rows, stored K-blocked:
+ *                           d_Q[i / 128][column][i % 128]; d_inv [nfeat] = the power of two that maps the
+ *                           integer sums back.  nfeat = SA_NACC(Dg, second_order).
  *   sa_digit_sums_f64       d_psum [count][nfeat] (the nsplit = 1 layout sa_sobol_finalize_f64 reads) from
  *                           d_w [count][w_pitch] uint8 multiplicities; workspace = int32 digit sums
  *                           [ksplit][count][ldc], ksplit = sa_digit_ksplit(...), ldc = sa_digit_ldc(...).
  *   sa_digit_gemm_i32       the GEMM alone (tests): d_C[ks][count][ldc] = d_w [count][K] * d_Q[ncols][K]^T over
- *                           the ks-th of `ksplit` ranges of K.                                              */
+ *                           the ks-th of `ksplit` ranges of K; d_Q row-major with pitch q_pitch, or K-blocked
+ *                           as above when q_pitch == 0.                                                     */
 uint64_t sa_digit_row_pitch(uint64_t N);
 uint64_t sa_digit_ldc(int nfeat, int ndigits);
 int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count);

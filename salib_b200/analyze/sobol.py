@@ -64,6 +64,7 @@ DIGITS = int(os.environ.get("SALIB_B200_DIGITS", "7"))   # radix-256 digits per 
 ENGINE_NAMES = {1: "fp64-generic", 3: "fp64-gemv", 4: "fp64-tile8", 5: "fp64-dmma", 6: "digits"}
 DIGITS_MIN_WORK = 1 << 31
 DIGITS_MAX_BYTES = 80 << 30
+DIGITS_MAX_FEATURES = 20000           # the per-feature maxima live in shared memory (Dg <= 198 with second order)
 PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
@@ -216,7 +217,7 @@ class SobolAnalyzer:
     def _digits_pays(self, resamples):
         q_bytes = self.nacc * self.ndigits * int(_lib.lib().sa_digit_row_pitch(self.N))
         return (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.N <= 1 << 24
-                and q_bytes <= DIGITS_MAX_BYTES and self.step <= 2048)
+                and q_bytes <= DIGITS_MAX_BYTES and self.nacc <= DIGITS_MAX_FEATURES)
 
     def _set_kind(self, kind):
         self.kind = kind

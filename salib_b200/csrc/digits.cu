@@ -18,7 +18,8 @@
 //
 // Kernels
 //   feature_table_kernel / feature_max_kernel / feature_scale_kernel / digit_split_kernel
-//       Y -> Q[nfeat*S][Kp] int8, K-major (rows of Y contiguous), column q*S+s = digit s of feature q
+//       Y -> Q int8, K-major, column q*S+s = digit s of feature q, stored K-blocked [Kp/128][nfeat*S][128]:
+//       128 consecutive rows of Y of all columns are contiguous (streaming writes, contiguous TMA boxes)
 //   digit_gemm_kernel     C[ks][count][ldc] int32 = W[count][K] (u8) * Q[ncols][K]^T (s8) per K split
 //       warp 0: TMA producer (128-byte-swizzled 128 x 128 B and BN x 128 B boxes, STAGES-deep mbarrier ring)
 //       warp 1: allocates TMEM, one lane issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=BN, K=32)
@@ -66,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1, int32_t c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // Arrives on `bar` once every tcgen05.mma this thread has issued so far has completed.
@@ -99,7 +107,8 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 digit_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
                   int32_t *__restrict__ C, uint32_t count, uint32_t ldc, uint32_t tiles_m, uint32_t tiles_n,
-                  uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band) {
+                  uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band, uint32_t q_blocked) {
+  // q_blocked: Q is stored [K / 128][ncols][128] (tmQ is 3-D) instead of [ncols][pitch]
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_sh;
@@ -151,7 +160,8 @@ digit_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_arrive_expect_tx(full(s), kABytes + kBBytes);
         const int32_t kbyte = (int32_t)((k0 + i) * BK);
         tma_load_2d(sA(s), &tmW, kbyte, (int32_t)(tile_m * BM), full(s));
-        tma_load_2d(sB(s), &tmQ, kbyte, (int32_t)(tile_n * BN), full(s));
+        if (q_blocked) tma_load_3d(sB(s), &tmQ, 0, (int32_t)(tile_n * BN), (int32_t)(k0 + i), full(s));
+        else tma_load_2d(sB(s), &tmQ, kbyte, (int32_t)(tile_n * BN), full(s));
       }
     }
     __syncwarp();
@@ -243,6 +253,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1,
+                                                 int32_t c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar & 0xFEFFFFFFu)
+      : "memory");
+}
 // Arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed.
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile(
@@ -263,7 +281,8 @@ template <int NACC, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
                        int32_t *__restrict__ C, uint32_t count, uint32_t ldc, uint32_t tiles_m, uint32_t tiles_n,
-                       uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band, uint32_t no_reload) {
+                       uint32_t ksteps, uint32_t ksteps_per_split, uint32_t band, uint32_t no_reload,
+                       uint32_t q_blocked) {
   // no_reload (sa_microbench_i8_tensor only): the ring is filled once and the MMAs keep re-reading it -- the
   // tensor-core rate of this instruction mix with no operand traffic, i.e. the roofline denominator.
   constexpr uint32_t PM = 256, PN = 256 * NACC;          // pair tile
@@ -322,8 +341,11 @@ digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
         const int32_t kbyte = (int32_t)((k0 + i) * BK);
         tma_load_2d_pair(sA(s), &tmW, kbyte, wrow, full(s));
 #pragma unroll
-        for (uint32_t j = 0; j < NACC; ++j)  // accumulator j: columns [j*256, j*256+256) of the pair tile, half each
-          tma_load_2d_pair(sB(s) + j * 128 * BK, &tmQ, kbyte, (int32_t)(tile_n * PN + j * 256 + rank * 128), full(s));
+        for (uint32_t j = 0; j < NACC; ++j) {  // accumulator j: columns [j*256, j*256+256) of the pair tile, half each
+          const int32_t col = (int32_t)(tile_n * PN + j * 256 + rank * 128);
+          if (q_blocked) tma_load_3d_pair(sB(s) + j * 128 * BK, &tmQ, 0, col, (int32_t)(k0 + i), full(s));
+          else tma_load_2d_pair(sB(s) + j * 128 * BK, &tmQ, kbyte, col, full(s));
+        }
       }
     }
     __syncwarp();
@@ -426,14 +448,18 @@ __device__ __forceinline__ double feature_value(const FeatDesc d, X x) {
   return __dmul_rn(t, t);
 }
 
-// Normalised rows [i0, i0 + rows) of Y -> xs[col * pitch + r] (column-major in shared memory); rows >= N are 0.
+// Normalised rows [i0, i0 + rows) of Y -> xs[col * pitch + slot(r)] (column-major in shared memory); rows >= N
+// are 0.  INTERLEAVE: slot(r) = (r % 4) * (rows / 4) + r / 4, so that lanes which own 4 consecutive rows each
+// read consecutive doubles for a given r % 4 (a plain row order would make those reads 4-way bank conflicts).
+template <bool INTERLEAVE>
 __device__ __forceinline__ void load_tile(const double *__restrict__ Y, uint64_t N, int step, uint64_t i0, int rows,
                                           int pitch, double mean, double sd, double *xs) {
   const int total = rows * step;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
     const int r = e / step, c = e - r * step;
     const uint64_t i = i0 + r;
-    xs[c * pitch + r] = i < N ? __ddiv_rn(__dsub_rn(Y[i * (uint64_t)step + c], mean), sd) : 0.0;
+    const int slot = INTERLEAVE ? (r & 3) * (rows >> 2) + (r >> 2) : r;
+    xs[c * pitch + slot] = i < N ? __ddiv_rn(__dsub_rn(Y[i * (uint64_t)step + c], mean), sd) : 0.0;
   }
 }
 
@@ -450,7 +476,7 @@ feature_max_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat
   const uint64_t tiles = ceil_div_u64(N, tile_rows);
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
-    load_tile(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
+    load_tile<false>(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
     __syncthreads();
     for (int q = threadIdx.x; q < nfeat; q += blockDim.x) {
       const FeatDesc d = tab[q];
@@ -478,8 +504,8 @@ feature_scale_kernel(const unsigned long long *__restrict__ fmax, int nfeat, int
   inv[q] = ldexp(1.0, e - bits);
 }
 
-// Q[(q*S + s) * Kp + i] = digit s of rint(F[i][q] * scale[q]).  Blocks take tiles of TR rows; LPF = TR/4 lanes
-// share a feature (4 consecutive rows each -> one 32-bit store per digit, TR contiguous bytes per column).
+// Q[i / 128][q*S + s][i % 128] = digit s of rint(F[i][q] * scale[q]).  Blocks take tiles of TR rows; LPF = TR/4
+// lanes share a feature (4 consecutive rows each -> one 32-bit store per digit, TR contiguous bytes per column).
 template <int S>
 __global__ void __launch_bounds__(256)
 digit_split_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat, const FeatDesc *__restrict__ tab,
@@ -495,29 +521,49 @@ digit_split_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat
   const uint64_t tiles = Kp / tile_rows;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
-    load_tile(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
+    load_tile<true>(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
     __syncthreads();
     for (int q = warp * fpw + fsel; q < nfeat; q += nwarps * fpw) {
       const FeatDesc d = tab[q];
       const double sc = scale[q];
-      uint32_t packed[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) packed[s] = 0;
+      // Balanced digits without a carry chain: with u_s = d_s + 128 in [0, 255],  t + sum_s 128 * 256^s =
+      // sum_s u_s * 256^s  is the plain base-256 form of a non-negative number below 256^S (|t| < 2^(8S-2)),
+      // and d_s as an int8 bit pattern is u_s with the top bit flipped.  One add and one xor per value give all
+      // digits; a 4 x 4 byte transpose (PRMT) per 32-bit half packs the four rows of each digit into a word.
+      constexpr unsigned long long kBias = 0x8080808080808080ull >> (8 * (8 - S));
+      uint32_t lo[4], hi[4];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        const int r = 4 * sub + rr;
-        const double f = feature_value(d, [&](int c) { return xs[c * pitch + r]; });
-        long long t = __double2ll_rn(__dmul_rn(f, sc));
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const long long dgt = (long long)(int8_t)(t & 0xff);
-          packed[s] |= ((uint32_t)dgt & 0xffu) << (8 * rr);
-          t = (t - dgt) >> 8;
-        }
+        const int slot = rr * lpf + sub;  // row 4 * sub + rr of the tile
+        const double f = feature_value(d, [&](int c) { return xs[c * pitch + slot]; });
+        const unsigned long long u =
+            ((unsigned long long)__double2ll_rn(__dmul_rn(f, sc)) + kBias) ^ 0x8080808080808080ull;
+        lo[rr] = (uint32_t)u;
+        hi[rr] = (uint32_t)(u >> 32);
       }
-      int8_t *dst = Q + (uint64_t)q * S * Kp + tile * tile_rows + 4 * sub;
+      uint32_t packed[8];
+      {
+        const uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[0], lo[1], 0x7362);
+        const uint32_t c = __byte_perm(lo[2], lo[3], 0x5140), e = __byte_perm(lo[2], lo[3], 0x7362);
+        packed[0] = __byte_perm(a, c, 0x5410);
+        packed[1] = __byte_perm(a, c, 0x7632);
+        packed[2] = __byte_perm(b, e, 0x5410);
+        packed[3] = __byte_perm(b, e, 0x7632);
+      }
+      if (S > 4) {
+        const uint32_t a = __byte_perm(hi[0], hi[1], 0x5140), b = __byte_perm(hi[0], hi[1], 0x7362);
+        const uint32_t c = __byte_perm(hi[2], hi[3], 0x5140), e = __byte_perm(hi[2], hi[3], 0x7362);
+        packed[4] = __byte_perm(a, c, 0x5410);
+        packed[5] = __byte_perm(a, c, 0x7632);
+        packed[6] = __byte_perm(b, e, 0x5410);
+        packed[7] = __byte_perm(b, e, 0x7632);
+      }
+      // K-blocked layout: block kb = 128 consecutive rows of Y holds [ncols][128] bytes contiguously, so a tile's
+      // digits form one streaming write (and one GEMM operand box = 128 columns x 128 bytes is contiguous too)
+      const uint64_t row0 = tile * tile_rows;
+      int8_t *dst = Q + ((row0 >> 7) * ((uint64_t)nfeat * S) + (uint64_t)q * S) * 128 + (row0 & 127) + 4 * sub;
 #pragma unroll
-      for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t *>(dst + (uint64_t)s * Kp) = packed[s];
+      for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t *>(dst + s * 128) = packed[s];
     }
   }
 }
@@ -592,6 +638,21 @@ static int make_map(CUtensorMap *map, const void *base, uint64_t K, uint64_t row
   return SA_OK;
 }
 
+// K-blocked byte matrix [nkb][cols][128]: boxes of box_cols x 128 bytes of one block, zero fill beyond `cols`.
+static int make_map_blocked(CUtensorMap *map, const void *base, uint64_t cols, uint64_t nkb, int box_cols) {
+  EncodeTiledFn fn = encode_tiled();
+  SA_REQUIRE(fn, SA_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)BK, cols, nkb};
+  const cuuint64_t strides[2] = {(cuuint64_t)BK, cols * BK};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_cols, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SA_REQUIRE(r == CUDA_SUCCESS, SA_ERR_ARG, "cuTensorMapEncodeTiled (blocked) failed with CUresult %d", (int)r);
+  return SA_OK;
+}
+
 static uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // K splits so that small launches still fill the GPU (at least ~2 blocks per SM, at least 8 K-steps each).
@@ -609,7 +670,7 @@ static int choose_ksplit(uint64_t count, uint64_t ncols, uint64_t K, int bm, int
 
 template <int BN, int STAGES>
 static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C, uint64_t count,
-                       uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit) {
+                       uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit, uint32_t q_blocked) {
   const uint64_t tm = ceil_div_u64(count, BM), tn = ceil_div_u64(ncols, BN);
   const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
   const uint64_t blocks = tm * tn * (uint64_t)ksplit;
@@ -618,7 +679,7 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap
   auto kern = digit_gemm_kernel<BN, STAGES>;
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, (uint32_t)tm,
-                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 16u);
+                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 16u, q_blocked);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -627,7 +688,7 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap
 template <int NACC, int STAGES>
 static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
                             uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
-                            uint32_t no_reload = 0) {
+                            uint32_t q_blocked, uint32_t no_reload = 0) {
   const uint64_t tm = ceil_div_u64(count, 256), tn = ceil_div_u64(ncols, 256 * NACC);
   const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
   const uint64_t blocks = 2 * tm * tn * (uint64_t)ksplit;
@@ -636,7 +697,7 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtens
   auto kern = digit_gemm_pair_kernel<NACC, STAGES>;
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, (uint32_t)tm,
-                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u, no_reload);
+                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u, no_reload, q_blocked);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -693,7 +754,8 @@ extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pi
   SA_REQUIRE(d_w && d_Q && d_C, SA_ERR_ARG, "sa_digit_gemm_i32: null pointer");
   SA_REQUIRE(count >= 1 && ncols >= 1 && K >= 1 && ksplit >= 1, SA_ERR_ARG, "sa_digit_gemm_i32: bad shape");
   SA_REQUIRE(K <= (1ull << 24), SA_ERR_UNSUPPORTED, "sa_digit_gemm_i32: more than 2^24 rows could overflow int32");
-  SA_REQUIRE(w_pitch % 16 == 0 && q_pitch % 16 == 0 && w_pitch >= K && q_pitch >= K, SA_ERR_ARG,
+  const uint32_t blocked = q_pitch == 0;  // Q stored [ceil(K / 128)][ncols][128]
+  SA_REQUIRE(w_pitch % 16 == 0 && w_pitch >= K && (blocked || (q_pitch % 16 == 0 && q_pitch >= K)), SA_ERR_ARG,
              "sa_digit_gemm_i32: row pitches must be multiples of 16 bytes and >= K");
   SA_REQUIRE(((uintptr_t)d_w & 15) == 0 && ((uintptr_t)d_Q & 15) == 0 && ((uintptr_t)d_C & 15) == 0, SA_ERR_ARG,
              "sa_digit_gemm_i32: pointers must be 16-byte aligned");
@@ -708,13 +770,14 @@ extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pi
   CUtensorMap mw, mq;
   int rc = make_map(&mw, d_w, K, count, w_pitch, BM);  // every variant loads W in boxes of 128 rows
   if (rc) return rc;
-  rc = make_map(&mq, d_Q, K, ncols, q_pitch, v == 1 ? 256 : 128);
+  rc = blocked ? make_map_blocked(&mq, d_Q, ncols, ceil_div_u64(K, BK), v == 1 ? 256 : 128)
+               : make_map(&mq, d_Q, K, ncols, q_pitch, v == 1 ? 256 : 128);
   if (rc) return rc;
   switch (v) {
-    case 0: return launch_gemm<128, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
-    case 1: return launch_gemm<256, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
-    case 2: return launch_gemm_pair<1, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
-    case 3: return launch_gemm_pair<2, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit);
+    case 0: return launch_gemm<128, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
+    case 1: return launch_gemm<256, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
+    case 2: return launch_gemm_pair<1, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
+    case 3: return launch_gemm_pair<2, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
   }
   SA_REQUIRE(false, SA_ERR_ARG, "sa_digit_gemm_i32: unknown kernel variant %d", v);
 }
@@ -777,7 +840,7 @@ extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *
   const uint64_t ncols = (uint64_t)nfeat * ndigits, ldc = sa_digit_ldc(nfeat, ndigits);
   const int ksplit = sa_digit_ksplit(N, nfeat, ndigits, count);
   int32_t *C = (int32_t *)d_work;
-  const int rc = sa_digit_gemm_i32(stream, d_w, w_pitch, count, d_Q, sa_digit_row_pitch(N), ncols, N, ksplit, C, ldc);
+  const int rc = sa_digit_gemm_i32(stream, d_w, w_pitch, count, d_Q, 0 /* K-blocked */, ncols, N, ksplit, C, ldc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t total = count * (uint64_t)nfeat;
@@ -807,7 +870,7 @@ extern "C" int sa_microbench_i8_tensor(void *stream, const uint8_t *d_w, const i
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(2 * pairs), kThreads, smem, (cudaStream_t)stream>>>(mw, mq, d_C, (uint32_t)(pairs * 256), 512u,
                                                                         (uint32_t)pairs, 1u, (uint32_t)ksteps,
-                                                                        (uint32_t)ksteps, 8u, 1u);
+                                                                        (uint32_t)ksteps, 8u, 1u, 0u);
   SA_LAUNCH_CHECK();
   *h_ops = 2.0 * 256 * 512 * 128 * (double)ksteps * (double)pairs;
   return SA_OK;

@@ -156,7 +156,8 @@ def test_digit_matrix_and_sums_match_the_oracle_bit_for_bit(Dg, N, c2, S):
     F = o_digits.features(Y, Dg, c2, stats[0], stats[1])
     dig, inv, _ = o_digits.split(F, S)
     pitch = int(_lib.lib().sa_digit_row_pitch(N))
-    Q = eng.Q.cpu().numpy().reshape(eng.nacc * S, pitch)
+    Q = eng.Q.cpu().numpy().reshape(pitch // 128, eng.nacc * S, 128)          # K-blocked [row block][column][128]
+    Q = Q.transpose(1, 0, 2).reshape(eng.nacc * S, pitch)
     assert np.array_equal(Q[:, :N], dig)
     assert not Q[:, N:].any()
     assert np.array_equal(eng.inv.cpu().numpy(), inv)
