@@ -404,7 +404,7 @@ def main():
                         "algorithmic flop of all N*R resample-rows"}
 
     if engine == "digits":
-        S_dig = analyze_sobol.DIGITS
+        S_dig = analyze_sobol.digits_for((hi - lo) if row_mode else N)
         ops_per_row = 2 * nacc * S_dig        # int8 multiply-adds x 2 per (resample, row)
         burst, sustained = i8_peak_tops()
         achieved = ops_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None

@@ -25,7 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dim", type=int, default=64)
 ap.add_argument("--log2n", type=int, default=20)
 ap.add_argument("--resamples", type=int, default=10000)
-ap.add_argument("--digits", type=int, default=7)
+ap.add_argument("--digits", type=int, default=0, help="0 = the library default (7)")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--skip-fp64", action="store_true")
 ap.add_argument("--first-order-only", action="store_true")
@@ -40,7 +40,8 @@ avec = np.resize(np.array([0, 1, 4.5, 9, 99, 99, 99, 99], dtype=np.float64), D)
 plan, first = sample_sobol._plan(problem, N, c2, False, N, None)
 Yd = rt.empty((step * N,), torch.float64)
 Sobol_G.evaluate_sample(plan, first, N, a=avec, out=Yd, check=False)
-sobol.DIGITS = a.digits
+sobol.DIGITS = a.digits or None
+a.digits = sobol.digits_for(N)
 
 
 def run(algo):
