@@ -344,13 +344,15 @@ class _CountsPrefetch:
     def __init__(self, resampler, batch, targets):
         """batch = (c0, c1); targets = [(row pitch, (row0, nrows) or None)]: one buffer per row shard."""
         self.c0, self.n = batch[0], batch[1] - batch[0]
-        self.ws = [rt.empty((self.n * npad,), torch.uint8) for npad, _ in targets]
+        # one spare row of ones behind the batch: the point estimate, if the engine takes it along (_ones_row)
+        self.ws = [rt.empty(((self.n + 1) * npad,), torch.uint8) for npad, _ in targets]
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(main)          # the cached blocks may still be read by earlier work on the main stream
         with torch.cuda.stream(side):
-            for w, (_, rows) in zip(self.ws, targets):
+            for w, (npad, rows) in zip(self.ws, targets):
                 resampler.counts(self.c0, self.n, w, rows=rows)
+                w[self.n * npad:].fill_(1)
             self.done = torch.cuda.Event()
             self.done.record(side)
 
@@ -362,11 +364,15 @@ class _CountsPrefetch:
         return self.ws
 
 
-def bootstrap_shared(engines, resampler, lo, hi, prefetch=None):
+def bootstrap_shared(engines, resampler, lo, hi, prefetch=None, points=None):
     """Estimates of resamples [lo, hi) for several model outputs of the same design (same N, Dg, order):
-    the multiplicities of each batch are built once and every output's rows are accumulated against them."""
+    the multiplicities of each batch are built once and every output's rows are accumulated against them.
+    ``points`` (an empty list): with the integer engine the point estimate -- one multiplicity row of ones --
+    rides in the first batch's GEMM instead of reading the digit matrix in a launch of its own; its
+    ``[1, nest]`` estimates are appended per engine (the list stays empty if that does not apply)."""
     lead = engines[0]
     ests = [rt.empty((hi - lo, e.nest), torch.float64) for e in engines]
+    fuse = points is not None and all(e.kind == 6 for e in engines)
     w = None
     for c0, c1 in lead._batches(lo, hi):
         n = c1 - c0
@@ -374,11 +380,20 @@ def bootstrap_shared(engines, resampler, lo, hi, prefetch=None):
         if ready is not None:
             w = ready[0]
         else:
-            if w is None or w.numel() < n * lead.Npad:
-                w = rt.empty((n * lead.Npad,), torch.uint8)
+            if w is None or w.numel() < (n + 1) * lead.Npad:
+                w = rt.empty(((n + 1) * lead.Npad,), torch.uint8)
             resampler.counts(c0, n, w)
+            if fuse:
+                w[n * lead.Npad:(n + 1) * lead.Npad].fill_(1)
         for e, est in zip(engines, ests):
-            e._accumulate(w, n, est[c0 - lo:c1 - lo])
+            if fuse:
+                ext = rt.empty((n + 1, e.nest), torch.float64)
+                e._accumulate(w, n + 1, ext)
+                est[c0 - lo:c1 - lo] = ext[:n]
+                points.append(ext[n:n + 1].clone())
+            else:
+                e._accumulate(w, n, est[c0 - lo:c1 - lo])
+        fuse = False
     if prefetch is not None:
         torch.cuda.current_stream().wait_event(prefetch.done)   # never leave the side stream unjoined
     return ests
@@ -512,7 +527,10 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         lead._finalize(tot, 1, count, N, est_out)
 
     point = rt.empty((1, lead.nest), torch.float64)
-    totals([None] * len(engines), 1, point)
+    # integer engine: the point estimate (a multiplicity row of ones) rides in the first batch's GEMM
+    fuse = R > 0 and all(e.kind == 6 for e in engines)
+    if not fuse:
+        totals([None] * len(engines), 1, point)
     est = None
     if R > 0:
         est = rt.empty((R, lead.nest), torch.float64)
@@ -525,11 +543,20 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
             else:
                 ws = []
                 for i, eng in enumerate(engines):
-                    if i not in wbuf or wbuf[i].numel() < n * eng.Npad:
-                        wbuf[i] = rt.empty((n * eng.Npad,), torch.uint8)
+                    if i not in wbuf or wbuf[i].numel() < (n + 1) * eng.Npad:
+                        wbuf[i] = rt.empty(((n + 1) * eng.Npad,), torch.uint8)
                     rs.counts(c0, n, wbuf[i], rows=(eng.row0, eng.N))
+                    if fuse:
+                        wbuf[i][n * eng.Npad:(n + 1) * eng.Npad].fill_(1)
                     ws.append(wbuf[i])
-            totals(ws, n, est[c0:c1])
+            if fuse:
+                ext = rt.empty((n + 1, lead.nest), torch.float64)
+                totals(ws, n + 1, ext)
+                est[c0:c1] = ext[:n]
+                point.copy_(ext[n:n + 1])
+                fuse = False
+            else:
+                totals(ws, n, est[c0:c1])
         if prefetch is not None:
             torch.cuda.current_stream().wait_event(prefetch.done)
         conf = lead.conf(est, Z)
@@ -638,10 +665,15 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
         eng.load(Yd.reshape(-1))
 
-    points = [eng.point() for eng in engines]
+    points = []
     ests = [None] * len(engines)
+    if hi > lo:
+        ests = bootstrap_shared(engines, rs, lo, hi, prefetch, points)
+    if not points:
+        points = [eng.point() for eng in engines]
     if R > 0:
-        ests = bootstrap_shared(engines, rs, lo, hi, prefetch)
+        if hi <= lo:
+            ests = bootstrap_shared(engines, rs, lo, hi, prefetch)
         if world > 1:
             ests = [allgather_estimates(e, R, rank, world) for e in ests]
         confs = [eng.conf(e, Z) for eng, e in zip(engines, ests)]
