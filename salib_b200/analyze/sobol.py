@@ -225,9 +225,19 @@ class SobolAnalyzer:
         return 4 if self.Dg <= 512 else 1
 
     def _digits_pays(self, resamples):
-        q_bytes = self.nacc * self.ndigits * int(_lib.lib().sa_digit_row_pitch(self.N))
-        return (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.N <= 1 << 24
-                and q_bytes <= DIGITS_MAX_BYTES and self.nacc <= DIGITS_MAX_FEATURES)
+        """"auto": is the integer engine applicable, worth it, and does its digit matrix fit next to the
+        multiplicity buffer in the memory this process can still get?"""
+        L = _lib.lib()
+        q_bytes = self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N))
+        if not (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.N <= 1 << 24
+                and q_bytes <= DIGITS_MAX_BYTES and self.nacc <= DIGITS_MAX_FEATURES):
+            return False
+        free, _ = torch.cuda.mem_get_info()
+        cached = torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        w_bytes = min(MAX_COUNT_BYTES, (max(resamples, 1) + 1) * int(L.sa_pad_rows(self.N)))
+        c_bytes = 4 * min(max(resamples, 1) + 1, MAX_COUNT_BYTES // int(L.sa_pad_rows(self.N)) + 1) \
+            * int(L.sa_digit_ldc(self.nacc, self.ndigits))
+        return q_bytes + w_bytes + c_bytes + (1 << 30) <= free + cached
 
     def _set_kind(self, kind):
         self.kind = kind

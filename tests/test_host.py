@@ -251,6 +251,25 @@ def test_work_decomposition_plans():
     assert plan_row_splits(4, 16, 100, sms, 11) == 3                  # never fewer than 32 rows per split
     assert plan_row_splits(3, 1000, 1 << 20, sms, 21) == 333             # 4 blocks of 256 resamples -> three waves of 3 per SM
     assert plan_row_splits(1, 1000, 4096, sms, 50) == 1
+    # integer engine (kind 6): one batch as large as the multiplicity buffer allows, in whole 128-resample tiles
+    assert plan_batches(6, 0, 10000, Npad, sms) == [(0, 10000)]
+    assert plan_batches(6, 3, 10000, Npad, sms, max_bytes=1000 * Npad) == \
+        [(3, 899), (899, 1795), (1795, 2691), (2691, 3587), (3587, 4483), (4483, 5379), (5379, 6275), (6275, 7171),
+         (7171, 8067), (8067, 8963), (8963, 9859), (9859, 10000)]
+    assert plan_batches(6, 0, 50, Npad, sms, max_bytes=10 * Npad) == [(0, 10), (10, 20), (20, 30), (30, 40), (40, 50)]
+    assert plan_batches(6, 7, 7, Npad, sms) == []
+
+
+def test_engine_selection_constants():
+    """Names and thresholds of the analyze engines (host logic; the selection itself needs a device)."""
+    from salib_b200.analyze import sobol as an
+
+    assert an._ALGO["auto"] == 0 and an._ALGO["fp64"] < 0 and an._ALGO["digits"] == 6
+    assert an.ENGINE_NAMES[6] == "digits" and an.ENGINE_NAMES[4] == "fp64-tile8"
+    assert an.digits_for(1 << 20) == 7 and an.digits_for(100) == 7
+    assert an._nacc(64, True) == 2149 and an._nest(64, True) == 2144
+    # the headline is far above the hand-over point, the README quick start far below
+    assert (1 << 20) * 10000 * an._nacc(64, True) >= an.DIGITS_MIN_WORK > 1024 * 100 * an._nacc(3, True)
 
 
 def test_read_param_file_and_cli_parsers(tmp_path):
