@@ -189,9 +189,12 @@ def plan_batches(kind, lo, hi, Npad, sms, max_bytes=None, groups=1):
 class SobolAnalyzer:
     """Device state of one ``analyze`` call; also usable directly with a device-resident Y."""
 
-    def __init__(self, Dg, N, calc_second_order, algo="auto", resamples=0):
+    def __init__(self, Dg, N, calc_second_order, algo="auto", resamples=0, total_rows=None):
+        """``total_rows``: base rows of the whole design when this engine holds one row shard of it (a resample
+        draws that many rows, which bounds the integer engine's int32 sums)."""
         rt.require_cuda()
         self.Dg, self.N, self.c2 = int(Dg), int(N), bool(calc_second_order)
+        self.total_rows = int(total_rows) if total_rows is not None else self.N
         self.step = 2 * Dg + 2 if self.c2 else Dg + 2
         self.nacc, self.nest = _nacc(Dg, self.c2), _nest(Dg, self.c2)
         self.algo = _ALGO[DEFAULT_ALGO if algo == "auto" else algo]
@@ -229,7 +232,8 @@ class SobolAnalyzer:
         multiplicity buffer in the memory this process can still get?"""
         L = _lib.lib()
         q_bytes = self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N))
-        if not (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.N <= 1 << 24
+        # |digit sum| <= 128 * (draws of one resample) must stay below 2^31
+        if not (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.total_rows <= 1 << 24
                 and q_bytes <= DIGITS_MAX_BYTES and self.nacc <= DIGITS_MAX_FEATURES):
             return False
         free, _ = torch.cuda.mem_get_info()
@@ -488,7 +492,9 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         if size % step or size == 0:
             raise RuntimeError("row shard size is not a multiple of the Saltelli block length")
         eng = SobolAnalyzer(Dg, size // step, c2, algo=algo,
-                            resamples=np.shape(r)[1] if r is not None else num_resamples)
+                            resamples=np.shape(r)[1] if r is not None else num_resamples, total_rows=N)
+        if eng.kind == 6 and N > 1 << 24:
+            raise ValueError("the integer engine is exact up to 2^24 base rows per resample; use algo='fp64'")
         eng.kernel_events = kernel_events
         eng.row0 = int(row0)
         engines.append(eng)
