@@ -55,10 +55,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// A barrier that never completes would hang the GPU: give up after ~10 s of polling and trap instead.
+// A barrier that never completes would hang the GPU: give up after 20 s (wall clock, %globaltimer) and trap.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 30)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 1023u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t c0, int32_t c1,
                                             uint32_t bar) {
