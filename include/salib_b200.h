@@ -225,6 +225,7 @@ int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, 
  *   sa_digit_gemm_i32       the GEMM alone (tests): d_C[ks][count][ldc] = d_w [count][K] * d_Q[ncols][K]^T over
  *                           the ks-th of `ksplit` ranges of K; d_Q row-major with pitch q_pitch, or K-blocked
  *                           as above when q_pitch == 0.                                                     */
+int sa_digit_available(void); /* 1: compute capability 10.x and cuTensorMapEncodeTiled exported by the driver */
 uint64_t sa_digit_row_pitch(uint64_t N);
 uint64_t sa_digit_ldc(int nfeat, int ndigits);
 int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count);

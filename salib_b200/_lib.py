@@ -56,6 +56,7 @@ SIGNATURES = {
     "sa_dgsm_features_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "sa_feature_sums_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _u64, _i32, _vp]),
     "sa_reduce_splits_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _dbl, _vp]),
+    "sa_digit_available": (C.c_int, []),
     "sa_digit_row_pitch": (_u64, [_u64]),
     "sa_digit_ldc": (_u64, [_i32, _i32]),
     "sa_digit_ksplit": (C.c_int, [_u64, _i32, _i32, _u64]),

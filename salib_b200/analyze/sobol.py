@@ -231,6 +231,8 @@ class SobolAnalyzer:
         """"auto": is the integer engine applicable, worth it, and does its digit matrix fit next to the
         multiplicity buffer in the memory this process can still get?"""
         L = _lib.lib()
+        if not L.sa_digit_available():
+            return False
         q_bytes = self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N))
         # |digit sum| <= 128 * (draws of one resample) must stay below 2^31
         if not (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.total_rows <= 1 << 24

@@ -738,6 +738,15 @@ static int feature_tile_rows(int step, int extra, size_t budget, int max_rows) {
 using namespace sa;
 using namespace sa::dg;
 
+// 1 if this process can run the integer engine: tcgen05/TMEM hardware (compute capability 10.x) and a driver
+// that exports cuTensorMapEncodeTiled.
+extern "C" int sa_digit_available(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 && encode_tiled() != nullptr;
+}
+
 extern "C" uint64_t sa_digit_row_pitch(uint64_t N) { return round_up(N, 128); }
 
 extern "C" uint64_t sa_digit_ldc(int nfeat, int ndigits) { return round_up((uint64_t)nfeat * ndigits, 32); }
