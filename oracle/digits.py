@@ -66,3 +66,48 @@ def sums(w, digits, inv, S):
                 v = v * 256 + int(acc[c, q * S + s])
             out[c, q] = float(v) * inv[q]      # int -> float is correctly rounded; the scaling is exact
     return out
+
+
+def estimates(psum, N, Dg, calc_second_order):
+    """Estimator algebra of analyze/sobol.py:219,232,242-246 on the weighted sums of one resample
+    (SA_NACC order) -> (S1 [Dg], ST [Dg], S2 [pairs] or None)."""
+    n = float(N)
+    m = (psum[0] + psum[1]) / (2.0 * n)
+    V = (psum[2] + psum[3]) / (2.0 * n) - m * m
+    S1 = (psum[5:5 + Dg] / n) / V
+    ST = 0.5 * (psum[5 + Dg:5 + 2 * Dg] / n) / V
+    S2 = None
+    if calc_second_order:
+        mab = psum[4] / n
+        pairs = [(j, k) for j in range(Dg) for k in range(j + 1, Dg)]
+        S2 = np.array([(psum[5 + 2 * Dg + p] / n - mab) / V - S1[j] - S1[k] for p, (j, k) in enumerate(pairs)])
+    return S1, ST, S2
+
+
+def analyze(Y, Dg, calc_second_order, r, conf_level=0.95, S=7):
+    """analyze/sobol.py:141-182 through the exact-integer route: normalise, split the features into digits, sum
+    them against the multiplicities of every column of the index matrix ``r`` (and a row of ones for the point
+    estimate) with integer arithmetic, apply the estimator algebra, Z * std(ddof=1) over the resamples."""
+    from scipy.stats import norm
+
+    Y = np.asarray(Y, dtype=np.float64)
+    step = 2 * Dg + 2 if calc_second_order else Dg + 2
+    N = Y.size // step
+    F = features(Y, Dg, calc_second_order, Y.mean(), Y.std())
+    dig, inv, _ = split(F, S)
+    R = r.shape[1]
+    w = np.stack([np.bincount(r[:, c], minlength=N) for c in range(R)] + [np.ones(N, dtype=np.int64)])
+    ps = sums(w, dig, inv, S)
+    est = [estimates(ps[c], N, Dg, calc_second_order) for c in range(R + 1)]
+    Z = norm.ppf(0.5 + conf_level / 2)
+    out = {"S1": est[R][0], "ST": est[R][1],
+           "S1_conf_all": np.array([e[0] for e in est[:R]]), "ST_conf_all": np.array([e[1] for e in est[:R]])}
+    out["S1_conf"] = Z * out["S1_conf_all"].std(ddof=1, axis=0)
+    out["ST_conf"] = Z * out["ST_conf_all"].std(ddof=1, axis=0)
+    if calc_second_order:
+        iu = np.triu_indices(Dg, 1)
+        out["S2"] = np.full((Dg, Dg), np.nan)
+        out["S2_conf"] = np.full((Dg, Dg), np.nan)
+        out["S2"][iu] = est[R][2]
+        out["S2_conf"][iu] = Z * np.array([e[2] for e in est[:R]]).std(ddof=1, axis=0)
+    return out
