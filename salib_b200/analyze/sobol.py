@@ -74,7 +74,9 @@ def digits_for(N):
 ENGINE_NAMES = {1: "fp64-generic", 3: "fp64-gemv", 4: "fp64-tile8", 5: "fp64-dmma", 6: "digits"}
 DIGITS_MIN_WORK = 1 << 31
 DIGITS_MAX_BYTES = 80 << 30
-DIGITS_MAX_FEATURES = 20000           # the per-feature maxima live in shared memory (Dg <= 198 with second order)
+# feature kernels: SA_NACC maxima + 9 doubles per model output of a base row must fit 200 KB of shared memory
+# (second order: Dg <= 205; first/total order only: Dg <= 2270)
+DIGITS_MAX_FEATURES = 25000
 PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
@@ -236,7 +238,7 @@ class SobolAnalyzer:
         q_bytes = self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N))
         # |digit sum| <= 128 * (draws of one resample) must stay below 2^31
         if not (self.N * max(resamples, 1) * self.nacc >= DIGITS_MIN_WORK and self.total_rows <= 1 << 24
-                and q_bytes <= DIGITS_MAX_BYTES and self.nacc <= DIGITS_MAX_FEATURES):
+                and q_bytes <= DIGITS_MAX_BYTES and self.nacc + 9 * self.step <= DIGITS_MAX_FEATURES):
             return False
         free, _ = torch.cuda.mem_get_info()
         cached = torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
@@ -281,7 +283,16 @@ class SobolAnalyzer:
             self.Yn = rt.zeros((self.N * self.stride + 16,), torch.float64)
             if self.kind in (4, 5):
                 self.Yt = rt.empty((2 * self.Npad,), torch.float64)
-        self.load_normalized(Yd)
+        try:
+            self.load_normalized(Yd)
+        except _lib.SalibB200Error:
+            if not self.auto_digits:
+                raise
+            # the integer engine refused the shape: "auto" continues with the FP64 engines
+            self.auto_digits = False
+            self._set_kind(self._fp64_kind())
+            self.Q = self.inv = None
+            return self.load(Yd, stats=self.stats.cpu().numpy())
 
     def load_normalized(self, Yd):
         """Re-run only the normalise/re-layout step with the current ``self.stats``."""
