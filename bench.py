@@ -418,7 +418,8 @@ def main():
         burst, sustained = i8_peak_tops()
         achieved = ops_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
         traffic = 436.6e9 if (c2 and D == 64 and a.log2n == 20 and R == 10000 and world == 1) else None
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TOP/s (int8)",
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                    "ops": "int8 tensor operations (u8 x s8 -> s32 multiply-add = 2), counted like flop",
                     "frac": (achieved / sustained) if achieved else None, "peak_burst": burst,
                     "traffic": traffic,
                     "traffic_source": "profiles/r01_digits_pair_gemm_ncu_summary.csv (dram read+write of the "
