@@ -229,6 +229,9 @@ int sa_digit_available(void); /* 1: compute capability 10.x and cuTensorMapEncod
 uint64_t sa_digit_row_pitch(uint64_t N);
 uint64_t sa_digit_ldc(int nfeat, int ndigits);
 int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count);
+/* work plan of the persistent CTA-pair GEMM (host logic only; tests): out[0..7] = pairs, full_waves, rem_tiles,
+ * rsplit, rper, band, epoch, slack */
+int sa_digit_pair_plan(uint64_t tiles_m, uint64_t tiles_n, uint64_t ksteps, int max_pairs, int band, uint32_t *out);
 size_t sa_digit_features_workspace_bytes(int nfeat);
 size_t sa_digit_sums_workspace_bytes(uint64_t N, int nfeat, int ndigits, uint64_t count);
 int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,

@@ -60,6 +60,7 @@ SIGNATURES = {
     "sa_digit_row_pitch": (_u64, [_u64]),
     "sa_digit_ldc": (_u64, [_i32, _i32]),
     "sa_digit_ksplit": (C.c_int, [_u64, _i32, _i32, _u64]),
+    "sa_digit_pair_plan": (C.c_int, [_u64, _u64, _u64, _i32, _i32, _vp]),
     "sa_digit_features_workspace_bytes": (_sz, [_i32]),
     "sa_digit_sums_workspace_bytes": (_sz, [_u64, _i32, _i32, _u64]),
     "sa_digit_features_i8": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _sz]),

@@ -411,6 +411,259 @@ digit_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// Persistent, K-synchronised CTA-pair kernel (the production kernel of the integer engine).
+//
+// Round-1 ncu of the one-tile-per-pair kernel above at the headline: 436 GB of DRAM reads for 26 GB of
+// operands (16x), L2 hit rate 47 % -- the 74 co-resident pairs share a band of W rows / Q columns but drift
+// apart in K, so each re-reads from HBM what a neighbour fetched a few hundred microseconds earlier; that
+// HBM power is what holds the SM clock (and with it the tensor pipe) at 1.3-1.4 GHz.  Here
+//   * P pairs (all that fit the GPU at once, cudaOccupancyMaxActiveClusters) stay resident and walk the tile
+//     list in WAVES: in wave w pair p owns tile w*P + p (band-major order, so a wave is ~band m-tiles x
+//     P/band n-tiles); ring, barriers and TMEM live across tiles, the epilogue of a tile (TMEM -> global,
+//     ~10 us of a ~6 ms tile) hands TMEM back through a `tmem_empty` barrier both CTAs' epilogue warps arrive
+//     on, while the producers already refill the ring for the next tile;
+//   * the leaders' producers keep the pairs of a wave within `slack` epochs of `epoch` K-steps of each other:
+//     at every epoch boundary a producer bumps a global counter and waits (bounded: it falls through after
+//     kSyncTimeoutNs and stops trying after kSyncStrikes time-outs, so correctness never depends on
+//     co-residency) until every pair has reached the boundary `slack` epochs back.  The operands of a wave's
+//     K-step (~0.85 MB) are then fetched from HBM once and served to all pairs from L2;
+//   * the tiles left over after the full waves are cut along K into `rsplit` chunks spread over all pairs
+//     (stream-K style remainder; int32 atomics into C, which the launcher zeroes for those tiles -- integer
+//     addition is associative, the result is bit-identical).  Small launches are all remainder.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned long long kSyncTimeoutNs = 200000ull;  // 0.2 ms per wait, ~30 tile K-steps
+constexpr int kSyncStrikes = 4;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct PairPlan {
+  uint32_t tiles_m, tiles_n, band;   // tile grid (pair tiles of 256 x PN), band of m-tiles swept over n
+  uint32_t ksteps;                   // K-steps (128 rows) of a whole tile
+  uint32_t pairs;                    // P: resident pairs = gridDim.x / 2
+  uint32_t full_waves;               // waves of P whole tiles
+  uint32_t rem_tiles, rsplit, rper;  // left-over tiles, K chunks per left-over tile, K-steps per chunk
+  uint32_t epoch, slack;             // K-sync: K-steps per epoch, epochs a pair may run ahead (0 = off)
+};
+
+template <int NACC, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+digit_gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
+                                  int32_t *__restrict__ C, uint32_t count, uint32_t ldc, const PairPlan pl,
+                                  uint32_t *__restrict__ sync_ctr, uint32_t no_reload, uint32_t q_blocked) {
+  constexpr uint32_t PM = 256, PN = 256 * NACC;
+  constexpr uint32_t kABytes = 128 * BK, kBBytes = NACC * 128 * BK;
+  constexpr uint32_t kCols = NACC * 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 2];
+  __shared__ uint32_t tmem_base_sh;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto sA = [&](uint32_t s) { return tiles_base + s * kABytes; };
+  auto sB = [&](uint32_t s) { return tiles_base + STAGES * kABytes + s * kBBytes; };
+  auto full = [&](uint32_t s) { return smem_u32(&bars[s]); };
+  auto empty = [&](uint32_t s) { return smem_u32(&bars[STAGES + s]); };
+  const uint32_t tmem_full = smem_u32(&bars[2 * STAGES]);
+  const uint32_t tmem_empty = smem_u32(&bars[2 * STAGES + 1]);
+
+  const uint32_t pair = blockIdx.x >> 1;
+  // work list of this pair: full_waves whole tiles, then its share of the K-chunked left-over tiles
+  const uint32_t rem_units = pl.rem_tiles * pl.rsplit;
+  const uint32_t my_rem = pair < rem_units ? (rem_units - pair + pl.pairs - 1) / pl.pairs : 0;
+  const uint32_t n_units = pl.full_waves + my_rem;
+  struct Unit {
+    uint32_t tile_m, tile_n, k0, nk, atomic;
+  };
+  auto unit = [&](uint32_t idx) {
+    Unit u;
+    uint32_t t;
+    if (idx < pl.full_waves) {
+      t = idx * pl.pairs + pair;
+      u.k0 = 0;
+      u.nk = pl.ksteps;
+      u.atomic = 0;
+    } else {
+      const uint32_t r = pair + (idx - pl.full_waves) * pl.pairs;  // units running side by side share a K chunk
+      t = pl.full_waves * pl.pairs + r % pl.rem_tiles;
+      u.k0 = (r / pl.rem_tiles) * pl.rper;
+      u.nk = min(pl.rper, pl.ksteps - u.k0);
+      u.atomic = pl.rsplit > 1;
+    }
+    const uint32_t b = t / (pl.band * pl.tiles_n);
+    const uint32_t in_band = t - b * pl.band * pl.tiles_n;
+    const uint32_t bm = min(pl.band, pl.tiles_m - b * pl.band);
+    u.tile_m = b * pl.band + in_band % bm;
+    u.tile_n = in_band / bm;
+    return u;
+  };
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), 2);   // leader: its own arrive.expect_tx + the peer's remote arrive
+      mbar_init(empty(s), 1);  // one multicast commit
+    }
+    mbar_init(tmem_full, 1);   // one multicast commit per unit
+    mbar_init(tmem_empty, 8);  // leader: 4 epilogue warps of each CTA per unit
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {  // TMA producer of this CTA's halves
+      uint32_t it = 0;  // running K-step of this pair: ring stage and phase
+      int strikes = 0;
+      const bool pace = rank == 0 && pl.slack > 0 && sync_ctr != nullptr && !no_reload;
+      for (uint32_t idx = 0; idx < n_units; ++idx) {
+        const Unit u = unit(idx);
+        const int32_t wrow = (int32_t)(u.tile_m * PM + rank * 128);
+        const uint32_t steps = no_reload ? min(u.nk, (uint32_t)STAGES) : u.nk;
+        for (uint32_t i = 0; i < steps; ++i, ++it) {
+          if (pace && idx < pl.full_waves && strikes < kSyncStrikes) {
+            const uint32_t g = idx * pl.ksteps + i;  // the same for every pair in a full wave
+            if (g % pl.epoch == 0) {
+              const uint32_t e = g / pl.epoch;
+              atomicAdd(sync_ctr + e, 1u);
+              if (e >= pl.slack && ld_relaxed_u32(sync_ctr + e - pl.slack) < pl.pairs) {
+                uint64_t t0, now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while (ld_relaxed_u32(sync_ctr + e - pl.slack) < pl.pairs) {
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                  if (now - t0 > kSyncTimeoutNs) {
+                    ++strikes;
+                    break;
+                  }
+                }
+              }
+            }
+          }
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full(s), 2 * (kABytes + kBBytes));
+          else mbar_arrive_remote(full(s), 0);
+          const int32_t kbyte = (int32_t)((u.k0 + i) * BK);
+          tma_load_2d_pair(sA(s), &tmW, kbyte, wrow, full(s));
+#pragma unroll
+          for (uint32_t j = 0; j < NACC; ++j) {
+            const int32_t col = (int32_t)(u.tile_n * PN + j * 256 + rank * 128);
+            if (q_blocked) tma_load_3d_pair(sB(s) + j * 128 * BK, &tmQ, 0, col, (int32_t)(u.k0 + i), full(s));
+            else tma_load_2d_pair(sB(s) + j * 128 * BK, &tmQ, kbyte, col, full(s));
+          }
+        }
+        if (no_reload) break;  // microbench: one ring fill, ever
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {  // the leader issues the MMAs of the pair
+      constexpr uint32_t idesc = instr_desc_i8(256, 256);
+      uint32_t it = 0;
+      for (uint32_t idx = 0; idx < n_units; ++idx) {
+        const Unit u = unit(idx);
+        if (idx > 0) {  // the epilogue warps of both CTAs have drained the previous unit's accumulators
+          mbar_wait(tmem_empty, (idx - 1) & 1);
+          tc_fence_after();
+        }
+        for (uint32_t i = 0; i < u.nk; ++i, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          if (!no_reload || it < STAGES) mbar_wait(full(s), ph);
+          tc_fence_after();
+          const uint64_t ad = smem_desc_sw128(sA(s));
+#pragma unroll
+          for (uint32_t k = 0; k < BK / UK; ++k)
+#pragma unroll
+            for (uint32_t j = 0; j < NACC; ++j)
+              umma_i8_pair(tmem + j * 256, ad + 2 * k, smem_desc_sw128(sB(s) + j * 128 * BK) + 2 * k, idesc,
+                           (i | k) != 0);
+          tc_commit_pair(empty(s));
+        }
+        tc_commit_pair(tmem_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t quarter = warp & 3;
+    for (uint32_t idx = 0; idx < n_units; ++idx) {
+      const Unit u = unit(idx);
+      mbar_wait(tmem_full, idx & 1);
+      tc_fence_after();
+      const uint32_t row = u.tile_m * PM + rank * 128 + quarter * 32 + lane;
+      int32_t *crow = C + (uint64_t)row * ldc + (uint64_t)u.tile_n * PN;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < PN; c0 += 32) {
+        if (u.tile_n * PN + c0 >= ldc) break;  // warp-uniform
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(tmem + ((quarter * 32u) << 16) + c0)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < count) {
+          if (u.atomic) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (v[q]) atomicAdd(crow + c0 + q, (int32_t)v[q]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4 *>(crow + c0 + 4 * q) =
+                  make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      // hand the accumulators back to the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+        else mbar_arrive_remote(tmem_empty, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();  // the peer's shared memory and TMEM stay alive until the pair is done
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols) : "memory");
+}
+
+// C[rows of tile][columns of tile] = 0 for the K-chunked left-over tiles (they are accumulated with atomics)
+__global__ void __launch_bounds__(256)
+zero_tiles_kernel(int32_t *__restrict__ C, uint32_t count, uint32_t ldc, uint32_t pn, uint32_t tiles_m,
+                  uint32_t tiles_n, uint32_t band, uint32_t first_tile) {
+  const uint32_t t = first_tile + blockIdx.x;
+  const uint32_t b = t / (band * tiles_n);
+  const uint32_t in_band = t - b * band * tiles_n;
+  const uint32_t bm = min(band, tiles_m - b * band);
+  const uint32_t tile_m = b * band + in_band % bm, tile_n = in_band / bm;
+  const uint32_t c_lo = tile_n * pn, c_hi = min(ldc, c_lo + pn);
+  const uint32_t r_lo = tile_m * 256, r_hi = min(count, r_lo + 256);
+  if (c_lo >= c_hi) return;
+  const uint32_t w4 = (c_hi - c_lo) >> 2;  // ldc and pn are multiples of 32
+  for (uint32_t r = r_lo + (threadIdx.x / 64); r < r_hi; r += 4) {
+    uint4 *dst = reinterpret_cast<uint4 *>(C + (uint64_t)r * ldc + c_lo);
+    for (uint32_t k = threadIdx.x % 64; k < w4; k += 64) dst[k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // features -> digits
 // ------------------------------------------------------------------------------------------
 // Feature q of a normalised row x[0..step) in the reference order [A, AB_0.., (BA_0..,) B], SA_NACC order:
@@ -694,9 +947,9 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap
 }
 
 template <int NACC, int STAGES>
-static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
-                            uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
-                            uint32_t q_blocked, uint32_t no_reload = 0) {
+static int launch_gemm_pair_oneshot(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
+                                    uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
+                                    uint32_t q_blocked) {
   const uint64_t tm = ceil_div_u64(count, 256), tn = ceil_div_u64(ncols, 256 * NACC);
   const uint64_t ksteps = ceil_div_u64(K, BK), per = ceil_div_u64(ksteps, ksplit);
   const uint64_t blocks = 2 * tm * tn * (uint64_t)ksplit;
@@ -705,7 +958,144 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtens
   auto kern = digit_gemm_pair_kernel<NACC, STAGES>;
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, (uint32_t)tm,
-                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u, no_reload, q_blocked);
+                                                (uint32_t)tn, (uint32_t)ksteps, (uint32_t)per, 8u, 0u, q_blocked);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+
+// Pairs that can be resident at once (clusters of 2 CTAs, one CTA per SM): 74 on a full B200.
+template <class Kern>
+static int resident_pairs(Kern kern, size_t smem) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static int cache[64];
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)sm_count(), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, (const void *)kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
+// Ring of K-sync counters: slots of kSyncRing counters handed out round-robin, so launches in flight on
+// different streams pace themselves on different counters.  One allocation per device and process.
+constexpr uint32_t kSyncRing = 1u << 15;
+constexpr int kSyncSlots = 8;
+static uint32_t *sync_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  static uint32_t *base[64];
+  static unsigned next[64];
+  if (!base[dev]) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)kSyncSlots * kSyncRing * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    base[dev] = (uint32_t *)p;
+  }
+  return base[dev] + (size_t)(next[dev]++ % kSyncSlots) * kSyncRing;
+}
+
+// Work plan of the persistent pair kernel (pure host logic, also exported for the tests): full waves of
+// `pairs` tiles, then the left-over tiles cut into `rsplit` K chunks so that the last partial wave costs
+// ~rem/pairs of a tile time instead of a whole one.
+static PairPlan plan_pairs(uint64_t tm, uint64_t tn, uint64_t ksteps, int max_pairs, int band) {
+  PairPlan pl = {};
+  const uint64_t tiles = tm * tn;
+  pl.tiles_m = (uint32_t)tm;
+  pl.tiles_n = (uint32_t)tn;
+  pl.band = (uint32_t)(band < 1 ? 1 : band);
+  pl.ksteps = (uint32_t)ksteps;
+  pl.full_waves = (uint32_t)(tiles / max_pairs);
+  pl.rem_tiles = (uint32_t)(tiles % max_pairs);
+  pl.rsplit = 1;
+  pl.rper = (uint32_t)ksteps;
+  if (pl.rem_tiles) {
+    // rounds(s) = ceil(rem * s / P) chunks of ksteps / s each; a chunk keeps >= 16 K-steps; the small penalty
+    // per split accounts for the extra epilogues (atomics)
+    double best = 1e30;
+    const uint32_t s_max = env_int("SALIB_B200_GEMM_RSPLIT_MAX", 16);
+    for (uint32_t s = 1; s <= s_max && ksteps / s >= 16; ++s) {
+      const uint64_t rounds = ceil_div_u64((uint64_t)pl.rem_tiles * s, max_pairs);
+      const double cost = (double)rounds * (double)ceil_div_u64(ksteps, s) / (double)ksteps + 0.004 * s;
+      if (cost < best - 1e-12) {
+        best = cost;
+        pl.rsplit = s;
+      }
+    }
+    pl.rper = (uint32_t)ceil_div_u64(ksteps, pl.rsplit);
+    pl.rsplit = (uint32_t)ceil_div_u64(ksteps, pl.rper);  // no empty chunk
+  }
+  const uint64_t rem_units = (uint64_t)pl.rem_tiles * pl.rsplit;
+  pl.pairs = (uint32_t)(pl.full_waves ? (uint64_t)max_pairs : (rem_units < (uint64_t)max_pairs ? rem_units : max_pairs));
+  pl.epoch = (uint32_t)env_int("SALIB_B200_GEMM_EPOCH", 16);
+  pl.slack = (uint32_t)env_int("SALIB_B200_GEMM_SLACK", 1);
+  if (pl.epoch < 1) pl.epoch = 1;
+  if (pl.full_waves == 0 || pl.pairs < 2) pl.slack = 0;
+  return pl;
+}
+
+// m-tiles per band: a wave of P tiles covers `band` m-tiles x P / band n-tiles and reads 256 * band W rows +
+// 512 * P / band Q columns per K byte -- least for band = sqrt(2 P) (12 at P = 74); bands of equal height.
+static int default_band(uint64_t tm, int pairs) {
+  int ideal = 1;
+  while ((ideal + 1) * (ideal + 1) <= 2 * pairs) ++ideal;
+  const uint64_t nb = (tm + ideal / 2) / ideal;
+  return (int)ceil_div_u64(tm, nb ? nb : 1);
+}
+
+template <int NACC, int STAGES>
+static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
+                            uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
+                            uint32_t q_blocked, uint32_t no_reload = 0, int force_pairs = 0) {
+  if (!no_reload && (ksplit > 1 || env_int("SALIB_B200_GEMM_PERSIST", 1) == 0))
+    return launch_gemm_pair_oneshot<NACC, STAGES>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, q_blocked);
+  const uint64_t tm = ceil_div_u64(count, 256), tn = ceil_div_u64(ncols, 256 * NACC);
+  const uint64_t ksteps = ceil_div_u64(K, BK);
+  SA_REQUIRE(tm * tn < (1ull << 31), SA_ERR_UNSUPPORTED, "digit GEMM: too many tiles");
+  const size_t smem = (size_t)STAGES * (128 + NACC * 128) * BK + 1024;
+  auto kern = digit_gemm_pair_persistent_kernel<NACC, STAGES>;
+  SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int max_pairs = force_pairs > 0 ? force_pairs : resident_pairs(kern, smem);
+  if (const int cap = env_int("SALIB_B200_GEMM_PAIRS", 0)) max_pairs = cap < max_pairs ? cap : max_pairs;
+  SA_REQUIRE(max_pairs >= 1, SA_ERR_UNSUPPORTED, "digit GEMM: no CTA pair fits this device");
+  PairPlan pl = plan_pairs(tm, tn, ksteps, max_pairs, env_int("SALIB_B200_GEMM_BAND", default_band(tm, max_pairs)));
+  uint32_t *ctr = nullptr;
+  if (pl.slack > 0 && !no_reload) {
+    // counters are used as a ring: epochs per launch must fit, else widen the epoch
+    const uint64_t steps = (uint64_t)pl.full_waves * pl.ksteps;
+    if (ceil_div_u64(steps, pl.epoch) + 1 > kSyncRing) pl.epoch = (uint32_t)ceil_div_u64(steps, kSyncRing - 1);
+    ctr = sync_slot();
+    if (ctr) SA_CUDA(cudaMemsetAsync(ctr, 0, (size_t)kSyncRing * sizeof(uint32_t), st));
+    else pl.slack = 0;
+  }
+  if (pl.rem_tiles && pl.rsplit > 1) {
+    zero_tiles_kernel<<<pl.rem_tiles, 256, 0, st>>>(d_C, (uint32_t)count, (uint32_t)ldc, 256u * NACC, pl.tiles_m,
+                                                   pl.tiles_n, pl.band, pl.full_waves * pl.pairs);
+    note_launches(1);
+  }
+  kern<<<2 * pl.pairs, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, pl, ctr, no_reload,
+                                             q_blocked);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -754,7 +1144,22 @@ extern "C" uint64_t sa_digit_ldc(int nfeat, int ndigits) { return round_up((uint
 extern "C" int sa_digit_ksplit(uint64_t N, int nfeat, int ndigits, uint64_t count) {
   const uint64_t ncols = (uint64_t)nfeat * ndigits;
   const int v = pick_variant(count, ncols);
+  // the persistent pair kernel cuts K by itself (left-over tiles, atomics into one C layer)
+  if (v >= 2 && env_int("SALIB_B200_GEMM_PERSIST", 1) != 0 && !getenv("SALIB_B200_DIGIT_KSPLIT")) return 1;
   return choose_ksplit(count, ncols, N, variant_bm(v), variant_bn(v));
+}
+
+// Work plan of the persistent CTA-pair kernel for `tiles_m x tiles_n` pair tiles of `ksteps` K-steps on
+// `max_pairs` resident pairs (pure host logic; tests).  out[0..7] = pairs, full_waves, rem_tiles, rsplit, rper,
+// band, epoch, slack.
+extern "C" int sa_digit_pair_plan(uint64_t tiles_m, uint64_t tiles_n, uint64_t ksteps, int max_pairs, int band,
+                                  uint32_t *out) {
+  SA_REQUIRE(out && tiles_m >= 1 && tiles_n >= 1 && ksteps >= 1 && max_pairs >= 1, SA_ERR_ARG,
+             "sa_digit_pair_plan: bad arguments");
+  const PairPlan pl = plan_pairs(tiles_m, tiles_n, ksteps, max_pairs, band);
+  out[0] = pl.pairs; out[1] = pl.full_waves; out[2] = pl.rem_tiles; out[3] = pl.rsplit;
+  out[4] = pl.rper; out[5] = pl.band; out[6] = pl.epoch; out[7] = pl.slack;
+  return SA_OK;
 }
 
 extern "C" size_t sa_digit_features_workspace_bytes(int nfeat) {
@@ -882,13 +1287,9 @@ extern "C" int sa_microbench_i8_tensor(void *stream, const uint8_t *d_w, const i
   if (rc) return rc;
   // the K coordinate runs past the 1024-byte rows after 8 steps: those boxes are zero-filled, and never loaded
   // anyway (no_reload stops the producer after the first ring fill)
-  const size_t smem = (size_t)4 * (128 + 256) * BK + 1024;
-  auto kern = digit_gemm_pair_kernel<2, 4>;
-  SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(2 * pairs), kThreads, smem, (cudaStream_t)stream>>>(mw, mq, d_C, (uint32_t)(pairs * 256), 512u,
-                                                                        (uint32_t)pairs, 1u, (uint32_t)ksteps,
-                                                                        (uint32_t)ksteps, 8u, 1u, 0u);
-  SA_LAUNCH_CHECK();
+  rc = launch_gemm_pair<2, 4>((cudaStream_t)stream, mw, mq, d_C, pairs * 256, 512, 512, (uint64_t)ksteps * BK, 1, 0u,
+                              1u, (int)pairs);
+  if (rc) return rc;
   *h_ops = 2.0 * 256 * 512 * 128 * (double)ksteps * (double)pairs;
   return SA_OK;
 }

@@ -67,6 +67,33 @@ def test_digit_gemm_variants_are_exact(variant, count, ncols, K, ksplit, monkeyp
         assert np.array_equal(got[ks].astype(np.int64), want), f"variant {variant}, K split {ks}"
 
 
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("count,ncols,K,pairs,epoch,slack", [
+    (1100, 1100, 5120, 4, 4, 1),      # full waves + K-chunked left-over tiles, K-sync on
+    (1100, 1100, 5120, 0, 16, 2),     # all pairs of the GPU: everything is left-over (atomics)
+    (700, 1500, 2100, 3, 2, 1),       # ragged K, ragged rows and columns
+    (2000, 3000, 4096, 7, 8, 0),      # several bands, sync off
+    (257, 513, 300, 1, 1, 1),         # a single pair walks every tile
+])
+def test_persistent_pair_gemm_is_exact(variant, count, ncols, K, pairs, epoch, slack, monkeypatch):
+    """The persistent, K-synchronised CTA-pair kernel: waves of whole tiles, the left-over tiles cut along K and
+    accumulated with int32 atomics, pairs paced by the global epoch counters -- all bit-exact."""
+    monkeypatch.setenv("SALIB_B200_DIGIT_GEMM", str(variant))
+    monkeypatch.setenv("SALIB_B200_GEMM_EPOCH", str(epoch))
+    monkeypatch.setenv("SALIB_B200_GEMM_SLACK", str(slack))
+    if pairs:
+        monkeypatch.setenv("SALIB_B200_GEMM_PAIRS", str(pairs))
+    rng = np.random.default_rng(variant * 7 + count + ncols + K)
+    W = rng.integers(0, 256, size=(count, K), dtype=np.uint8)
+    Q = rng.integers(-128, 128, size=(ncols, K), dtype=np.int8)
+    got = _gemm(W, Q, 1)[0]
+    want = W.astype(np.int64) @ Q.astype(np.int64).T
+    assert np.array_equal(got.astype(np.int64), want)
+    # the one-tile-per-pair kernel of round 1 stays available and agrees
+    monkeypatch.setenv("SALIB_B200_GEMM_PERSIST", "0")
+    assert np.array_equal(_gemm(W, Q, 1)[0], got)
+
+
 def test_digit_gemm_one_hot_layout():
     """Each output picks exactly one (row of W, column of Q, k) product: any operand-layout error shows up
     as a misplaced value rather than as noise."""

@@ -371,3 +371,48 @@ def test_allgather_estimates_gloo_world2(R):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("tm,tn,ksteps,pairs,band", [(40, 30, 8192, 74, 8), (5, 3, 40, 4, 8), (1, 1, 1024, 74, 8),
+                                                     (3, 7, 17, 5, 2), (40, 30, 1024, 74, 10), (10, 30, 64, 74, 8),
+                                                     (2, 2, 8, 3, 8)])
+def test_persistent_pair_plan_covers_every_tile_once(tm, tn, ksteps, pairs, band):
+    """Work list of the persistent CTA-pair GEMM (digits.cu: unit() in digit_gemm_pair_persistent_kernel,
+    restated here): full waves of whole tiles plus K-chunked left-over tiles must cover every (tile, K-step)
+    exactly once, and a left-over tile is only ever touched by atomic units."""
+    from salib_b200 import _lib
+
+    out = (ctypes.c_uint32 * 8)()
+    _lib.call("sa_digit_pair_plan", tm, tn, ksteps, pairs, band, out)
+    P, full_waves, rem_tiles, rsplit, rper, band_, epoch, slack = list(out)
+    tiles = tm * tn
+    assert 1 <= P <= pairs and band_ == band
+    assert full_waves * P + rem_tiles == tiles or (full_waves == 0 and rem_tiles == tiles)
+    assert rper * (rsplit - 1) < ksteps <= rper * rsplit
+    cover = np.zeros((tiles, ksteps), dtype=np.int32)
+    seen_mn = set()
+    for pair in range(P):
+        rem_units = rem_tiles * rsplit
+        my_rem = (rem_units - pair + P - 1) // P if pair < rem_units else 0
+        for idx in range(full_waves + my_rem):
+            if idx < full_waves:
+                t, k0, nk = idx * P + pair, 0, ksteps
+            else:
+                r = pair + (idx - full_waves) * P
+                t = full_waves * P + r % rem_tiles
+                k0 = (r // rem_tiles) * rper
+                nk = min(rper, ksteps - k0)
+                assert nk >= 1
+            cover[t, k0:k0 + nk] += 1
+            b = t // (band * tn)
+            in_band = t - b * band * tn
+            bm = min(band, tm - b * band)
+            seen_mn.add((t, b * band + in_band % bm, in_band // bm))
+    assert (cover == 1).all()
+    assert sorted({(m, n) for _, m, n in seen_mn}) == [(m, n) for m in range(tm) for n in range(tn)]
+    if full_waves == 0:
+        assert slack == 0           # nothing to keep in step
+    # the left-over wave costs about rem/pairs of a tile, not a whole one
+    if rem_tiles and ksteps >= 256:
+        rounds = -(-rem_tiles * rsplit // P)
+        assert rounds * rper / ksteps <= rem_tiles / P + 0.15
