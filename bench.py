@@ -3,13 +3,15 @@
 sample generation on the Sobol' G function, D=64, N=2^20, second order, R=10^4 (configs[2]).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
-    python bench.py --impl reference ...                     # reference CPU algorithm (oracle port)
+    python bench.py --impl reference ...                     # the unmodified reference on the host cores
 
 One JSON line on stdout (rank 0).  A *step* is one full ``sobol.analyze`` of the resident model output Y
-(moments, normalise, point estimates, R bootstrap resamples sharded over the ranks, all-gather, CIs).
-``value`` = N*R / step time (resample-rows/s, the unit BASELINE.md section 3 defines for both arms);
-``analyze_s`` is the same number as seconds.  Sample generation is timed in its own loop and reported under
-``sample`` (Grows/s) with its HBM roofline.  See DESIGN.md "Measurement".
+(moments, digit features, multiplicities, exact integer GEMM, estimator algebra, CIs; with several ranks each holds
+a base-row range and the partial sums are reduce-scattered).  ``value`` = N*R / step time (resample-rows/s, the unit
+BASELINE.md section 3 defines for both arms); ``analyze_s`` is the same number as seconds; ``e2e`` is the drop-in
+``analyze(problem, Y_host, ...)`` call with the host-to-device copy of Y and the read-back inside the timed region.
+Sample generation is timed in its own loop and reported under ``roofline.sample`` (Grows/s, HBM roofline).
+The run exits non-zero if the result is wrong (see ``result_check``).  See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -54,8 +56,11 @@ def parse_args():
                          "the integer engine scales with) or resample ids (all-gather of estimates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample", action="store_true", help="skip the 70 GB sample-generation leg")
-    ap.add_argument("--ref-log2n", type=int, default=10, help="bounded sample of the reference arm")
-    ap.add_argument("--ref-resamples", type=int, default=48)
+    ap.add_argument("--ref-log2n", type=int, default=11, help="bounded sample of the reference arm (SURVEY 8(d): "
+                                                              "D=64, N=2^11..2^13, R=100)")
+    ap.add_argument("--ref-resamples", type=int, default=100)
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the reference arm")
+    ap.add_argument("--cpu-log2n", type=int, default=10, help="bounded sample of the in-line cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -73,67 +78,170 @@ def g_a(D):
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 sustained TFLOP/s, bf16 burst TFLOP/s, source) from the driver-written MEASURED_PEAKS.json,
+    else the fallback B200_PROFILING.md states."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
                 p = json.load(f)
-            return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return (float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]),
+                    "measured (MEASURED_PEAKS.json)")
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle's reference-form analyze on a bounded sample
+# reference arm / cpu baseline: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.sh) on a bounded sample
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(a, steps, warmup, processes):
-    """Times oracle.analyze.analyze_reference_form(_parallel) (a NumPy restatement of
-    analyze/sobol.py:147-194, same gathers and reductions) on D=a.dim, N=2^ref_log2n, R=ref_resamples.
-    Returns (resample_rows_per_s, seconds_per_step, description)."""
-    from oracle import analyze as o_analyze
-    from oracle import saltelli as o_saltelli
-    from oracle import test_functions as o_tf
+def load_reference():
+    """-> (analyze module, sample module, Sobol_G module, kind).  kind "reference": SALib itself from oracle/_ref
+    (a copy of /root/reference/src/SALib made by oracle/make_ref.sh; it travels to the GPU box with the snapshot);
+    kind "port": the oracle's restatement, only if the staged reference is missing."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(os.path.join(ref, "SALib")):
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        from SALib.analyze import sobol as ref_analyze
+        from SALib.sample import sobol as ref_sample
+        from SALib.test_functions import Sobol_G as ref_g
+        return ref_analyze, ref_sample, ref_g, "reference"
+    return None, None, None, "port"
 
-    D, N, R = a.dim, 1 << a.ref_log2n, a.ref_resamples
+
+def reference_inputs(a, log2n):
+    """(problem, Y, sample seconds, rows) of the bounded sample, made by the reference's own sampler and model."""
+    import warnings
+
+    ref_analyze, ref_sample, ref_g, kind = load_reference()
+    D, N = a.dim, 1 << log2n
     c2 = not a.first_order_only
-    X = o_saltelli.sample(g_problem(D), N, c2, skip_values=N, closed_form=True)
-    Y = o_tf.sobol_g(X, a=g_a(D))
-    times = []
-    for it in range(warmup + steps):
+    problem = g_problem(D)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
         t0 = time.perf_counter()
-        if processes > 1:
-            o_analyze.analyze_reference_form_parallel(D, Y, c2, R, seed=100, n_processors=processes)
+        if kind == "reference":
+            X = ref_sample.sample(dict(problem), N, calc_second_order=c2, scramble=False, skip_values=N)
         else:
-            o_analyze.analyze_reference_form(D, Y, c2, R, seed=100)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    sec = float(np.mean(times))
-    desc = (f"oracle port of analyze/sobol.py on G-function D={D}, N=2^{a.ref_log2n}, R={R}, "
-            f"{'second' if c2 else 'first+total'} order, {processes} process(es); "
+            from oracle import saltelli as o_saltelli
+            X = o_saltelli.sample(problem, N, c2, skip_values=N, closed_form=True)
+        t_sample = time.perf_counter() - t0
+        if kind == "reference":
+            Y = ref_g.evaluate(X, a=g_a(D))
+        else:
+            from oracle import test_functions as o_tf
+            Y = o_tf.sobol_g(X, a=g_a(D))
+    return problem, Y, t_sample, X.shape[0]
+
+
+def reference_analyze_once(a, problem, Y, R, processes):
+    """One ``SALib.analyze.sobol.analyze`` call (serial, or its own process pool) -> seconds."""
+    import warnings
+
+    ref_analyze, _, _, kind = load_reference()
+    c2 = not a.first_order_only
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        if kind == "reference":
+            ref_analyze.analyze(dict(problem), Y, calc_second_order=c2, num_resamples=R, seed=100,
+                                parallel=processes > 1, n_processors=processes if processes > 1 else None)
+        else:
+            from oracle import analyze as o_analyze
+            if processes > 1:
+                o_analyze.analyze_reference_form_parallel(a.dim, Y, c2, R, seed=100, n_processors=processes)
+            else:
+                o_analyze.analyze_reference_form(a.dim, Y, c2, R, seed=100)
+        return time.perf_counter() - t0
+
+
+def sample_desc(a, log2n, R, processes, kind):
+    what = "SALib.analyze.sobol.analyze (unmodified reference, oracle/_ref)" if kind == "reference" \
+        else "oracle port of analyze/sobol.py"
+    how = f"parallel=True, n_processors={processes}" if processes > 1 else "serial"
+    return (f"{what}, {how}, on G-function D={a.dim}, N=2^{log2n}, R={R}, "
+            f"{'first+total' if a.first_order_only else 'second'} order; normalised to resample-rows/s (N*R/s); "
             f"the headline itself needs 84 GB for r alone on the CPU (BASELINE.md)")
-    return N * R / sec, sec, desc
 
 
 def run_reference_arm(a):
+    """``--impl reference``: the reference's own CPU implementation (process pool on all host cores) on a bounded
+    sample of the workload, sized so that warmup + steps fit ``--ref-budget-s``."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind = load_reference()[3]
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
-    # keep the whole run within a few minutes: warm-up is capped at 1 for the CPU arm
-    val, sec, desc = cpu_reference_run(a, max(1, a.steps), min(a.warmup, 1), procs)
+    procs = max(1, min(cores, 64))
+    R = a.ref_resamples
+    total = max(1, a.steps) + max(0, a.warmup)
+    # size the sample: probe at N = 2^8, time grows ~ N (each of the ~2100 tasks gathers [N, R] arrays)
+    problem, Y, _, _ = reference_inputs(a, 8)
+    reference_analyze_once(a, problem, Y, R, procs)                      # pool start-up, imports
+    t_probe = reference_analyze_once(a, problem, Y, R, procs)
+    log2n = a.ref_log2n
+    while log2n > 8 and t_probe * (1 << (log2n - 8)) * 1.3 * total > a.ref_budget_s:
+        log2n -= 1
+    problem, Y, t_sample, rows = reference_inputs(a, log2n)
+    N = 1 << log2n
+    times = []
+    for it in range(total):
+        dt = reference_analyze_once(a, problem, Y, R, procs)
+        if it >= a.warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    val = N * R / sec
+    desc = sample_desc(a, log2n, R, procs, kind)
+    Nh, Rh = 1 << a.log2n, a.resamples
     line = {
         "metric": "sobol.analyze resample-rows/s (N*R/s)", "value": val, "unit": "resample-rows/s",
-        "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+        "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": desc},
-        "cpu_baseline": {"value": val, "unit": "resample-rows/s", "cores": procs, "kind": "port", "sample": desc},
+        "dtype": "f64", "data": "synthetic", "config": bench_config(a),
+        "cpu_baseline": {"value": val, "unit": "resample-rows/s", "cores": procs, "kind": kind, "sample": desc,
+                         "seconds_per_step": sec,
+                         "headline_seconds_extrapolated": Nh * Rh / val,
+                         "extrapolation": "linear in N*R from the bounded sample (labelled estimate; SURVEY section 6)"},
+        "sample": {"value": rows / t_sample / 1e9, "unit": "Grows/s", "rows": rows, "seconds": t_sample,
+                   "what": f"SALib.sample.sobol.sample(scramble=False) D={a.dim}, N=2^{log2n}, 1 core"
+                   if kind == "reference" else "oracle port"},
         "e2e": {"value": val, "unit": "resample-rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def cpu_baseline_leg(a):
+    """The in-line ``cpu_baseline`` of this repo's arm (rank 0, N=1): the reference serial on one core, ~10-30 s."""
+    kind = load_reference()[3]
+    R = a.ref_resamples
+    problem, Y, t_sample, rows = reference_inputs(a, a.cpu_log2n)
+    sec = reference_analyze_once(a, problem, Y, R, 1)
+    N = 1 << a.cpu_log2n
+    return {"value": N * R / sec, "unit": "resample-rows/s", "cores": 1, "kind": kind,
+            "sample": sample_desc(a, a.cpu_log2n, R, 1, kind), "seconds": sec,
+            "sample_generation": {"value": rows / t_sample / 1e9, "unit": "Grows/s", "seconds": t_sample,
+                                  "what": f"reference sobol.sample(scramble=False), D={a.dim}, N=2^{a.cpu_log2n}"}}
+
+
+def bench_config(a):
+    """The workload both arms are quoted on (identical dict in the two JSON lines)."""
+    return {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
+            "skip_values": 1 << a.log2n, "seed": 100,
+            "l2": "Y (1.09 GB) and the operands of the GEMM (26 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+def profile_traffic(key):
+    """DRAM bytes per launch of the dominant kernel for this configuration, from the committed ncu capture
+    (profiles/r02_traffic.json; null when that configuration has not been profiled)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        e = t.get(key)
+        return (e["bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -252,7 +360,7 @@ def main():
     skip = N
     plan, first = sample_sobol._plan(problem, N, c2, False, skip, None)
     lo, hi = rt.shard_range(N, rank, world)
-    hbm_peak, hbm_src = measured_peaks()
+    hbm_peak, bf16_sustained, bf16_burst, peak_src = measured_peaks()
 
     # ---- leg 1: Saltelli sample generation into HBM (sharded by Sobol' index range, no communication)
     sample = None
@@ -264,32 +372,39 @@ def main():
         rows = step_rows * N
         sample_bytes_rank = step_rows * (hi - lo) * D * 8
         gbs = sample_bytes_rank * a.steps / t / 1e9  # per GPU
-        sample = {"value": rows * a.steps / t / 1e9, "unit": "Grows/s", "ms_per_pass": t / a.steps * 1e3,
-                  "rows": rows, "bytes_per_gpu": sample_bytes_rank, "launches": int(launches),
-                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": gbs / hbm_peak,
-                               # ncu (profiles/r01_final_ncu_full_summary.csv): dram write 69.736 GB, read 1 MB
-                               "traffic": 69.737e9 if (D == 64 and a.log2n == 20 and c2 and world == 1) else None,
-                               "peak_source": hbm_src,
-                               "kernel": "saltelli_reg_kernel" if D % 2 == 0 else "saltelli_generic_kernel"}}
+        tr, tr_src = profile_traffic(f"sample_d{D}_n{a.log2n}_c{int(c2)}_g{world}")
+        sample = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                  "traffic": tr, "traffic_source": tr_src, "peak_source": peak_src,
+                  "kernel": "saltelli_reg_kernel" if D % 2 == 0 else "saltelli_generic_kernel",
+                  "value": rows * a.steps / t / 1e9, "value_unit": "Grows/s (whole job)",
+                  "ms_per_pass": t / a.steps * 1e3, "rows": rows, "bytes_per_gpu": sample_bytes_rank,
+                  "launches": int(launches)}
         del X
         torch.cuda.empty_cache()
 
-    # ---- model output: fused Sobol' -> G evaluation of this rank's index range, all-gathered
+    # ---- model output: fused Sobol' -> G evaluation of this rank's index range
     Ypart = rt.empty((step_rows * (hi - lo),), torch.float64)
     t_eval = timed(lambda: Sobol_G.evaluate_sample(plan, first + lo, hi - lo, a=avec, out=Ypart, check=False),
                    a.steps, a.warmup)
-    # multi-GPU analyze: by base-row range for the integer engine (features, multiplicities and GEMM all shrink
-    # with the shard; one all-reduce of [R, SA_NACC] partial sums), by resample id for the FP64 engines
-    row_mode = world > 1 and (a.shard == "rows" or (a.shard == "auto" and a.algo in ("auto", "digits")))
-    if world > 1 and not row_mode:
-        sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0]) for g in range(world)]
-        parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
-        dist.all_gather(parts, Ypart)
-        Yd = torch.cat(parts)
-    else:
-        Yd = Ypart
     fused = {"value": step_rows * N * a.steps / t_eval / 1e9, "unit": "Grows/s", "ms_per_pass": t_eval / a.steps * 1e3}
+    # multi-GPU analyze: by base-row range for the integer engine (features, multiplicities and GEMM all shrink
+    # with the shard; reduce-scatter of [R, SA_NACC] partial sums), by resample id for the FP64 engines.  This is
+    # the decision analyze() makes by itself under torchrun (analyze_device(shard="auto")); the device-resident
+    # leg calls the route directly because its Y shard is already on the GPU.
+    row_mode = world > 1 and (a.shard == "rows" or (a.shard == "auto" and a.algo in ("auto", "digits")))
+
+    _full = []
+
+    def full_y():
+        if world == 1:
+            return Ypart
+        if not _full:
+            sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0])
+                     for g in range(world)]
+            parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
+            dist.all_gather(parts, Ypart)
+            _full.append(torch.cat(parts))
+        return _full[0]
 
     # ---- leg 2 (the metric): sobol.analyze on resident Y
     import ctypes
@@ -298,19 +413,17 @@ def main():
         """Times `steps` analyze calls; returns (seconds per step, accumulate-kernel ms per step, resample-rows the
         accumulate launches covered per step, launches in the timed region, last result, clocks)."""
         events = []
-
         rows_mode = row_mode and algo != "fp64"
+        Yres = Ypart if (rows_mode or world == 1) else full_y()
 
         def analyze_step():
             if rows_mode:
-                return analyze_sobol.analyze_row_sharded(problem, [(lo, Yd)], N, calc_second_order=c2,
+                return analyze_sobol.analyze_row_sharded(problem, [(lo, Yres)], N, calc_second_order=c2,
                                                          num_resamples=R, seed=100, resample="philox",
                                                          kernel_events=events, algo=algo)
-            if row_mode:    # FP64 leg of a row-sharded run: every rank needs all of Y
-                return analyze_sobol.analyze_device(problem, full_y(), calc_second_order=c2, num_resamples=R,
-                                                    seed=100, resample="philox", kernel_events=events, algo=algo)
-            return analyze_sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100,
-                                                resample="philox", kernel_events=events, algo=algo)
+            return analyze_sobol.analyze_device(problem, Yres, calc_second_order=c2, num_resamples=R, seed=100,
+                                                resample="philox", kernel_events=events, algo=algo,
+                                                shard="resamples")
 
         for _ in range(warmup):
             analyze_step()
@@ -329,17 +442,6 @@ def main():
         rows = sum(c for c, _, _ in timed_events) * ((hi - lo) if rows_mode else N) / steps
         return t / steps, ms, rows, n_launch, S_, clk
 
-    _full = []
-
-    def full_y():
-        if not _full:
-            sizes = [step_rows * (rt.shard_range(N, g, world)[1] - rt.shard_range(N, g, world)[0])
-                     for g in range(world)]
-            parts = [torch.empty((s,), dtype=torch.float64, device="cuda") for s in sizes]
-            dist.all_gather(parts, Ypart)
-            _full.append(torch.cat(parts))
-        return _full[0]
-
     engine_fallback = None
     try:
         t_step, k_ms, k_rows, launches, S, clocks = measure(a.algo, a.steps, a.warmup, True)
@@ -353,6 +455,7 @@ def main():
     t_an = t_step * a.steps
     engine = getattr(S, "engine", "?")
     nacc = analyze_sobol._nacc(D, c2)
+    clk_sum = clocks.summary()
 
     def fp64_peak_tflops():
         out = rt.zeros((1,), torch.float64)
@@ -399,16 +502,13 @@ def main():
             kernel = "fo_gemv_kernel"
         peak = fp64_peak_tflops()
         achieved = flop_per_row * rows / (ms / 1e3) / 1e12 if ms > 0 else None
-        # DRAM bytes of one tile-kernel launch from the committed ncu capture (1184 resamples = one wave at
-        # N = 2^20: Y in analysis layout 1.36 GB + multiplicities 1.24 GB, each read once)
-        traffic = 2.635e9 if (c2 and D == 64 and a.log2n == 20) else None
+        tr, tr_src = profile_traffic(f"fp64_d{D}_n{a.log2n}_c{int(c2)}")
         return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "profiles/r01_final_ncu_full_summary.csv (dram read+write per 1184-resample "
-                                  "launch)" if traffic else None,
+                "frac": (achieved / peak) if achieved else None, "traffic": tr, "traffic_source": tr_src,
                 "kernel": kernel, "kernel_ms_per_step": ms, "kernel_share_of_step": (ms / 1e3) / t_step_,
                 "algorithmic_flop_per_resample_row": flop_per_row,
-                "peak_source": "measured here: sa_microbench_fp64 (16 independent DFMA chains/thread)",
+                "peak_source": "measured here: sa_microbench_fp64 (16 independent DFMA chains/thread); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
                 "note": "FP64-FMA-pipe bound; rows with multiplicity 0 are skipped, so achieved counts "
                         "algorithmic flop of all N*R resample-rows"}
 
@@ -417,64 +517,109 @@ def main():
         ops_per_row = 2 * nacc * S_dig        # int8 multiply-adds x 2 per (resample, row)
         burst, sustained = i8_peak_tops()
         achieved = ops_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
-        traffic = 436.6e9 if (c2 and D == 64 and a.log2n == 20 and R == 10000 and world == 1) else None
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+        tr, tr_src = profile_traffic(f"digits_d{D}_n{a.log2n}_r{R}_c{int(c2)}_g{world}")
+        # MEASURED_PEAKS.json has no int8 entry: the int8 tensor rate is twice the bf16 rate on this part (8192
+        # vs 4096 MAC/clk/SM), so the denominator is 2 x the driver's SUSTAINED bf16 figure (the kernel runs
+        # inside a long, power-capped step)
+        peak = 2.0 * bf16_sustained
+        sm_mhz = clk_sum.get("sm_mhz") or 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "ops": "int8 tensor operations (u8 x s8 -> s32 multiply-add = 2), counted like flop",
-                    "frac": (achieved / sustained) if achieved else None, "peak_burst": burst,
-                    "traffic": traffic,
-                    "traffic_source": "profiles/r01_digits_pair_gemm_ncu_summary.csv (dram read+write of the "
-                                      "10^4-resample launch)" if traffic else None,
-                    "kernel": "digit_gemm_pair_kernel<2,4> (tcgen05.mma.cta_group::2.kind::i8)",
+                    "frac": (achieved / peak) if achieved else None,
+                    "peak_source": f"2 x bf16_tflops_sustained ({bf16_sustained}) of {peak_src}: int8 runs at twice "
+                                   "the bf16 MAC rate and the file has no int8 entry",
+                    "peak_2x_bf16_burst": 2.0 * bf16_burst,
+                    "frac_of_2x_bf16_burst": (achieved / (2.0 * bf16_burst)) if achieved else None,
+                    "peak_no_traffic_microbench": sustained, "peak_no_traffic_microbench_burst": burst,
+                    "frac_of_no_traffic_microbench": (achieved / sustained) if achieved else None,
+                    "peak_at_measured_clock": 2 * 8192 * 148 * sm_mhz * 1e6 / 1e12 if sm_mhz else None,
+                    "frac_of_peak_at_measured_clock": (achieved / (2 * 8192 * 148 * sm_mhz * 1e6 / 1e12))
+                    if (achieved and sm_mhz) else None,
+                    "traffic": tr, "traffic_source": tr_src,
+                    "algorithmic_bytes": ((R + 1) + nacc * S_dig) * ((hi - lo) if row_mode else N)
+                    + 4 * (R + 1) * nacc * S_dig,
+                    "kernel": "digit_gemm_pair_persistent_kernel<2,4> (tcgen05.mma.cta_group::2.kind::i8)",
                     "kernel_ms_per_step": k_ms, "kernel_share_of_step": (k_ms / 1e3) / t_step,
                     "algorithmic_int8_ops_per_resample_row": ops_per_row, "digits": S_dig,
-                    "equivalent_fp64_tflops": (2 * (D * (D - 1) // 2) + 6 * D + 6 if c2 else 6 * D + 6) * k_rows
-                    / (k_ms / 1e3) / 1e12 if k_ms > 0 else None,
-                    "peak_source": "measured here: sa_microbench_i8_tensor (the kernel's own MMA mix, operand ring "
-                                   "filled once, ~0.1 s run at power-limited clocks); MEASURED_PEAKS.json has no "
-                                   "int8 figure (2 x its bf16 numbers: 3282 burst / 2771 sustained)",
-                    "note": "exact integer GEMM of the multiplicities with the int8 digits of the features; "
-                            "tensor pipe 94 % active at the 1.36 GHz the 1000 W cap allows (ncu)"}
+                    "note": "exact integer GEMM of the multiplicities with the int8 digits of the features; the work "
+                            "moved from the FP64 pipe (4422 flop per resample-row, SURVEY 8(d)) to the int8 tensor "
+                            "pipe at 6.8x the raw operation count; ncu: tensor pipe 98.8 % active at the clock the "
+                            "1000 W cap allows (profiles/r02_pair_persist_v1_ncu_summary.csv)"}
     else:
         roofline = fp64_roofline(k_ms, k_rows, t_step)
+    roofline["sample"] = sample
 
+    checks = {}
     fp64_leg = None
     if engine == "digits" and not a.no_fp64_leg:
         t2, k2, rows2, launches2, S2, _ = measure("fp64", 1, 1, False)
+        diffs = {k: float(np.nanmax(np.abs(np.asarray(S[k]) - np.asarray(S2[k])))) for k in S if k in S2}
         fp64_leg = {"analyze_s": t2, "value": N * R / t2, "unit": "resample-rows/s", "engine": S2.engine,
                     "gpu_launches": launches2, "roofline": fp64_roofline(k2, rows2, t2),
-                    "max_abs_diff_vs_default": {k: float(np.nanmax(np.abs(np.asarray(S[k]) - np.asarray(S2[k]))))
-                                                for k in S if k in S2},
+                    "max_abs_diff_vs_default": diffs,
                     "note": "the north-star design (no tensor cores) measured in the same run: 1 step after 1 "
                             "warm-up, same Philox multiplicities"}
-
-    # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region
-    Yh = torch.empty(Yd.shape, dtype=torch.float64, pin_memory=True)
-    Yh.copy_(Yd)
-    torch.cuda.synchronize()
-
-    def e2e_step():
-        if row_mode:   # every rank uploads only its own base-row range
-            return analyze_sobol.analyze_row_sharded(problem, [(lo, Yh)], N, calc_second_order=c2, num_resamples=R,
-                                                     seed=100, resample="philox", algo=a.algo)
-        return analyze_sobol.analyze_device(problem, Yh, calc_second_order=c2, num_resamples=R, seed=100,
-                                            resample="philox", algo=a.algo)
-
-    t_e2e = timed(e2e_step, a.steps, 1)
-    nest = analyze_sobol._nest(D, c2)
-    e2e = {"value": N * R * a.steps / t_e2e, "unit": "resample-rows/s", "analyze_s": t_e2e / a.steps,
-           "h2d_bytes_per_step": int(Yh.numel() * 8) * (world if row_mode else 1), "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4)}
-
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        val, sec, desc = cpu_reference_run(a, 1, 0, 1)
-        cpu = {"value": val, "unit": "resample-rows/s", "cores": 1, "kind": "port", "sample": desc,
-               "seconds": sec}
+        checks["max_abs_diff_digits_vs_fp64"] = max(diffs.values())
+        checks["digits_vs_fp64_ok"] = bool(max(diffs.values()) <= 1e-12)
 
     # analytic indices of the G function (alpha = 1, delta = 0): V_i = 1 / (3 (1 + a_i)^2)
     Vi = 1.0 / (3.0 * (1.0 + avec) ** 2)
     var_total = float(np.prod(1.0 + Vi) - 1.0)
     analytic = (float(Vi[0] / var_total), float(Vi[0] * np.prod(1.0 + Vi[1:]) / var_total))
+    # (i) S1/ST of x1 within 4 sigma of the analytic values (conf = 1.96 sigma)
+    sig1, sigT = float(S["S1_conf"][0]) / 1.959964, float(S["ST_conf"][0]) / 1.959964
+    checks.update({"S1_0": float(S["S1"][0]), "ST_0": float(S["ST"][0]), "S1_conf_0": float(S["S1_conf"][0]),
+                   "ST_conf_0": float(S["ST_conf"][0]), "analytic_S1_0": analytic[0], "analytic_ST_0": analytic[1],
+                   "analytic_ok": bool(abs(S["S1"][0] - analytic[0]) <= 4 * sig1
+                                       and abs(S["ST"][0] - analytic[1]) <= 4 * sigT
+                                       and np.all(np.isfinite(S["S1"])) and np.all(np.isfinite(S["ST_conf"])))})
+    # (iii) several ranks: the point estimates must equal a single-rank recomputation on rank 0
+    if world > 1:
+        Yall = full_y()
+        if rank == 0:
+            S0 = analyze_sobol.analyze_device(problem, Yall, calc_second_order=c2, num_resamples=0, algo=a.algo,
+                                              distributed=False)
+            keys = ["S1", "ST"] + (["S2"] if c2 else [])
+            d = max(float(np.nanmax(np.abs(np.asarray(S[k]) - np.asarray(S0[k])))) for k in keys)
+            checks["max_abs_diff_point_vs_single_rank"] = d
+            checks["multi_rank_ok"] = bool(d <= 1e-12)
+        barrier()
 
+    # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region.  Every rank
+    # holds the host array, as every process of a torchrun job would; analyze() routes by itself.
+    Yfull = full_y()
+    Yh = torch.empty(Yfull.shape, dtype=torch.float64, pin_memory=True)
+    Yh.copy_(Yfull)
+    torch.cuda.synchronize()
+    Yh_np = Yh.numpy()
+    _full.clear()
+    del Yfull
+
+    def e2e_step():
+        if a.algo == "auto":
+            return analyze_sobol.analyze(problem, Yh_np, calc_second_order=c2, num_resamples=R, seed=100)
+        return analyze_sobol.analyze_device(problem, Yh_np, calc_second_order=c2, num_resamples=R, seed=100,
+                                            algo=a.algo, shard="rows" if row_mode else "resamples")
+
+    t_e2e = timed(e2e_step, a.steps, 1)
+    S_e2e = e2e_step()
+    checks["e2e_route"] = {"engine": getattr(S_e2e, "engine", "?"),
+                           "resample_mode": getattr(S_e2e, "resample_mode", "?"),
+                           "max_abs_diff_vs_device_leg": max(
+                               float(np.nanmax(np.abs(np.asarray(S[k]) - np.asarray(S_e2e[k])))) for k in S)}
+    checks["e2e_ok"] = bool(checks["e2e_route"]["max_abs_diff_vs_device_leg"] <= 1e-12)
+    nest = analyze_sobol._nest(D, c2)
+    h2d = int(Yh.numel() * 8) if not (world > 1 and getattr(S_e2e, "engine", "") == "digits") \
+        else int(step_rows * N * 8)      # row shards: the ranks together upload Y once
+    e2e = {"value": N * R * a.steps / t_e2e, "unit": "resample-rows/s", "analyze_s": t_e2e / a.steps,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4),
+           "call": "salib_b200.analyze.sobol.analyze(problem, Y_host, calc_second_order, num_resamples, seed=100)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline_leg(a)
+
+    ok = all(v for k, v in checks.items() if k.endswith("_ok"))
     if rank == 0:
         line = {
             "metric": "sobol.analyze resample-rows/s (N*R/s)", "value": N * R * a.steps / t_an,
@@ -483,20 +628,22 @@ def main():
             "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (sums: exact u8 x s8 -> s32 digit GEMM)" if engine == "digits" else "f64",
             "data": "synthetic", "engine": engine, "engine_fallback": engine_fallback,
-            "config": {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
-                       "skip_values": skip, "resample": "philox seed 100", "parallelism": (f"base-row range x{world} (all-reduce of partial sums)" if row_mode
-                                       else f"resample-id x{world}"),
-                       "l2": f"Y is {Yd.numel() * 8 / 1e6:.0f} MB (> 126 MB L2), no explicit flush"
-                       if Yd.numel() * 8 > 126e6 else "Y fits L2 (resident by design)"},
-            "sample": sample, "fused_sample_eval": fused, "roofline": roofline, "fp64_engine": fp64_leg,
+            "config": bench_config(a),
+            "parallelism": (f"base-row range x{world} (reduce-scatter of partial sums)" if row_mode
+                            else f"resample-id x{world}"),
+            "resample": "philox seed 100",
+            "fused_sample_eval": fused, "roofline": roofline, "fp64_engine": fp64_leg,
             "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-            "result_check": {"S1_0": float(S["S1"][0]), "ST_0": float(S["ST"][0]), "S1_conf_0": float(S["S1_conf"][0]),
-                             "ST_conf_0": float(S["ST_conf"][0]), "analytic_S1_0": analytic[0], "analytic_ST_0": analytic[1]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk_sum,
+            "result_check": checks, "result_ok": ok,
         }
+        line["roofline"]["result_check"] = {k: v for k, v in checks.items() if not isinstance(v, dict)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write(f"bench.py: RESULT CHECK FAILED: {checks}\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -156,7 +156,7 @@ int sa_normalize_f64(void *stream, const double *d_Y, uint64_t N, int Dg, int se
  *                           (it is: the function memsets it on `stream`).
  *   sa_counts_philox:       device Philox4x32-10 draw of N iid uniform indices per resample, as
  *                           multiplicities ~ Multinomial(N, 1/N): a tree of Binomial(n, 1/2) splits
- *                           (popcounts of n random bits) down to windows of <= 32768 rows, then
+ *                           (popcounts of n random bits) down to windows of <= 16384 rows, then
  *                           uniform draws inside each window, histogrammed in shared memory
  *                           (when 2^L | N; otherwise N direct draws with global atomics).  Counters
  *                           are keyed by (seed, global resample id c0+c, tree node | window, word):
@@ -175,6 +175,11 @@ int sa_counts_from_indices_rows(void *stream, const int64_t *d_r, uint64_t N, ui
                                 int32_t *d_overflow);
 int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
                           uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow);
+/* slim != 0: the low-footprint launch shape -- one 1024-thread block per SM with a single 16 KB window, which fits
+ * next to a CTA of the persistent GEMM kernel, so a side stream can draw batch b+1 while batch b is in the tensor
+ * cores.  Same multiplicities as the wide launch (the Philox counters do not depend on the launch shape).      */
+int sa_counts_philox_rows_ex(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                             uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow, int slim);
 
 /* ---- analyze: accumulate / finalize -------------------------------------------------------
  * sa_sobol_accumulate_f64 replaces the gathers and reductions inside first_order / total_order
@@ -205,6 +210,17 @@ int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_t N, int Dg
  * d_conf[SA_NEST].                                                                            */
 int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, double z,
                       double *d_conf);
+/* The two passes of sa_sobol_conf_f64 for estimates spread over the ranks of a row-sharded analyze (replaces the
+ * all-gather of [R, nest] estimates: two all-reduces of nest doubles).  d_mean == NULL: d_out[col] = column sums of
+ * the local d_est [R_local, ncols]; else d_out[col] = sum_r (est - mean[col])^2.  sa_conf_finish_f64 scales a
+ * vector in place (finish == 0: x *= scale) or turns the all-reduced squared deviations into the CI
+ * z * sqrt(x / (R - 1)) (analyze/sobol.py:159,170,180-182: Z * std(ddof=1)).                                   */
+int sa_col_moment_f64(void *stream, const double *d_est, uint64_t R, int ncols, const double *d_mean, double *d_out);
+int sa_conf_finish_f64(void *stream, double *d_x, int ncols, double scale, double z, uint64_t R, int finish);
+/* Mean / population std / min / max of the union of k row shards from per-shard records
+ * d_parts[k][9] = (n_values, the 8 statistics of sa_moments_f64) -> d_out[9] = the 8 statistics of the whole
+ * design + n_values (replaces Y.mean(), Y.std() of analyze/sobol.py:141 when Y is partitioned over GPUs).  */
+int sa_combine_moments_f64(void *stream, const double *d_parts, int k, double *d_out);
 
 /* ---- analyze: opt-in exact-integer tensor-core engine ("digits", csrc/digits.cu) ---------------------
  * The sums of sa_sobol_accumulate_f64 by another route: psum[c][q] = sum_i w[c][i] * F[i][q] with integer
@@ -217,8 +233,10 @@ int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, 
  *   sa_digit_row_pitch(N)   bytes of one digit column (rows of Y padded to 128)
  *   sa_digit_features_i8    d_Y [N*step] reference order + d_stats -> d_Q int8, nfeat*ndigits columns (column
  *                           q*ndigits+s = digit s of feature q) of sa_digit_row_pitch(N) rows, stored K-blocked:
- *                           d_Q[i / 128][column][i % 128]; d_inv [nfeat] = the power of two that maps the
- *                           integer sums back.  nfeat = SA_NACC(Dg, second_order).
+ *                           d_Q[i / 128][column][i % 128]; d_inv [nfeat + 1]: the power of two that maps each
+ *                           column's integer sums back, then (entry nfeat) the heavy-tail guard: how many
+ *                           normalised values of these rows lie within 7 bits of the design's largest |x|
+ *                           (d_stats[2..3] = global min / max).  nfeat = SA_NACC(Dg, second_order).
  *   sa_digit_sums_f64       d_psum [count][nfeat] (the nsplit = 1 layout sa_sobol_finalize_f64 reads) from
  *                           d_w [count][w_pitch] uint8 multiplicities; workspace = int32 digit sums
  *                           [ksplit][count][ldc], ksplit = sa_digit_ksplit(...), ldc = sa_digit_ldc(...).
@@ -258,6 +276,11 @@ int sa_finite_diff_expand_f64(void *stream, const double *d_base, uint64_t n, in
 int sa_dgsm_features_f64(void *stream, const double *d_X, const double *d_Y, uint64_t N, int D, double *d_F);
 int sa_feature_sums_f64(void *stream, const double *d_F, uint64_t N, int nfeat, const uint8_t *d_w,
                         uint64_t count, int nsplit, double *d_psum);
+/* d_out[q] = sum_i (F[i][q] - d_center[q])^2 for the first ncols columns of the chunked feature matrix: the second
+ * pass of np.std(dfdx) in calc_vi_stats (analyze/dgsm.py:103-109), which a one-pass E[x^2] - E[x]^2 cannot
+ * reproduce for nearly constant derivatives.                                                                */
+int sa_feature_centered_ss_f64(void *stream, const double *d_F, uint64_t N, int nfeat, int ncols,
+                               const double *d_center, double *d_out);
 int sa_reduce_splits_f64(void *stream, const double *d_psum, uint64_t count, int nfeat, int nsplit,
                          double scale, double *d_out);
 

@@ -29,6 +29,18 @@ def features(Y, Dg, calc_second_order, mean, std):
     return np.stack(cols, axis=1)
 
 
+GUARD_BITS = 7
+
+
+def guard_count(Y, Dg, calc_second_order, mean, std, vmin, vmax):
+    """Heavy-tail guard of the integer engine (digits.cu: feature_max_kernel): the number of normalised values
+    within GUARD_BITS bits of the design's largest |x|.  ``vmin``/``vmax``: the global min / max of Y."""
+    step = 2 * Dg + 2 if calc_second_order else Dg + 2
+    M = (np.asarray(Y, dtype=np.float64).reshape(-1, step) - mean) / std
+    thr = np.ldexp(max(abs((vmin - mean) / std), abs((vmax - mean) / std)), -GUARD_BITS)
+    return int(np.count_nonzero(np.abs(M) > thr))
+
+
 def split(F, S):
     """(digits int8 [nfeat*S, N] with row q*S+s = digit s of feature q, inv float64 [nfeat], t int64 [N, nfeat])."""
     N, nfeat = F.shape

@@ -47,15 +47,20 @@ SIGNATURES = {
     "sa_counts_philox": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _vp, _vp]),
     "sa_counts_from_indices_rows": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
     "sa_counts_philox_rows": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "sa_counts_philox_rows_ex": (C.c_int, [_vp, _u64, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _i32]),
     "sa_sobol_accumulate_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp]),
     "sa_sobol_accumulate_ex_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _i32, _vp, _i32]),
     "sa_sobol_finalize_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _u64, _i32, _vp, _vp]),
     "sa_sobol_conf_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp]),
+    "sa_col_moment_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp]),
+    "sa_conf_finish_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _u64, _i32]),
+    "sa_combine_moments_f64": (C.c_int, [_vp, _vp, _i32, _vp]),
     "sa_chunked_feature_doubles": (C.c_int, [_i32]),
     "sa_finite_diff_expand_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp, _vp, _vp]),
     "sa_dgsm_features_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp]),
     "sa_feature_sums_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _u64, _i32, _vp]),
     "sa_reduce_splits_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _dbl, _vp]),
+    "sa_feature_centered_ss_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _vp]),
     "sa_digit_available": (C.c_int, []),
     "sa_digit_row_pitch": (_u64, [_u64]),
     "sa_digit_ldc": (_u64, [_i32, _i32]),

@@ -29,11 +29,15 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def to_device(a, dtype=None):
-    """numpy / torch -> contiguous device tensor (no copy if already there)."""
+def to_device(a, dtype=None, non_blocking=False):
+    """numpy / torch -> contiguous device tensor (no copy if already there).  ``non_blocking``: a pinned host
+    tensor is uploaded asynchronously on the current stream (the caller keeps it alive until the result is read)."""
     dev = device()
     if isinstance(a, torch.Tensor):
-        t = a.to(device=dev, dtype=dtype) if (a.device != dev or (dtype and a.dtype != dtype)) else a
+        if a.device != dev or (dtype and a.dtype != dtype):
+            t = a.to(device=dev, dtype=dtype, non_blocking=bool(non_blocking and a.device.type == "cpu" and a.is_pinned()))
+        else:
+            t = a
         return t.contiguous()
     arr = np.ascontiguousarray(a)
     with warnings.catch_warnings():
@@ -41,7 +45,7 @@ def to_device(a, dtype=None):
         t = torch.from_numpy(arr)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    return t.to(dev, non_blocking=False)
+    return t.to(dev, non_blocking=bool(non_blocking and t.is_pinned()))
 
 
 def to_device_sharded(a, dtype, min_bytes=64 << 20):

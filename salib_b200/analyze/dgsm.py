@@ -57,9 +57,13 @@ def analyze(problem, X, Y, num_resamples=100, conf_level=0.95, print_to_console=
     _lib.call("sa_dgsm_features_f64", rt.stream_ptr(), rt.ptr(Xd), rt.ptr(Yd), N, D, rt.ptr(F))
 
     # point values: mean(g^2), std(g^2), var(base)
-    m = _feature_sums(F, N, nfeat, None, 1, sms)[0].cpu().numpy()
-    vi = m[:D]
-    vi_std = np.sqrt(np.maximum(m[D:] - vi * vi, 0.0))
+    m_dev = _feature_sums(F, N, nfeat, None, 1, sms)
+    # np.std(dfdx) (:109) is two-pass: squared deviations from the mean, not E[g^4] - E[g^2]^2, which cancels
+    # catastrophically for nearly constant derivatives (a linear model must give exactly 0)
+    ss = rt.empty((D,), torch.float64)
+    _lib.call("sa_feature_centered_ss_f64", rt.stream_ptr(), rt.ptr(F), N, nfeat, D, rt.ptr(m_dev), rt.ptr(ss))
+    vi = m_dev[0].cpu().numpy()[:D]
+    vi_std = np.sqrt(ss.cpu().numpy() / N)
     base = Yd[0::D + 1].contiguous()
     stats = rt.zeros((8,), torch.float64)
     work = rt.empty((int(L.sa_moments_workspace_bytes()),), torch.uint8)

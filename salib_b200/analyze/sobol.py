@@ -19,15 +19,22 @@ too) whose left operand holds small integers.  Two families of engines compute i
 Resample indices.  The reference draws ``r = rng.integers(N, size=(N, R))`` on the host
 (:113-117,144).  ``RESAMPLE_MODE``:
   * ``"numpy"``  -- draw exactly that matrix on the host (same seed semantics, ``seed`` falsy -> legacy
-                    global RNG), upload it, build multiplicities on the device: results match the
-                    reference to ~1e-13;
+                    global RNG), in row blocks that continue one generator stream (bounded host memory),
+                    upload it, build multiplicities on the device: results match the reference to ~1e-13;
   * ``"philox"`` -- device Philox4x32-10 keyed by (seed, resample id, draw): statistically
                     equivalent CIs, independent of the number of GPUs, no N*R host array;
-  * ``"auto"``   -- numpy while N*R <= NUMPY_RESAMPLE_MAX, else philox (the reference cannot even
-                    allocate ``r`` there: 84 GB at N=2^20, R=10^4).
+  * ``"auto"``   -- numpy whenever a ``seed`` is given and the draw is one the reference itself could make
+                    (N*R <= NUMPY_SEEDED_MAX = 2^31 draws: the caller asked for the reference's resamples),
+                    numpy for small unseeded problems (N*R <= NUMPY_RESAMPLE_MAX), else philox -- with a
+                    warning if a seed was given (the CIs then differ from the reference's for that seed; the
+                    reference cannot allocate ``r`` there anyway: 84 GB at N=2^20, R=10^4).  The mode that ran
+                    is recorded as ``ResultDict.resample_mode``.
 
-Multi-GPU: when a ``torch.distributed`` job is initialised, resamples are sharded by resample id
-across ranks and the per-rank estimates are all-gathered (NCCL); every rank returns the full result.
+Multi-GPU: when a ``torch.distributed`` job is initialised, ``analyze`` picks the decomposition by itself, like
+the reference picks serial vs. pool inside ``analyze`` (:147,183): with the integer engine every rank keeps a
+base-row range of Y, walks all resamples over it and the partial sums are reduce-scattered (``shard="rows"``);
+with the FP64 engines resamples are sharded by resample id and the per-rank estimates are all-gathered
+(``shard="resamples"``).  Every rank returns the full result.
 """
 import os
 from itertools import combinations
@@ -51,8 +58,13 @@ CONST_RESULT_MSG = (
 )
 
 RESAMPLE_MODE = os.environ.get("SALIB_B200_RESAMPLE", "auto")
-NUMPY_RESAMPLE_MAX = 2 ** 24          # N*R index draws made on the host in "auto" mode (~0.1 s of NumPy RNG)
-MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad])
+NUMPY_RESAMPLE_MAX = 2 ** 24          # unseeded "auto": N*R index draws made on the host (~0.1 s of NumPy RNG)
+NUMPY_SEEDED_MAX = 2 ** 31            # seeded "auto": keep the reference's own resamples up to here (17 GB on device)
+NUMPY_BLOCK_DRAWS = 2 ** 24           # host block of the streamed draw (128 MB of int64)
+MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad]), FP64 engines
+# integer engine: resamples go through the GEMM in batches of about this many multiplicity bytes; two buffers
+# alternate, the next batch is drawn (slim Philox kernel, side stream) while the current one is in the tensor cores
+DIGITS_BATCH_BYTES = int(os.environ.get("SALIB_B200_BATCH_BYTES", 2752 << 20))
 _ALGO = {"auto": 0, "fp64": -1, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5, "digits": 6}
 # Engines.  "digits": the bootstrap sums as an exact integer GEMM on the tensor cores (csrc/digits.cu);
 # "fp64": the FP64-pipe engines (feature GEMV / 8x8 register-tile kernel / generic).  "auto" takes "digits"
@@ -72,6 +84,12 @@ def digits_for(N):
 
 
 ENGINE_NAMES = {1: "fp64-generic", 3: "fp64-gemv", 4: "fp64-tile8", 5: "fp64-dmma", 6: "digits"}
+# Heavy-tail guard of the integer engine ("auto" only): the digits of a feature column are relative to the
+# column maximum, so when fewer than GUARD_MIN_ROWS base rows carry every value within 7 bits of the design's
+# largest |x| (an outlier row), a resample can miss them all and be left with entries whose low bits were cut.
+# Such outputs are analysed again with the FP64 engines; 33+ rows are all absent from a resample with
+# probability e^-33, i.e. never.  The count comes from the feature kernels (inv[nacc]).
+GUARD_MIN_ROWS = 32
 DIGITS_MIN_WORK = 1 << 31
 DIGITS_MAX_BYTES = 80 << 30
 # feature kernels: SA_NACC maxima + 9 doubles per model output of a base row must fit 200 KB of shared memory
@@ -89,27 +107,61 @@ def _nest(Dg, c2):
     return 2 * Dg + (Dg * (Dg - 1) // 2 if c2 else 0)
 
 
+def _bcast_from_rank0(t):
+    """In a torch.distributed job every rank must use rank 0's draw (seedless calls would otherwise resample
+    each row shard from a different bootstrap)."""
+    rank, world = rt.world()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.broadcast(t, src=0)
+    return t
+
+
 class _Resampler:
     """Produces the multiplicity rows w[c][:] for resamples [c0, c0+count) on the device."""
 
-    def __init__(self, N, R, seed, mode):
+    def __init__(self, N, R, seed, mode, distributed=True):
         self.N, self.R = N, R
         if mode == "auto":
-            mode = "numpy" if N * R <= NUMPY_RESAMPLE_MAX else "philox"
+            if seed and N * R <= NUMPY_SEEDED_MAX:
+                mode = "numpy"
+            elif N * R <= NUMPY_RESAMPLE_MAX:
+                mode = "numpy"
+            else:
+                mode = "philox"
+                if seed:
+                    warn(f"num_resamples * N = {N * R} index draws exceed what is drawn on the host "
+                         f"({NUMPY_SEEDED_MAX}); resample indices come from the device Philox generator: "
+                         "confidence intervals are statistically equivalent to, but not identical with, "
+                         "the reference's for this seed.")
         if mode not in ("numpy", "philox"):
             raise ValueError(f"unknown resample mode {mode!r}")
         self.mode = mode
         self.flag = rt.zeros((1,), torch.int32)
+        world = rt.world()[1] if distributed else 1
         if mode == "numpy":
-            # analyze/sobol.py:113-117,144 -- identical draw, C order [N, R]
-            rng = np.random.default_rng(seed).integers if seed else np.random.randint
-            r = rng(N, size=(N, R))
-            self.r = rt.to_device(np.ascontiguousarray(r, dtype=np.int64), torch.int64)
+            # analyze/sobol.py:113-117,144 -- identical draw, C order [N, R]; row blocks of one generator
+            # continue the same stream as a single call (tests/test_oracle.py), so host memory stays bounded
+            self.r = rt.empty((N, R), torch.int64)
+            if seed or world == 1 or rt.world()[0] == 0:
+                rng = np.random.default_rng(seed).integers if seed else np.random.randint
+                blk = max(1, NUMPY_BLOCK_DRAWS // max(R, 1))
+                for i0 in range(0, N, blk):
+                    i1 = min(N, i0 + blk)
+                    part = np.ascontiguousarray(rng(N, size=(i1 - i0, R)), dtype=np.int64)
+                    self.r[i0:i1].copy_(torch.from_numpy(part), non_blocking=False)
+            if not seed and world > 1:
+                _bcast_from_rank0(self.r)
         else:
             if seed:
                 self.key = int(np.random.default_rng(seed).integers(0, 2 ** 63))
             else:
-                self.key = int(np.random.randint(0, 2 ** 62))
+                key = int(np.random.randint(0, 2 ** 62))
+                if world > 1:
+                    t = torch.tensor([key], dtype=torch.int64, device=rt.device())
+                    key = int(_bcast_from_rank0(t).item())
+                self.key = key
 
     @classmethod
     def from_indices(cls, r):
@@ -121,23 +173,29 @@ class _Resampler:
         self.r = rt.to_device(np.ascontiguousarray(r, dtype=np.int64), torch.int64)
         return self
 
-    def counts(self, c0, count, w, rows=None):
+    def counts(self, c0, count, w, rows=None, slim=False):
         """w[count][pad_rows(nrows)] <- multiplicities of resamples [c0, c0+count) over the row window
-        ``rows = (row0, nrows)`` (default: all N rows)."""
+        ``rows = (row0, nrows)`` (default: all N rows).  ``slim``: the low-footprint Philox launch that runs
+        beside the persistent GEMM kernel."""
+        if count <= 0:
+            return
         row0, nrows = rows if rows is not None else (0, self.N)
         if self.mode == "numpy":
             _lib.call("sa_counts_from_indices_rows", rt.stream_ptr(), rt.ptr(self.r), self.N, self.R, int(c0),
                       int(count), int(row0), int(nrows), rt.ptr(w), rt.ptr(self.flag))
         else:
-            _lib.call("sa_counts_philox_rows", rt.stream_ptr(), self.key, self.N, int(c0), int(count),
-                      int(row0), int(nrows), rt.ptr(w), rt.ptr(self.flag))
+            _lib.call("sa_counts_philox_rows_ex", rt.stream_ptr(), self.key, self.N, int(c0), int(count),
+                      int(row0), int(nrows), rt.ptr(w), rt.ptr(self.flag), int(bool(slim)))
+
+    @staticmethod
+    def raise_for(flag):
+        if flag & 2:
+            raise ValueError("resample indices out of range [0, N)")
+        if flag & 1:
+            raise OverflowError("a row was drawn more than 255 times in one resample")
 
     def check(self):
-        f = int(self.flag.item())
-        if f & 2:
-            raise ValueError("resample indices out of range [0, N)")
-        if f & 1:
-            raise OverflowError("a row was drawn more than 255 times in one resample")
+        self.raise_for(int(self.flag.item()))
 
 
 def tile_groups(Dg):
@@ -260,23 +318,20 @@ class SobolAnalyzer:
                   rt.ptr(work), int(work.numel()))
 
     def load(self, Yd, stats=None):
-        """Yd: device float64 [N*step] in the reference order -> stats, Yn (and Yt).  ``stats`` (8 doubles)
-        replaces the moments of Yd -- the statistics of the whole design when Yd is one row shard of it."""
+        """Yd: device float64 [N*step] in the reference order -> stats, Yn (and Yt).  ``stats`` (8 doubles, host
+        or device) replaces the moments of Yd -- the statistics of the whole design when Yd is one row shard of
+        it.  No host synchronisation: whether Y was degenerate (non-finite / constant, which the integer engine
+        cannot scale) is read from ``self.stats`` by the caller together with the results (``degenerate``)."""
         L = _lib.lib()
         if stats is None:
             self.moments(Yd)
+        elif isinstance(stats, torch.Tensor):
+            self.stats.copy_(stats.reshape(-1)[:8])
         else:
             self.stats.copy_(rt.to_device(np.asarray(stats, dtype=np.float64), torch.float64))
-        if self.auto_digits:
-            # the integer engine needs finite, non-degenerate values to scale; NaN/inf/constant outputs keep the
-            # reference's NaN propagation through the FP64 engines (SURVEY F12)
-            st = self.stats[:4].cpu().numpy()
-            if not (np.all(np.isfinite(st)) and st[1] > 0.0):
-                self.auto_digits = False
-                self._set_kind(self._fp64_kind())
         if self.kind == 6:                   # digit columns of the features (int8, K-major) + their scales
             self.Q = rt.empty((self.nacc * self.ndigits * int(L.sa_digit_row_pitch(self.N)),), torch.int8)
-            self.inv = rt.empty((self.nacc,), torch.float64)
+            self.inv = rt.empty((self.nacc + 1,), torch.float64)     # column scales + the heavy-tail guard count
         elif self.kind == 3:                 # feature matrix (first order, or second order with pair products)
             self.Yt = rt.empty((self.N * int(L.sa_chunked_feature_doubles(self.nacc)),), torch.float64)
         else:                                # analysis-layout rows (+ the A and B columns for kinds 4, 5)
@@ -292,7 +347,34 @@ class SobolAnalyzer:
             self.auto_digits = False
             self._set_kind(self._fp64_kind())
             self.Q = self.inv = None
-            return self.load(Yd, stats=self.stats.cpu().numpy())
+            return self.load(Yd, stats=self.stats.clone())
+
+    @staticmethod
+    def degenerate(stats):
+        """Host copy of ``stats`` -> True when the integer engine's result must be discarded: NaN/inf/constant
+        outputs keep the reference's NaN propagation through the FP64 engines."""
+        st = np.asarray(stats, dtype=np.float64)[:4]
+        return not (np.all(np.isfinite(st)) and st[1] > 0.0)
+
+    def digit_sums(self, w, count, rows_alloc=None):
+        """Integer engine: psum [rows_alloc >= count, nacc] float64 of this engine's rows for the multiplicity rows
+        w[count][Npad]; rows beyond ``count`` are zero (padding for the reduce-scatter)."""
+        rows_alloc = int(rows_alloc or count)
+        psum = rt.empty((rows_alloc, self.nacc), torch.float64)
+        if rows_alloc > count:
+            psum[count:].zero_()
+        work = rt.empty((int(_lib.lib().sa_digit_sums_workspace_bytes(self.N, self.nacc, self.ndigits,
+                                                                       int(count))),), torch.uint8)
+        ev = None
+        if self.kernel_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.call("sa_digit_sums_f64", rt.stream_ptr(), rt.ptr(self.Q), rt.ptr(self.inv), self.N, self.nacc,
+                  self.ndigits, rt.ptr(w), self.Npad, int(count), rt.ptr(work), int(work.numel()), rt.ptr(psum))
+        if ev is not None:
+            ev[1].record()
+            self.kernel_events.append((int(count), ev[0], ev[1]))
+        return psum
 
     def load_normalized(self, Yd):
         """Re-run only the normalise/re-layout step with the current ``self.stats``."""
@@ -476,18 +558,219 @@ def allgather_moments(local, world):
     return [(row[0], row[1:]) for row in everyone.cpu().numpy() if row[0] > 0]
 
 
+def _agree(values_max):
+    """One small all-reduce (MAX) + host read: quantities every rank must agree on before it issues collectives
+    (engine family, batch sizes).  Returns the agreed python ints; identity without a process group."""
+    rank, world = rt.world()
+    if world == 1:
+        return [int(v) for v in values_max]
+    import torch.distributed as dist
+
+    t = torch.tensor([int(v) for v in values_max], dtype=torch.int64,
+                     device=rt.device() if torch.cuda.is_available() else "cpu")   # "cpu": the gloo tests
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [int(v) for v in t.cpu().numpy()]
+
+
+def digits_batch(R, npad_max):
+    """Resamples per GEMM batch of the integer engine: about DIGITS_BATCH_BYTES of multiplicities, whole
+    256-resample tiles, batches of equal size.  Pure host logic."""
+    cap = max(256, DIGITS_BATCH_BYTES // max(int(npad_max), 1) // 256 * 256)
+    if R <= cap:
+        return max(R, 1)
+    nb = -(-R // cap)
+    return min(cap, -(-(-(-R // nb)) // 256) * 256)
+
+
+def _side_stream():
+    """Stream of the multiplicity draws that run beside the GEMM (the slim Philox kernel needs no priority: it
+    fits next to a GEMM CTA whichever kernel reaches an SM first)."""
+    return torch.cuda.Stream()
+
+
+def batch_share(n, count, world, g):
+    """Reduce-scatter bookkeeping of one batch of ``count`` rows (``n`` resamples + possibly the row of ones) over
+    ``world`` ranks: rank g keeps rows [lo, lo + chunk) of the batch, of which the first ``valid`` are resamples.
+    Pure host logic -> (chunk, lo, valid)."""
+    chunk = -(-count // world)
+    lo = g * chunk
+    return chunk, lo, max(0, min(n - lo, chunk))
+
+
+class _DigitsRows:
+    """The integer engine's analyze over base-row shards -- ONE code path for one GPU (a single shard that holds
+    all rows) and for a torch.distributed job (every rank holds a row range).
+
+    Per batch of resamples: multiplicities of the batch over every local row window (Philox or the reference's
+    own index matrix) -> exact integer GEMM against the window's digit matrix -> float64 partial sums
+    ``[count, nacc]`` -> (multi-GPU) reduce-scatter over resamples, so each rank runs the estimator algebra on its
+    share -> estimates.  Two multiplicity buffers alternate: while batch b is in the tensor cores, batch b+1 is
+    drawn on a side stream by the slim Philox kernel, which fits next to the persistent GEMM CTAs.  The point
+    estimate is the multiplicity row of ones appended to the last batch.  The CI is ``Z * std(ddof=1)`` over all
+    R estimates: two-pass on one GPU; across ranks two all-reduces of ``nest`` doubles (column sums, then squared
+    deviations) replace the all-gather of the estimates.  No host synchronisation before the final read-back.
+    """
+
+    def __init__(self, outputs, N, R, rs, npad_max, rank, world):
+        """outputs[o] = the engines (kind 6, ``row0`` set) of model output o, one per local row shard; all outputs
+        share the row shards (and therefore the multiplicities)."""
+        self.outputs, self.N, self.R, self.rs = outputs, int(N), int(R), rs
+        self.rank, self.world = rank, world
+        self.shards = outputs[0]
+        self.lead = outputs[0][0]
+        B = digits_batch(self.R, npad_max)
+        self.batches = [(c, min(c + B, self.R)) for c in range(0, self.R, B)] or [(0, 0)]
+        self.nbuf = 2 if len(self.batches) > 1 else 1
+        rows_buf = max(c1 - c0 for c0, c1 in self.batches) + 1
+        self.wsets = [[rt.empty((rows_buf * e.Npad,), torch.uint8) for e in self.shards] for _ in range(self.nbuf)]
+        self.main = torch.cuda.current_stream()
+        self.side = _side_stream()
+        self.side.wait_stream(self.main)     # cached blocks may still be read by earlier work on the main stream
+        self.drawn, self.gemm_done = {}, {}
+        self.draw(0, slim=False)             # the first batch is drawn while Y is uploaded / split into digits
+
+    def draw(self, b, slim):
+        c0, c1 = self.batches[b]
+        n = c1 - c0
+        last = b == len(self.batches) - 1
+        with torch.cuda.stream(self.side):
+            if b >= self.nbuf:               # the GEMM that read this buffer two batches ago
+                self.side.wait_event(self.gemm_done[b - self.nbuf])
+            for w, e in zip(self.wsets[b % self.nbuf], self.shards):
+                if self.rs is not None:
+                    self.rs.counts(c0, n, w, rows=(e.row0, e.N), slim=slim)
+                if last:                     # the point estimate: every row once
+                    w[n * e.Npad:(n + 1) * e.Npad].fill_(1)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.drawn[b] = ev
+
+    def abandon(self):
+        """Join the side stream before the buffers go back to the allocator (the engine fell back to FP64)."""
+        self.main.wait_stream(self.side)
+
+    def run(self, Z, keep):
+        """-> per output (point [nest], conf [nest], kept [R, 2Dg] or None) as device/host arrays."""
+        import torch.distributed as dist
+
+        lead, world, rank, R = self.lead, self.world, self.rank, self.R
+        nacc, nest, Dg = lead.nacc, lead.nest, lead.Dg
+        nout = len(self.outputs)
+        chunk_max = max(-(-(c1 - c0 + 1) // world) for c0, c1 in self.batches)
+        est_loc = [rt.empty((-(-R // world) + len(self.batches) + 2 * chunk_max, nest), torch.float64)
+                   for _ in range(nout)]
+        point = rt.zeros((nout, nest), torch.float64)
+        pos, ids = 0, []
+        pending = None
+
+        def finish(item):
+            nonlocal pos
+            b, n, count, chunk, sums, works = item
+            for work in works:
+                work.wait()                  # the current stream waits for the collective; the host does not
+            _, lo, valid = batch_share(n, count, world, rank)
+            for o, engs in enumerate(self.outputs):
+                engs[0]._finalize(sums[o], 1, chunk, self.N, est_loc[o][pos:pos + chunk])
+                if count > n and lo <= n < lo + chunk:          # the row of ones sits in this rank's share
+                    point[o].copy_(est_loc[o][pos + n - lo])
+            ids.append((self.batches[b][0] + lo, valid))
+            pos += valid
+
+        for b, (c0, c1) in enumerate(self.batches):
+            n = c1 - c0
+            count = n + (1 if b == len(self.batches) - 1 else 0)
+            if b + 1 < len(self.batches):
+                self.draw(b + 1, slim=True)
+            self.main.wait_event(self.drawn[b])
+            chunk = -(-count // world)
+            sums = []
+            for engs in self.outputs:
+                tot = None
+                for e, w in zip(engs, self.wsets[b % self.nbuf]):
+                    ps = e.digit_sums(w, count, rows_alloc=chunk * world)
+                    tot = ps if tot is None else tot.add_(ps)
+                sums.append(tot)
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.gemm_done[b] = ev
+            works = []
+            if world > 1:
+                # partial sums of all ranks' rows, scattered along the resample axis: rank g keeps rows
+                # [g * chunk, (g + 1) * chunk) of the batch
+                outs = []
+                for o in range(nout):
+                    out = rt.empty((chunk, nacc), torch.float64)
+                    works.append(dist.reduce_scatter_tensor(out.view(-1), sums[o].view(-1), async_op=True))
+                    outs.append(out)
+                sums_local = outs
+            else:
+                sums_local = sums
+            if pending is not None:
+                finish(pending)              # estimator algebra of the previous batch, behind this batch's GEMM
+            pending = (b, n, count, chunk, sums_local, works)
+        finish(pending)
+        self.main.wait_stream(self.side)     # never leave the side stream unjoined
+
+        confs = []
+        for o in range(nout):
+            if R == 0:
+                confs.append(torch.full((nest,), float("nan"), dtype=torch.float64, device=rt.device()))
+            elif world == 1:
+                confs.append(lead.conf(est_loc[o][:R], Z))
+            else:
+                mean = rt.empty((nest,), torch.float64)
+                _lib.call("sa_col_moment_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, 0, rt.ptr(mean))
+                dist.all_reduce(mean)
+                _lib.call("sa_conf_finish_f64", rt.stream_ptr(), rt.ptr(mean), nest, 1.0 / R, 0.0, R, 0)
+                ss = rt.empty((nest,), torch.float64)
+                _lib.call("sa_col_moment_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, rt.ptr(mean),
+                          rt.ptr(ss))
+                dist.all_reduce(ss)
+                _lib.call("sa_conf_finish_f64", rt.stream_ptr(), rt.ptr(ss), nest, 1.0, float(Z), R, 1)
+                confs.append(ss)
+        # heavy-tail guard: values near the design's largest |x|, over all local shards (and ranks)
+        self.guard = torch.stack([torch.stack([e.inv[e.nacc] for e in engs]).sum() for engs in self.outputs])
+        if world > 1:
+            dist.all_reduce(point)           # zero everywhere but on the rank that owned the row of ones
+            dist.all_reduce(self.guard)
+        kept = [None] * nout
+        if keep:
+            for o in range(nout):
+                if world == 1:
+                    kept[o] = est_loc[o][:R, :2 * Dg].cpu().numpy()
+                    continue
+                rows_max = -(-R // world) + len(self.batches)
+                mine = torch.zeros((rows_max, 2 * Dg), dtype=torch.float64, device=rt.device())
+                mine[:pos] = est_loc[o][:pos, :2 * Dg]
+                everyone = torch.empty((world * rows_max, 2 * Dg), dtype=torch.float64, device=rt.device())
+                dist.all_gather_into_tensor(everyone, mine)
+                everyone = everyone.cpu().numpy().reshape(world, rows_max, 2 * Dg)
+                full = np.zeros((R, 2 * Dg))
+                for g in range(world):       # the same bookkeeping as finish(), for every rank
+                    at = 0
+                    for c0, c1 in self.batches:
+                        n = c1 - c0
+                        _, lo, valid = batch_share(n, n + (1 if c1 == R else 0), world, g)
+                        full[c0 + lo:c0 + lo + valid] = everyone[g, at:at + valid]
+                        at += valid
+                kept[o] = full
+        return [(point[o], confs[o], kept[o]) for o in range(nout)]
+
+
 def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resamples=100, conf_level=0.95,
                         keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
                         kernel_events=None):
-    """``analyze`` for a model output partitioned by base-row range ("when Y exceeds one GPU").
+    """``analyze`` for a model output partitioned by base-row range ("when Y exceeds one GPU") --
+    and the route of the integer engine in general (one GPU = one shard with every row).
 
     ``shards``: the ``(row0, Y_local)`` pieces this process holds, ``Y_local`` = the ``n_local*step`` outputs
     of base rows ``[row0, row0+n_local)`` (host or CUDA); over all ranks of the torch.distributed job the
     pieces tile ``[0, N)``.  Every rank walks all resamples over its own rows: the multiplicity kernels
     keep the draws that land in the shard's row window, the accumulate kernels produce partial sums
-    ``[count, nacc]``, one all-reduce per batch adds them across ranks, and the estimator algebra runs on
-    the totals -- the all-reduce of partial sums replaces the all-gather of estimates of the resample-sharded
-    path.  Statistics for the normalisation come from per-shard moments combined by ``combine_moments``.
+    ``[count, nacc]``, which are added across ranks (integer engine: reduce-scatter, see ``_DigitsRows``; FP64
+    engines: all-reduce) before the estimator algebra.  Statistics for the normalisation come from per-shard
+    moments combined on the device (``sa_combine_moments_f64``).  Engine family, batch sizes and the seedless
+    resample key are agreed across ranks before any collective is issued.
     """
     import torch.distributed as dist
 
@@ -498,22 +781,32 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         raise RuntimeError("Confidence level must be between 0-1.")
     rt.require_cuda()
     rank, world = rt.world() if distributed else (0, 1)
+    R_req = np.shape(r)[1] if r is not None else int(num_resamples)
 
-    engines, local = [], []
-    for row0, Y in shards:
-        size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
-        if size % step or size == 0:
-            raise RuntimeError("row shard size is not a multiple of the Saltelli block length")
-        eng = SobolAnalyzer(Dg, size // step, c2, algo=algo,
-                            resamples=np.shape(r)[1] if r is not None else num_resamples, total_rows=N)
-        if eng.kind == 6 and N > 1 << 24:
-            raise ValueError("the integer engine is exact up to 2^24 base rows per resample; use algo='fp64'")
-        eng.kernel_events = kernel_events
-        eng.row0 = int(row0)
-        engines.append(eng)
+    def build(algo_):
+        engs = []
+        for row0, Y in shards:
+            size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+            if size % step or size == 0:
+                raise RuntimeError("row shard size is not a multiple of the Saltelli block length")
+            eng = SobolAnalyzer(Dg, size // step, c2, algo=algo_, resamples=R_req, total_rows=N)
+            if eng.kind == 6 and N > 1 << 24:
+                raise ValueError("the integer engine is exact up to 2^24 base rows per resample; use algo='fp64'")
+            eng.kernel_events = kernel_events
+            eng.row0 = int(row0)
+            engs.append(eng)
+        return engs
+
+    engines = build(algo)
+    # every rank must take the same engine family and the same batches: one tiny all-reduce
+    not_digits, npad_max = _agree([0 if all(e.kind == 6 for e in engines) else 1, max(e.Npad for e in engines)])
+    if not_digits and any(e.kind == 6 for e in engines):
+        engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
+    digits = not not_digits
     rows_here = sum(e.N for e in engines)
+    if world == 1 and rows_here != N:        # with several ranks the count is checked on the combined moments
+        raise RuntimeError(f"row shards hold {rows_here} base rows, expected {N}")
     lead = engines[0]
-    big = max(engines, key=lambda e: e.Npad)
     Z = norm.ppf(0.5 + conf_level / 2)
 
     if r is not None:
@@ -523,25 +816,95 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         R = rs.R
     else:
         R = int(num_resamples)
-        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
-    # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of the shards
-    prefetch = None
-    if R > 0 and rs.mode == "philox":
-        prefetch = _CountsPrefetch(rs, big._batches(0, R)[0], [(e.Npad, (e.row0, e.N)) for e in engines])
+        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE, distributed=distributed) if R > 0 else None
 
+    pipe = prefetch = None
+    if digits:
+        pipe = _DigitsRows([engines], N, R, rs, npad_max, rank, world)      # starts drawing batch 0 right away
+    elif R > 0 and rs.mode == "philox":
+        # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of the shards
+        first = plan_batches(lead.kind, 0, R, npad_max, lead.sms, groups=lead.groups)[0]
+        prefetch = _CountsPrefetch(rs, first, [(e.Npad, (e.row0, e.N)) for e in engines])
+
+    # moments of the whole design: per-shard records -> all-gather -> combined on the device (no host round trip)
     loaded = []
-    for eng, (_, Y) in zip(engines, shards):
-        Yd = rt.to_device(Y, torch.float64).reshape(-1)
+    parts = rt.zeros((len(engines), 9), torch.float64)
+    for i, (eng, (_, Y)) in enumerate(zip(engines, shards)):
+        Yd = rt.to_device(Y, torch.float64, non_blocking=True).reshape(-1)
         eng.moments(Yd)
         loaded.append(Yd)
-        local.append((float(Yd.numel()), eng.stats.cpu().numpy().copy()))
-    parts = allgather_moments(local, world)
-    if int(round(sum(c for c, _ in parts))) != N * step:
-        raise RuntimeError(f"row shards hold {int(sum(c for c, _ in parts)) // step} base rows, expected {N}")
-    stats = combine_moments(parts)
-    for eng, Yd in zip(engines, loaded):
-        eng.load(Yd, stats=stats)
+        parts[i, 0] = float(Yd.numel())
+        parts[i, 1:].copy_(eng.stats)
+    if world > 1:
+        nsh = _agree([len(engines)])[0]
+        mine = rt.zeros((nsh, 9), torch.float64)
+        mine[:len(engines)] = parts
+        parts = rt.empty((world * nsh, 9), torch.float64)
+        dist.all_gather_into_tensor(parts, mine)
+    if world > 1 or len(engines) > 1:
+        stats9 = rt.empty((9,), torch.float64)
+        _lib.call("sa_combine_moments_f64", rt.stream_ptr(), rt.ptr(parts), int(parts.shape[0]), rt.ptr(stats9))
+        for eng, Yd in zip(engines, loaded):
+            eng.load(Yd, stats=stats9)
+    else:
+        stats9 = None
+        lead.load(loaded[0], stats=lead.stats)      # the moments are already there
     del loaded
+
+    def again_fp64():
+        return analyze_row_sharded(problem, shards, N, calc_second_order=calc_second_order,
+                                   num_resamples=num_resamples, conf_level=conf_level,
+                                   keep_resamples=keep_resamples, seed=seed, resample=resample, r=r, algo="fp64",
+                                   distributed=distributed, kernel_events=kernel_events)
+
+    if digits and not all(e.kind == 6 for e in engines):
+        # the feature kernels refused the shape (a function of Dg and the order only, so every rank lands here)
+        pipe.abandon()
+        return again_fp64()
+    if digits:
+        (point, conf, kept), = pipe.run(Z, bool(keep_resamples))
+        flag = rs.flag if rs is not None else None
+    else:
+        point, conf, kept, flag = _row_sharded_fp64(engines, N, R, rs, Z, bool(keep_resamples), npad_max, prefetch,
+                                                    world)
+
+    # one read-back: results, statistics, flags
+    point_h, conf_h = point.reshape(-1).cpu().numpy(), conf.cpu().numpy()
+    stats = lead.stats.cpu().numpy()
+    if stats9 is not None:
+        total = int(round(float(stats9.cpu().numpy()[8])))
+        if total != N * step:
+            raise RuntimeError(f"row shards hold {total // step} base rows, expected {N}")
+    if flag is not None:
+        _Resampler.raise_for(int(flag.item()))
+    guard = float(pipe.guard.cpu().numpy()[0]) if digits else None
+    if digits and lead.auto_digits and (SobolAnalyzer.degenerate(stats) or guard <= GUARD_MIN_ROWS * step):
+        # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
+        # an outlier row: the FP64 engines keep every row's own exponent (GUARD_MIN_ROWS)
+        return again_fp64()
+
+    const_y = not (stats[4] < stats[5])
+    if const_y:
+        warn(CONST_RESULT_MSG)
+    keep = bool(keep_resamples)
+    if keep and kept is None:
+        kept = np.zeros((0, 2 * Dg))
+    S = _assemble(Dg, c2, keep, point_h, conf_h, kept, const_y)
+    S.problem = problem
+    S.to_df = MethodType(to_df, S)
+    S.rows_here = rows_here
+    S.engine = ENGINE_NAMES[lead.kind]
+    S.resample_mode = rs.mode if rs is not None else None
+    S.digits_guard = guard
+    return S
+
+
+def _row_sharded_fp64(engines, N, R, rs, Z, keep, npad_max, prefetch, world):
+    """Row shards through the FP64 engines: partial sums of every batch are all-reduced, then the estimator
+    algebra runs on the totals on every rank.  Returns (point, conf, kept, flag) on the device / host."""
+    import torch.distributed as dist
+
+    lead = engines[0]
 
     def totals(ws, count, est_out):
         tot = rt.zeros((count * lead.nacc,), torch.float64)
@@ -556,15 +919,13 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         lead._finalize(tot, 1, count, N, est_out)
 
     point = rt.empty((1, lead.nest), torch.float64)
-    # integer engine: the point estimate (a multiplicity row of ones) rides in the first batch's GEMM
-    fuse = R > 0 and all(e.kind == 6 for e in engines)
-    if not fuse:
-        totals([None] * len(engines), 1, point)
+    totals([None] * len(engines), 1, point)
     est = None
     if R > 0:
         est = rt.empty((R, lead.nest), torch.float64)
         wbuf = {}
-        for c0, c1 in big._batches(0, R):
+        # batches from quantities every rank shares (the largest shard of the job), not from this rank's shard
+        for c0, c1 in plan_batches(lead.kind, 0, R, npad_max, lead.sms, groups=lead.groups):
             n = c1 - c0
             ws = prefetch.take(c0, n) if prefetch is not None else None
             if ws is not None:
@@ -575,37 +936,17 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
                     if i not in wbuf or wbuf[i].numel() < (n + 1) * eng.Npad:
                         wbuf[i] = rt.empty(((n + 1) * eng.Npad,), torch.uint8)
                     rs.counts(c0, n, wbuf[i], rows=(eng.row0, eng.N))
-                    if fuse:
-                        wbuf[i][n * eng.Npad:(n + 1) * eng.Npad].fill_(1)
                     ws.append(wbuf[i])
-            if fuse:
-                ext = rt.empty((n + 1, lead.nest), torch.float64)
-                totals(ws, n + 1, ext)
-                est[c0:c1] = ext[:n]
-                point.copy_(ext[n:n + 1])
-                fuse = False
-            else:
-                totals(ws, n, est[c0:c1])
+            totals(ws, n, est[c0:c1])
         if prefetch is not None:
             torch.cuda.current_stream().wait_event(prefetch.done)
         conf = lead.conf(est, Z)
-        rs.check()
     else:
         conf = torch.full((lead.nest,), float("nan"), dtype=torch.float64, device=point.device)
-
-    const_y = not (stats[4] < stats[5])
-    if const_y:
-        warn(CONST_RESULT_MSG)
-    keep = bool(keep_resamples)
     kept = None
     if keep:
-        kept = est[:, :2 * Dg].cpu().numpy() if est is not None else np.zeros((0, 2 * Dg))
-    S = _assemble(Dg, c2, keep, point[0].cpu().numpy(), conf.cpu().numpy(), kept, const_y)
-    S.problem = problem
-    S.to_df = MethodType(to_df, S)
-    S.rows_here = rows_here
-    S.engine = ENGINE_NAMES[lead.kind]
-    return S
+        kept = est[:, :2 * lead.Dg].cpu().numpy() if est is not None else None
+    return point, conf, kept, (rs.flag if rs is not None else None)
 
 
 def _assemble(Dg, c2, keep, point, conf, est_all, const_y):
@@ -656,7 +997,8 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
     (host or CUDA).  All outputs share one resample draw -- with a ``seed`` that is exactly what the
     reference's per-output calls produce (``ProblemSpec.analyze``, util/problem.py:368-371, re-seeds each
     call); without a seed the reference would redraw per output, which is statistically equivalent.
-    Returns a list of ResultDicts."""
+    Returns a list of ResultDicts.  In a torch.distributed job the resamples are sharded by resample id and the
+    estimates all-gathered (the row-sharded route of the integer engine is ``analyze_device(shard="rows")``)."""
     _, Dg = extract_group_names(problem)
     sizes = {int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y)) for Y in Ys}
     if len(sizes) != 1:
@@ -666,12 +1008,21 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         raise RuntimeError("Confidence level must be between 0-1.")
 
     rt.require_cuda()
-    engines = []
-    for Y in Ys:
-        eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo,
-                            resamples=np.shape(r)[1] if r is not None else num_resamples)
-        eng.kernel_events = kernel_events
-        engines.append(eng)
+    rank, world = rt.world() if distributed else (0, 1)
+    R_req = np.shape(r)[1] if r is not None else int(num_resamples)
+
+    def build(algo_):
+        engs = []
+        for _ in Ys:
+            eng = SobolAnalyzer(Dg, N, calc_second_order, algo=algo_, resamples=R_req)
+            eng.kernel_events = kernel_events
+            eng.row0 = 0
+            engs.append(eng)
+        return engs
+
+    engines = build(algo)
+    if world > 1 and _agree([0 if all(e.kind == 6 for e in engines) else 1])[0] and any(e.kind == 6 for e in engines):
+        engines = build("fp64")             # ranks must issue the same collectives: one engine family for all
     Z = norm.ppf(0.5 + conf_level / 2)
 
     if r is not None:
@@ -681,74 +1032,119 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         R = rs.R
     else:
         R = int(num_resamples)
-        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE) if R > 0 else None
-    rank, world = rt.world() if distributed else (0, 1)
+        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE, distributed=distributed) if R > 0 else None
+
+    def again_fp64():
+        return analyze_outputs(problem, Ys, calc_second_order=calc_second_order, num_resamples=num_resamples,
+                               conf_level=conf_level, keep_resamples=keep_resamples, seed=seed, resample=resample,
+                               r=r, algo="fp64", distributed=distributed, kernel_events=kernel_events)
+
+    keep = bool(keep_resamples)
+    # one GPU + integer engine: the pipelined row route with a single shard that holds every row
+    pipe = None
+    if world == 1 and all(e.kind == 6 for e in engines):
+        pipe = _DigitsRows([[e] for e in engines], N, R, rs, engines[0].Npad, 0, 1)
     lo, hi = rt.shard_range(R, rank, world)
     # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of Y
     prefetch = None
-    if hi > lo and rs.mode == "philox":
+    if pipe is None and hi > lo and rs.mode == "philox":
         prefetch = _CountsPrefetch(rs, engines[0]._batches(lo, hi)[0], [(engines[0].Npad, None)])
 
     for eng, Y in zip(engines, Ys):
         # multi-GPU: a host Y is uploaded as one shard per rank and all-gathered over NVLink
-        Yd = rt.to_device_sharded(Y, torch.float64) if distributed else rt.to_device(Y, torch.float64)
+        Yd = rt.to_device_sharded(Y, torch.float64) if world > 1 else rt.to_device(Y, torch.float64, non_blocking=True)
         eng.load(Yd.reshape(-1))
 
-    points = []
-    ests = [None] * len(engines)
-    if hi > lo:
-        ests = bootstrap_shared(engines, rs, lo, hi, prefetch, points)
-    if not points:
-        points = [eng.point() for eng in engines]
-    if R > 0:
-        if hi <= lo:
-            ests = bootstrap_shared(engines, rs, lo, hi, prefetch)
-        if world > 1:
-            ests = [allgather_estimates(e, R, rank, world) for e in ests]
-        confs = [eng.conf(e, Z) for eng, e in zip(engines, ests)]
+    if pipe is not None:
+        if not all(e.kind == 6 for e in engines):     # the feature kernels refused the shape
+            pipe.abandon()
+            return again_fp64()
+        res = pipe.run(Z, keep)
+        points = [p.reshape(1, -1) for p, _, _ in res]
+        confs = [c for _, c, _ in res]
+        kepts = [k for _, _, k in res]
+        guards = pipe.guard.cpu().numpy()
     else:
-        confs = [torch.full((eng.nest,), float("nan"), dtype=torch.float64, device=points[0].device)
-                 for eng in engines]
-    if rs is not None:
-        rs.check()
+        points = []
+        ests = [None] * len(engines)
+        if hi > lo:
+            ests = bootstrap_shared(engines, rs, lo, hi, prefetch, points)
+        if not points:
+            points = [eng.point() for eng in engines]
+        if R > 0:
+            if hi <= lo:
+                ests = bootstrap_shared(engines, rs, lo, hi, prefetch)
+            if world > 1:
+                ests = [allgather_estimates(e, R, rank, world) for e in ests]
+            confs = [eng.conf(e, Z) for eng, e in zip(engines, ests)]
+        else:
+            confs = [torch.full((eng.nest,), float("nan"), dtype=torch.float64, device=points[0].device)
+                     for eng in engines]
+        kepts = [None] * len(engines)
+        if keep:
+            kepts = [est[:, :2 * Dg].cpu().numpy() if est is not None else None for est in ests]
 
-    keep = bool(keep_resamples)
     out = []
-    for eng, point, est, conf in zip(engines, points, ests, confs):
+    step = 2 * Dg + 2 if calc_second_order else Dg + 2
+    for o, (eng, point, conf, kept) in enumerate(zip(engines, points, confs, kepts)):
+        point_h, conf_h = point[0].cpu().numpy(), conf.cpu().numpy()
         stats = eng.stats.cpu().numpy()
+        guard = float(guards[o]) if pipe is not None else None
+        if eng.kind == 6 and eng.auto_digits and (SobolAnalyzer.degenerate(stats)
+                                                  or (guard is not None and guard <= GUARD_MIN_ROWS * step)):
+            # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
+            # an outlier row: the FP64 engines keep every row's own exponent (GUARD_MIN_ROWS)
+            return again_fp64()
         # ptp([A;B]) == 0 -- or a constant Y, whose normalisation is 0/0 (tested outcome is zeros)
         const_y = not (stats[4] < stats[5])
         if const_y:
             warn(CONST_RESULT_MSG)
-        kept = None
-        if keep:
-            kept = est[:, :2 * Dg].cpu().numpy() if est is not None else np.zeros((0, 2 * Dg))
-        S = _assemble(Dg, bool(calc_second_order), keep, point[0].cpu().numpy(), conf.cpu().numpy(), kept, const_y)
+        if keep and kept is None:
+            kept = np.zeros((0, 2 * Dg))
+        S = _assemble(Dg, bool(calc_second_order), keep, point_h, conf_h, kept, const_y)
         S.problem = problem
         S.to_df = MethodType(to_df, S)
         S.engine = ENGINE_NAMES[eng.kind]
+        S.resample_mode = rs.mode if rs is not None else None
+        S.digits_guard = guard
         out.append(S)
+    if rs is not None:
+        rs.check()
     return out
 
 
 def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_level=0.95,
                    keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
-                   kernel_events=None, shard="resamples"):
+                   kernel_events=None, shard="auto"):
     """``analyze`` with the device knobs exposed.
 
     Y may be a host ndarray or a CUDA tensor.  ``resample``: "numpy" | "philox" | "auto" (default: module
     ``RESAMPLE_MODE``); ``r``: explicit int [N, R] index matrix (overrides ``resample``/``seed``);
-    ``algo``: "auto" | "fp64" | "digits", or one kernel ("generic" | "tile8" | "gemv" | "dmma"); ``distributed``: shard the
-    resamples over the initialised torch.distributed job; ``shard``: "resamples" (default: every rank holds
-    Y, resample ids are split) or "rows" (every rank keeps only its base-row range of Y and all resamples'
-    partial sums are all-reduced -- ``analyze_row_sharded``).
+    ``algo``: "auto" | "fp64" | "digits", or one kernel ("generic" | "tile8" | "gemv" | "dmma"); ``distributed``:
+    use the initialised torch.distributed job; ``shard``: "resamples" (every rank holds Y, resample ids are split,
+    estimates all-gathered), "rows" (every rank keeps only its base-row range of Y and the partial sums of all
+    resamples are reduced -- ``analyze_row_sharded``) or "auto": rows when the ranks agree that the integer engine
+    applies to their row range (everything it does shrinks with the rows a rank holds), resamples otherwise --
+    the strategy switch the reference makes inside ``analyze`` (analyze/sobol.py:147,183).
     """
+    rank, world = rt.world() if distributed else (0, 1)
+    if shard == "auto":
+        shard = "resamples"
+        if world > 1:
+            _, Dg = extract_group_names(problem)
+            size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
+            N = _n_from_size(size, Dg, calc_second_order)
+            lo, hi = rt.shard_range(N, rank, world)
+            R_req = np.shape(r)[1] if r is not None else int(num_resamples)
+            mine = hi > lo and SobolAnalyzer(Dg, hi - lo, calc_second_order, algo=algo, resamples=R_req,
+                                             total_rows=N).kind == 6
+            if not _agree([0 if mine else 1])[0]:
+                shard, algo = "rows", "digits"
     if shard == "rows":
         _, Dg = extract_group_names(problem)
         size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
         N = _n_from_size(size, Dg, calc_second_order)
         step = size // N
-        rank, world = rt.world() if distributed else (0, 1)
         lo, hi = rt.shard_range(N, rank, world)
         flat = Y.reshape(-1)
         return analyze_row_sharded(problem, [(lo, flat[lo * step:hi * step])], N,
@@ -779,7 +1175,11 @@ def analyze(
 
     Same contract as ``SALib.analyze.sobol.analyze``.  ``parallel`` / ``n_processors`` (the reference's
     CPU process pool, analyze/sobol.py:183-194) are accepted and ignored: the GPU path is always the
-    serial path's arithmetic, sharded over GPUs when torch.distributed is initialised.
+    serial path's arithmetic.  Like the reference, which switches between its serial loop and its pool inside
+    this function (:147,183), the decomposition is chosen here: one GPU, or -- when torch.distributed is
+    initialised -- base-row shards (integer engine) or resample-id shards (FP64 engines) over the ranks.
+    With a ``seed`` the resample indices are the reference's own (``default_rng(seed).integers``) for every
+    problem whose index matrix the reference could draw (up to 2^31 draws); see the module docstring.
     """
     S = analyze_device(problem, Y, calc_second_order=calc_second_order, num_resamples=num_resamples,
                        conf_level=conf_level, keep_resamples=keep_resamples, seed=seed)

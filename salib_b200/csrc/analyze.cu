@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "counts.cuh"
 
 namespace sa {
 
@@ -234,28 +235,6 @@ counts_from_indices_kernel(const int64_t *__restrict__ r, uint64_t N, uint64_t R
   }
 }
 
-// Philox4x32-10 (Salmon et al. 2011), counter-based: 128-bit counter, 64-bit key.
-struct Philox4 {
-  uint32_t x, y, z, w;
-};
-__host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int round = 0; round < 10; ++round) {
-    const uint64_t p0 = (uint64_t)M0 * c0;
-    const uint64_t p1 = (uint64_t)M1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n1 = (uint32_t)p1;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-    const uint32_t n3 = (uint32_t)p0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0;
-    k1 += W1;
-  }
-  return Philox4{c0, c1, c2, c3};
-}
-
 // Draw t of resample c: u64 = philox(counter = (t/2, c), key = seed) word pair (t & 1);
 // index = floor(u64 * N / 2^64).
 __global__ void __launch_bounds__(256)
@@ -279,151 +258,22 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t row0, uint
   }
 }
 
-// Same distribution without global atomics (the kernel above is bound by the L2 RED rate, 2.2e11/s).
-// The N draws of a resample are a multinomial over the rows; a multinomial splits exactly: the number of
-// draws that land in the left half of a row range holding n draws is Binomial(n, 1/2) -- the popcount of n
-// random bits -- and the draws inside a range are iid uniform over it.  One block owns one resample: it
-// walks L levels of that tree in shared memory (N random bits per level) down to windows of W = N / 2^L
-// <= 32768 rows, then fills one window at a time: n_w uniform draws into a W-byte shared-memory
-// histogram (shared atomics), copied out as coalesced words.  Philox counters are keyed by (seed,
-// resample id, tree node | window, word), so the multiplicities of a resample do not depend on the batch,
-// the GPU or the row window it is generated for.  Requires 2^L | N (N <= 32768: L = 0, any N).
-constexpr int kWinMax = 32768;
+// Same distribution without global atomics (the kernel above is bound by the L2 RED rate, 2.2e11/s): the
+// binomial split tree + window histograms of counts.cuh, one block per resample.
+// Two launch shapes: "wide" -- 256 threads, one block per resample, up to 8 blocks per SM (fastest when the GPU is
+// otherwise idle) -- and "slim" -- one block of 1024 threads per SM looping over resamples with a single 16 KB
+// window: it always fits NEXT TO a CTA of the persistent GEMM kernel (198 KB of shared memory, 192 threads), so
+// the next batch's multiplicities are drawn on a side stream while the tensor cores work on the current batch.
 constexpr int kWinThreads = 256;
+constexpr int kWinThreadsSlim = 1024;
 
-__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *scratch) {
-  v = __reduce_add_sync(kFull, v);
-  __syncthreads();
-  if (threadIdx.x == 0) *scratch = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && v) atomicAdd(scratch, v);
-  __syncthreads();
-  return *scratch;
-}
-
-// popcount of the first min(128, n - 128*word) bits of the 128-bit Philox block `word` of tree node (level, j)
-__device__ __forceinline__ uint32_t tree_bits(uint32_t k0, uint32_t k1, uint64_t c, int level, uint32_t j,
-                                              uint32_t word, uint32_t n) {
-  const Philox4 p = philox4x32_10(word, 0x80000000u | ((uint32_t)level << 20) | j, (uint32_t)c,
-                                  (uint32_t)(c >> 32), k0, k1);
-  const uint32_t left = n - (word << 7);
-  uint32_t v[4] = {p.x, p.y, p.z, p.w};
-  uint32_t s = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t lo = 32u * q;
-    if (left >= lo + 32) s += __popc(v[q]);
-    else if (left > lo) s += __popc(v[q] & ((1u << (left - lo)) - 1u));
-  }
-  return s;
-}
-
-__global__ void __launch_bounds__(kWinThreads)
-counts_window_kernel(uint64_t seed, uint64_t N, uint64_t c0, int L, uint64_t row0, uint64_t nrows,
+template <int NT>
+__global__ void __launch_bounds__(NT)
+counts_window_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t count, int L, uint64_t row0, uint64_t nrows,
                      uint64_t Npad, uint8_t *__restrict__ w) {
   extern __shared__ __align__(16) uint32_t wsm[];
-  const uint32_t W = (uint32_t)(N >> L);
-  uint32_t *hist = wsm;                       // W bytes (rounded up to words)
-  uint32_t *heap = wsm + ((W + 3) >> 2) + 1;  // heap[k]: draws in node k (root 1, children 2k, 2k+1)
-  uint32_t *scratch = wsm + ((W + 3) >> 2);
-  const uint64_t c = c0 + blockIdx.x;
-  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) heap[1] = (uint32_t)N;
-  __syncthreads();
-  for (int l = 0; l < L; ++l) {
-    const uint32_t nodes = 1u << l;
-    if (nodes < kWinThreads / 32) {
-      for (uint32_t j = 0; j < nodes; ++j) {
-        const uint32_t n = heap[nodes + j];
-        const uint32_t words = (n + 127) >> 7;
-        uint32_t sum = 0;
-        for (uint32_t wd = tid; wd < words; wd += kWinThreads) sum += tree_bits(k0, k1, c, l, j, wd, n);
-        sum = block_sum_u32(sum, scratch);
-        if (tid == 0) {
-          heap[2 * (nodes + j)] = sum;
-          heap[2 * (nodes + j) + 1] = n - sum;
-        }
-        __syncthreads();
-      }
-    } else {
-      for (uint32_t j = warp; j < nodes; j += kWinThreads / 32) {
-        const uint32_t n = heap[nodes + j];
-        const uint32_t words = (n + 127) >> 7;
-        uint32_t sum = 0;
-        for (uint32_t wd = lane; wd < words; wd += 32) sum += tree_bits(k0, k1, c, l, j, wd, n);
-        sum = __reduce_add_sync(kFull, sum);
-        if (lane == 0) {
-          heap[2 * (nodes + j)] = sum;
-          heap[2 * (nodes + j) + 1] = n - sum;
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  const bool pow2 = (W & (W - 1)) == 0;
-  const int shift16 = 16 - (31 - __clz(W));  // W = 2^b, b <= 15: index = 16-bit field >> (16 - b)
-  const uint32_t nwin = 1u << L;
-  const uint32_t win_lo = (uint32_t)(row0 / W), win_hi = (uint32_t)((row0 + nrows - 1) / W);
-  uint8_t *wrow = w + (uint64_t)blockIdx.x * Npad;
-  for (uint32_t v = win_lo; v <= win_hi && v < nwin; ++v) {
-    const uint32_t n = heap[nwin + v];
-    for (uint32_t k = tid; k < ((W + 3) >> 2); k += kWinThreads) hist[k] = 0;
-    __syncthreads();
-    if (pow2) {
-      const uint32_t calls = (n + 7) >> 3;
-      for (uint32_t q = tid; q < calls; q += kWinThreads) {
-        const Philox4 p = philox4x32_10(q, 0x40000000u | v, (uint32_t)c, (uint32_t)(c >> 32), k0, k1);
-        const uint32_t f[4] = {p.x, p.y, p.z, p.w};
-        const uint32_t left = n - (q << 3);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          if ((uint32_t)d < left) {
-            const uint32_t idx = ((f[d >> 1] >> (16 * (d & 1))) & 0xffffu) >> shift16;
-            atomicAdd(hist + (idx >> 2), 1u << (8u * (idx & 3)));
-          }
-        }
-      }
-    } else {
-      const uint32_t calls = (n + 1) >> 1;
-      for (uint32_t q = tid; q < calls; q += kWinThreads) {
-        const Philox4 p = philox4x32_10(q, 0x40000000u | v, (uint32_t)c, (uint32_t)(c >> 32), k0, k1);
-        const uint32_t i0 = (uint32_t)__umul64hi(((uint64_t)p.y << 32) | p.x, (uint64_t)W);
-        atomicAdd(hist + (i0 >> 2), 1u << (8u * (i0 & 3)));
-        if (2 * q + 1 < n) {
-          const uint32_t i1 = (uint32_t)__umul64hi(((uint64_t)p.w << 32) | p.z, (uint64_t)W);
-          atomicAdd(hist + (i1 >> 2), 1u << (8u * (i1 & 3)));
-        }
-      }
-    }
-    __syncthreads();
-    // rows [lo, lo+W) of the window, clipped to the caller's row range, -> wrow[row - row0]
-    const uint64_t lo = (uint64_t)v * W;
-    const uint32_t r0 = (uint32_t)(row0 > lo ? row0 - lo : 0);
-    const uint32_t r1 = (uint32_t)((row0 + nrows < lo + W) ? row0 + nrows - lo : W);
-    const int64_t dst0 = (int64_t)lo - (int64_t)row0;  // destination of window row 0
-    if (((dst0 | (int64_t)r0) & 3) == 0) {
-      uint32_t *dw = reinterpret_cast<uint32_t *>(wrow + dst0);
-      const uint32_t full = r1 >> 2;
-      for (uint32_t k = (r0 >> 2) + tid; k < full; k += kWinThreads) dw[k] = hist[k];
-      const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
-      for (uint32_t r = (full << 2) + tid; r < r1; r += kWinThreads) wrow[dst0 + r] = hb[r];
-    } else {
-      const uint8_t *hb = reinterpret_cast<const uint8_t *>(hist);
-      for (uint32_t r = r0 + tid; r < r1; r += kWinThreads) wrow[dst0 + (int64_t)r] = hb[r];
-    }
-    __syncthreads();
-  }
-}
-
-// levels of the split tree for N rows; -1 if the window scheme does not apply (2^L does not divide N)
-static int window_levels(uint64_t N) {
-  int L = 0;
-  while ((N >> L) > (uint64_t)kWinMax) ++L;
-  if (L > 16 || (N & ((1ull << L) - 1)) != 0) return -1;
-  return L;
+  for (uint64_t i = blockIdx.x; i < count; i += gridDim.x)
+    counts_window_resample<NT, 0>(wsm, seed, c0 + i, N, L, row0, nrows, w + i * Npad, (int)threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1520,6 +1370,107 @@ conf_kernel(const double *__restrict__ est, uint64_t R, int ncols, double z, dou
   }
 }
 
+// out[q] = sum_i (F[i][q] - center[q])^2 over the rows of the chunked feature matrix (q < ncols): the second pass of
+// a two-pass standard deviation (np.std of analyze/dgsm.py:109).  One block per column, fixed-order reduction.
+__global__ void __launch_bounds__(256)
+feature_centered_ss_kernel(const double *__restrict__ F, uint64_t N, int nfeat, const double *__restrict__ center,
+                           double *__restrict__ out) {
+  __shared__ double sh[8];
+  const int q = blockIdx.x;
+  const int CW = chunk_width(nfeat);
+  const double *col = F + (uint64_t)(q / CW) * N * CW + (q % CW);
+  const double c = center[q];
+  double s = 0.0;
+  for (uint64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const double d = col[i * (uint64_t)CW] - c;
+    s = fma(d, d, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    out[q] = t;
+  }
+}
+
+// The two passes of conf_kernel as separate column reductions, for estimates that are spread over ranks:
+//   power 1: out[col] = sum_r est[r][col]                     (all-reduced, / R -> mean)
+//   power 2: out[col] = sum_r (est[r][col] - mean[col])^2     (all-reduced -> conf_finish_kernel)
+__global__ void __launch_bounds__(512)
+col_moment_kernel(const double *__restrict__ est, uint64_t R, int ncols, const double *__restrict__ mean,
+                  double *__restrict__ out) {
+  __shared__ double sh[16][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int ty = threadIdx.y;
+  double s = 0.0;
+  if (col < ncols) {
+    if (mean == nullptr) {
+      for (uint64_t c = ty; c < R; c += 16) s += est[c * (uint64_t)ncols + col];
+    } else {
+      const double m = mean[col];
+      for (uint64_t c = ty; c < R; c += 16) {
+        const double d = est[c * (uint64_t)ncols + col] - m;
+        s = fma(d, d, s);
+      }
+    }
+  }
+  sh[ty][threadIdx.x] = s;
+  __syncthreads();
+  if (ty == 0 && col < ncols) {
+    double t = 0.0;
+    for (int q = 0; q < 16; ++q) t += sh[q][threadIdx.x];
+    out[col] = t;
+  }
+}
+
+// x[col] = x[col] * scale   or   x[col] = z * sqrt(x[col] / (R - 1))  (the last step of the CI)
+__global__ void __launch_bounds__(256)
+conf_finish_kernel(double *__restrict__ x, int ncols, double scale, double z, uint64_t R, int finish) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  x[col] = finish ? z * sqrt(x[col] / (double)(R - 1)) : x[col] * scale;
+}
+
+// Statistics of the union of k row shards from per-shard (n_values, stats8) records (Chan, Golub & LeVeque), on
+// the device so that a row-sharded analyze needs no host round trip between the moments and the features:
+// out[0..7] = mean, population std, min, max, min/max over the A and B columns, 0, 0; out[8] = total n_values.
+__global__ void combine_moments_kernel(const double *__restrict__ parts, int k, double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double n = 0.0, sum = 0.0;
+  for (int i = 0; i < k; ++i) {
+    const double c = parts[9 * i];
+    if (c > 0.0) {
+      n += c;
+      sum += c * parts[9 * i + 1];
+    }
+  }
+  const double mean = sum / n;
+  double m2 = 0.0, mn = INFINITY, mx = -INFINITY, amn = INFINITY, amx = -INFINITY;
+  for (int i = 0; i < k; ++i) {
+    const double *p = parts + 9 * i;
+    if (!(p[0] > 0.0)) continue;
+    const double d = p[1] - mean;
+    m2 += p[0] * (p[2] * p[2] + d * d);
+    mn = fmin(mn, p[3]);
+    mx = fmax(mx, p[4]);
+    amn = fmin(amn, p[5]);
+    amx = fmax(amx, p[6]);
+    // a NaN anywhere must survive (fmin/fmax drop it): the caller's degenerate-output test looks at these
+    if (p[3] != p[3] || p[4] != p[4]) mn = mx = p[3] + p[4];
+  }
+  out[0] = mean;
+  out[1] = sqrt(m2 / n);
+  out[2] = mn;
+  out[3] = mx;
+  out[4] = amn;
+  out[5] = amx;
+  out[6] = 0.0;
+  out[7] = 0.0;
+  out[8] = n;
+}
+
 }  // namespace sa
 
 using namespace sa;
@@ -1665,8 +1616,9 @@ extern "C" int sa_counts_from_indices(void *stream, const int64_t *d_r, uint64_t
   return sa_counts_from_indices_rows(stream, d_r, N, R, c0, count, 0, N, d_w, d_overflow);
 }
 
-extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
-                                     uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow) {
+// slim != 0: the low-footprint launch (one 1024-thread block per SM) that co-resides with the persistent GEMM.
+extern "C" int sa_counts_philox_rows_ex(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                        uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow, int slim) {
   (void)d_overflow;  // P(multiplicity > 255) < 1e-500 for N iid uniform draws over N rows, N >= 256
   SA_REQUIRE(d_w, SA_ERR_ARG, "sa_counts_philox: null pointer");
   SA_REQUIRE(N >= 1, SA_ERR_ARG, "sa_counts_philox: bad N");
@@ -1680,20 +1632,24 @@ extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, ui
     // every byte of the row window is written by the kernel: only the pad bytes of each row are cleared
     // (a full memset of the 10.5 GB headline buffer costs 3 ms)
     if (Npad > nrows) SA_CUDA(cudaMemset2DAsync(d_w + nrows, Npad, 0, Npad - nrows, count, st));
-    const uint32_t W = (uint32_t)(N >> L);
-    const size_t smem = ((size_t)((W + 3) >> 2) + 1 + ((size_t)2 << L)) * sizeof(uint32_t);
-    static bool attr_done = false;
-    if (!attr_done) {
-      SA_CUDA(cudaFuncSetAttribute(counts_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_done = true;
+    const size_t smem = window_smem_bytes(N, L);
+    SA_REQUIRE(smem <= 200 * 1024, SA_ERR_ARG, "sa_counts_philox: N too large");
+    // per device and cheap: no process-wide cache (a second GPU of the process would miss the opt-in)
+    const int opt_in = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
+    if (slim) {
+      SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<kWinThreadsSlim>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, opt_in));
+      const uint64_t nb = count < (uint64_t)sm_count() ? count : (uint64_t)sm_count();
+      counts_window_kernel<kWinThreadsSlim><<<(unsigned)nb, kWinThreadsSlim, smem, st>>>(seed, N, c0, count, L, row0,
+                                                                                        nrows, Npad, d_w);
+    } else {
+      SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<kWinThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   opt_in));
+      const uint64_t nb = count < (1u << 30) ? count : (1u << 30);
+      counts_window_kernel<kWinThreads><<<(unsigned)nb, kWinThreads, smem, st>>>(seed, N, c0, count, L, row0, nrows,
+                                                                                Npad, d_w);
     }
-    SA_REQUIRE(smem <= 96 * 1024, SA_ERR_ARG, "sa_counts_philox: N too large");
-    for (uint64_t done = 0; done < count; done += 1u << 30) {
-      const uint64_t nb = (count - done < (1u << 30)) ? count - done : (1u << 30);
-      counts_window_kernel<<<(unsigned)nb, kWinThreads, smem, st>>>(seed, N, c0 + done, L, row0, nrows, Npad,
-                                                                  d_w + done * Npad);
-      note_launches(1);
-    }
+    note_launches(1);
     SA_LAUNCH_CHECK();
     return SA_OK;
   }
@@ -1711,6 +1667,11 @@ extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, ui
   }
   SA_LAUNCH_CHECK();
   return SA_OK;
+}
+
+extern "C" int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                     uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow) {
+  return sa_counts_philox_rows_ex(stream, seed, N, c0, count, row0, nrows, d_w, d_overflow, 0);
 }
 
 extern "C" int sa_counts_philox(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
@@ -1807,11 +1768,9 @@ extern "C" int sa_sobol_finalize_f64(void *stream, const double *d_psum, uint64_
   SA_REQUIRE(count < (1ull << 31), SA_ERR_UNSUPPORTED, "too many resamples in one call");
   const size_t fin_smem = ((size_t)Dg + SA_NACC(Dg, second_order)) * sizeof(double);
   if (fin_smem <= 200 * 1024) {
-    static size_t fin_attr = 48 * 1024;
-    if (fin_smem > fin_attr) {
+    // the attribute is per device: set it whenever the opt-in is needed (no process-wide cache)
+    if (fin_smem > 48 * 1024)
       SA_CUDA(cudaFuncSetAttribute(finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-      fin_attr = fin_smem;
-    }
     finalize_kernel<true><<<(unsigned)count, 128, fin_smem, (cudaStream_t)stream>>>(
         d_psum, N, Dg, second_order, count, nsplit, d_stats, d_est, SA_NACC(Dg, second_order),
         SA_NEST(Dg, second_order));
@@ -1832,6 +1791,33 @@ extern "C" int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, 
   SA_REQUIRE(R >= 1 && ncols >= 1, SA_ERR_ARG, "sa_sobol_conf_f64: bad shape");
   dim3 block(32, 16);
   conf_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, z, d_conf);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_col_moment_f64(void *stream, const double *d_est, uint64_t R, int ncols, const double *d_mean,
+                                 double *d_out) {
+  SA_REQUIRE(d_out && ncols >= 1 && (d_est || R == 0), SA_ERR_ARG, "sa_col_moment_f64: bad arguments");
+  dim3 block(32, 16);
+  col_moment_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, d_mean, d_out);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_conf_finish_f64(void *stream, double *d_x, int ncols, double scale, double z, uint64_t R,
+                                  int finish) {
+  SA_REQUIRE(d_x && ncols >= 1, SA_ERR_ARG, "sa_conf_finish_f64: bad arguments");
+  conf_finish_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, ncols, scale, z, R, finish);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_combine_moments_f64(void *stream, const double *d_parts, int k, double *d_out) {
+  SA_REQUIRE(d_parts && d_out && k >= 1, SA_ERR_ARG, "sa_combine_moments_f64: bad arguments");
+  combine_moments_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_parts, k, d_out);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -1871,6 +1857,16 @@ extern "C" int sa_feature_sums_f64(void *stream, const double *d_F, uint64_t N, 
   uint64_t rps = ceil_div_u64(N, nsplit);
   rps = (rps + 31) & ~(uint64_t)31;
   return launch_feature_gemv((cudaStream_t)stream, d_F, N, nfeat, d_w, pad_rows(N), count, nsplit, rps, d_psum);
+}
+
+extern "C" int sa_feature_centered_ss_f64(void *stream, const double *d_F, uint64_t N, int nfeat, int ncols,
+                                          const double *d_center, double *d_out) {
+  SA_REQUIRE(d_F && d_center && d_out && N >= 1 && nfeat >= 1 && ncols >= 1 && ncols <= nfeat, SA_ERR_ARG,
+             "sa_feature_centered_ss_f64: bad arguments");
+  feature_centered_ss_kernel<<<(unsigned)ncols, 256, 0, (cudaStream_t)stream>>>(d_F, N, nfeat, d_center, d_out);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
 }
 
 extern "C" int sa_reduce_splits_f64(void *stream, const double *d_psum, uint64_t count, int nfeat, int nsplit,

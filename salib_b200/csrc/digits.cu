@@ -724,21 +724,40 @@ __device__ __forceinline__ void load_tile(const double *__restrict__ Y, uint64_t
   }
 }
 
-// fmax_bits[q] (bit pattern of a non-negative double, zeroed by the caller) = max_i |F[i][q]|
+// fmax_bits[q] (bit pattern of a non-negative double, zeroed by the caller) = max_i |F[i][q]|.
+// big_count (zeroed by the caller) += the number of normalised values within kGuardBits bits of the largest |x| of
+// the whole design -- the heavy-tail guard of the integer engine: the digits of a column are relative to its
+// maximum, so if only a handful of rows carry the large values (an outlier row), a resample that happens to miss
+// them is left with entries whose low bits were cut; "auto" then repeats the call with the FP64 engines
+// (analyze/sobol.py), which is what keeps 1e-10 against the reference on such data.
+constexpr int kGuardBits = 7;
+
 __global__ void __launch_bounds__(256)
 feature_max_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat, const FeatDesc *__restrict__ tab,
-                   const double *__restrict__ stats, int tile_rows, unsigned long long *__restrict__ fmax_bits) {
+                   const double *__restrict__ stats, int tile_rows, unsigned long long *__restrict__ fmax_bits,
+                   unsigned long long *__restrict__ big_count) {
   extern __shared__ double dsm[];
   const int pitch = tile_rows + 1;
   double *xs = dsm;                       // [step][pitch]
   double *best = dsm + step * pitch;      // [nfeat], entry q owned by thread q % 256
   const double mean = stats[0], sd = stats[1];
+  const double thr = ldexp(fmax(fabs(__ddiv_rn(__dsub_rn(stats[2], mean), sd)),
+                                fabs(__ddiv_rn(__dsub_rn(stats[3], mean), sd))), -kGuardBits);
+  unsigned big = 0;
   for (int q = threadIdx.x; q < nfeat; q += blockDim.x) best[q] = 0.0;
   const uint64_t tiles = ceil_div_u64(N, tile_rows);
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
     load_tile<false>(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
     __syncthreads();
+    {
+      const uint64_t i0 = tile * tile_rows;
+      const int rows = (int)((N - i0 < (uint64_t)tile_rows) ? N - i0 : (uint64_t)tile_rows);
+      for (int e = threadIdx.x; e < rows * step; e += blockDim.x) {
+        const int r = e / step, c = e - r * step;
+        big += fabs(xs[c * pitch + r]) > thr;
+      }
+    }
     for (int q = threadIdx.x; q < nfeat; q += blockDim.x) {
       const FeatDesc d = tab[q];
       double m = best[q];
@@ -749,13 +768,16 @@ feature_max_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat
   }
   for (int q = threadIdx.x; q < nfeat; q += blockDim.x)
     atomicMax(fmax_bits + q, (unsigned long long)__double_as_longlong(best[q]));
+  big = __reduce_add_sync(kFull, big);
+  if ((threadIdx.x & 31) == 0 && big) atomicAdd(big_count, (unsigned long long)big);
 }
 
 // scale[q] = 2^(bits - e), inv[q] = 2^(e - bits) with max |F[:, q]| < 2^e: |F * scale| < 2^bits
 __global__ void __launch_bounds__(256)
 feature_scale_kernel(const unsigned long long *__restrict__ fmax, int nfeat, int bits, double *__restrict__ scale,
-                     double *__restrict__ inv) {
+                     double *__restrict__ inv, const unsigned long long *__restrict__ big_count) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) inv[nfeat] = (double)*big_count;  // the heavy-tail guard rides behind the column scales
   if (q >= nfeat) return;
   const double m = __longlong_as_double((long long)fmax[q]);
   int e = 0;
@@ -767,64 +789,178 @@ feature_scale_kernel(const unsigned long long *__restrict__ fmax, int nfeat, int
 
 // Q[i / 128][q*S + s][i % 128] = digit s of rint(F[i][q] * scale[q]).  Blocks take tiles of TR rows; LPF = TR/4
 // lanes share a feature (4 consecutive rows each -> one 32-bit store per digit, TR contiguous bytes per column).
+//
+// Round-1 ncu of the first version: 5.1 ms for 15.8 GB (3.1 TB/s), 40 instructions per value, warps waiting on
+// the per-feature descriptor / scale loads (long scoreboard 5.6 per issue) at 24 warps per SM.  This version
+//   * walks the pair products BA_j * AB_k (94 % of the columns at Dg = 64) with (j, k) advanced incrementally --
+//     no descriptor loads -- and the next feature's scale fetched one iteration ahead,
+//   * reads the four rows of a lane with two LDS.128 per operand (tile layout below) and keeps two features in
+//     flight per lane,
+//   * writes the digits with streaming stores (Q is read next by the GEMM's TMA, 15.8 GB later).
+// Tile layout: column-major, pitch = rows + 2 doubles; row r of the tile sits in slot
+//   ((r >> 1) & 1) * (rows / 2) + 2 * (r >> 2) + (r & 1)
+// so lane `sub` (rows 4 sub .. 4 sub + 3) finds rows (0, 1) at slot 2 sub and rows (2, 3) at rows / 2 + 2 sub:
+// consecutive lanes read consecutive 16-byte chunks.
+__device__ __forceinline__ int split_slot(int r, int rows) {
+  return ((r >> 1) & 1) * (rows >> 1) + 2 * (r >> 2) + (r & 1);
+}
+
+__device__ __forceinline__ void load_tile_split(const double *__restrict__ Y, uint64_t N, int step, uint64_t i0,
+                                                int rows, int pitch, double mean, double sd, double *xs) {
+  const int total = rows * step;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int r = e / step, c = e - r * step;
+    const uint64_t i = i0 + r;
+    xs[c * pitch + split_slot(r, rows)] =
+        i < N ? __ddiv_rn(__dsub_rn(__ldcs(Y + i * (uint64_t)step + c), mean), sd) : 0.0;
+  }
+}
+
+// The four rows of this lane of column c.
+__device__ __forceinline__ void lds_rows4(const double *xs, int c, int pitch, int half, int sub, double v[4]) {
+  const double2 a = *reinterpret_cast<const double2 *>(xs + c * pitch + 2 * sub);
+  const double2 b = *reinterpret_cast<const double2 *>(xs + c * pitch + half + 2 * sub);
+  v[0] = a.x;
+  v[1] = a.y;
+  v[2] = b.x;
+  v[3] = b.y;
+}
+
+// Balanced digits without a carry chain: with u_s = d_s + 128 in [0, 255],  t + sum_s 128 * 256^s =
+// sum_s u_s * 256^s  is the plain base-256 form of a non-negative number below 256^S (|t| < 2^(8S-2)), and d_s
+// as an int8 bit pattern is u_s with the top bit flipped.  One add and one xor per value give all digits; a
+// 4 x 4 byte transpose (PRMT) per 32-bit half packs the four rows of each digit into a word.
+template <int S>
+__device__ __forceinline__ void emit_digits4(const double f[4], double sc, int8_t *dst) {
+  constexpr unsigned long long kBias = 0x8080808080808080ull >> (8 * (8 - S));
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const unsigned long long u =
+        ((unsigned long long)__double2ll_rn(__dmul_rn(f[rr], sc)) + kBias) ^ 0x8080808080808080ull;
+    lo[rr] = (uint32_t)u;
+    hi[rr] = (uint32_t)(u >> 32);
+  }
+  uint32_t packed[8];
+  {
+    const uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[0], lo[1], 0x7362);
+    const uint32_t c = __byte_perm(lo[2], lo[3], 0x5140), e = __byte_perm(lo[2], lo[3], 0x7362);
+    packed[0] = __byte_perm(a, c, 0x5410);
+    packed[1] = __byte_perm(a, c, 0x7632);
+    packed[2] = __byte_perm(b, e, 0x5410);
+    packed[3] = __byte_perm(b, e, 0x7632);
+  }
+  if (S > 4) {
+    const uint32_t a = __byte_perm(hi[0], hi[1], 0x5140), b = __byte_perm(hi[0], hi[1], 0x7362);
+    const uint32_t c = __byte_perm(hi[2], hi[3], 0x5140), e = __byte_perm(hi[2], hi[3], 0x7362);
+    packed[4] = __byte_perm(a, c, 0x5410);
+    packed[5] = __byte_perm(a, c, 0x7632);
+    packed[6] = __byte_perm(b, e, 0x5410);
+    packed[7] = __byte_perm(b, e, 0x7632);
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) __stcs(reinterpret_cast<uint32_t *>(dst + s * 128), packed[s]);
+}
+
+// Pair p + step of the strict upper triangle (row-major) from pair p = (j, k); the caller guarantees it exists.
+__device__ __forceinline__ void advance_pair(int Dg, int step, int &j, int &k) {
+  int pos = k - j - 1 + step;
+  while (pos >= Dg - 1 - j) {
+    pos -= Dg - 1 - j;
+    ++j;
+  }
+  k = j + 1 + pos;
+}
+
 template <int S>
 __global__ void __launch_bounds__(256)
-digit_split_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat, const FeatDesc *__restrict__ tab,
-                   const double *__restrict__ stats, const double *__restrict__ scale, int tile_rows, uint64_t Kp,
-                   int8_t *__restrict__ Q) {
-  extern __shared__ double dsm[];
-  const int pitch = tile_rows + 1;
+digit_split_kernel(const double *__restrict__ Y, uint64_t N, int step, int Dg, int nhead, int nfeat,
+                   const FeatDesc *__restrict__ tab, const double *__restrict__ stats,
+                   const double *__restrict__ scale, int tile_rows, uint64_t Kp, int8_t *__restrict__ Q) {
+  extern __shared__ __align__(16) double dsm[];
+  const int pitch = tile_rows + 2, half = tile_rows >> 1;
   double *xs = dsm;
   const double mean = stats[0], sd = stats[1];
   const int lpf = tile_rows >> 2, fpw = 32 / lpf;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int sub = lane % lpf, fsel = lane / lpf;
+  const int sub = lane % lpf, g = warp * fpw + lane / lpf, G = nwarps * fpw;  // feature group of this lane
+  const int npairs = nfeat - nhead;
+  // first pair of this lane group
+  int j0 = 0, k0 = 1;
+  if (g < npairs) {
+    int pos = g;
+    while (pos >= Dg - 1 - j0) {
+      pos -= Dg - 1 - j0;
+      ++j0;
+    }
+    k0 = j0 + 1 + pos;
+  }
   const uint64_t tiles = Kp / tile_rows;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
-    load_tile<true>(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
+    load_tile_split(Y, N, step, tile * tile_rows, tile_rows, pitch, mean, sd, xs);
     __syncthreads();
-    for (int q = warp * fpw + fsel; q < nfeat; q += nwarps * fpw) {
+    // K-blocked layout: block kb = 128 consecutive rows of Y holds [ncols][128] bytes contiguously, so a tile's
+    // digits form one streaming write (and one GEMM operand box = 128 columns x 128 bytes is contiguous too)
+    const uint64_t row0 = tile * tile_rows;
+    int8_t *qtile = Q + (row0 >> 7) * ((uint64_t)nfeat * S) * 128 + (row0 & 127) + 4 * sub;
+    // scalar, square, first- and total-order features: descriptors from the table
+    for (int q = g; q < nhead; q += G) {
       const FeatDesc d = tab[q];
       const double sc = scale[q];
-      // Balanced digits without a carry chain: with u_s = d_s + 128 in [0, 255],  t + sum_s 128 * 256^s =
-      // sum_s u_s * 256^s  is the plain base-256 form of a non-negative number below 256^S (|t| < 2^(8S-2)),
-      // and d_s as an int8 bit pattern is u_s with the top bit flipped.  One add and one xor per value give all
-      // digits; a 4 x 4 byte transpose (PRMT) per 32-bit half packs the four rows of each digit into a word.
-      constexpr unsigned long long kBias = 0x8080808080808080ull >> (8 * (8 - S));
-      uint32_t lo[4], hi[4];
+      double a[4], b[4], f[4];
+      lds_rows4(xs, d.u, pitch, half, sub, a);
+      if (d.type == 0) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int slot = rr * lpf + sub;  // row 4 * sub + rr of the tile
-        const double f = feature_value(d, [&](int c) { return xs[c * pitch + slot]; });
-        const unsigned long long u =
-            ((unsigned long long)__double2ll_rn(__dmul_rn(f, sc)) + kBias) ^ 0x8080808080808080ull;
-        lo[rr] = (uint32_t)u;
-        hi[rr] = (uint32_t)(u >> 32);
-      }
-      uint32_t packed[8];
-      {
-        const uint32_t a = __byte_perm(lo[0], lo[1], 0x5140), b = __byte_perm(lo[0], lo[1], 0x7362);
-        const uint32_t c = __byte_perm(lo[2], lo[3], 0x5140), e = __byte_perm(lo[2], lo[3], 0x7362);
-        packed[0] = __byte_perm(a, c, 0x5410);
-        packed[1] = __byte_perm(a, c, 0x7632);
-        packed[2] = __byte_perm(b, e, 0x5410);
-        packed[3] = __byte_perm(b, e, 0x7632);
-      }
-      if (S > 4) {
-        const uint32_t a = __byte_perm(hi[0], hi[1], 0x5140), b = __byte_perm(hi[0], hi[1], 0x7362);
-        const uint32_t c = __byte_perm(hi[2], hi[3], 0x5140), e = __byte_perm(hi[2], hi[3], 0x7362);
-        packed[4] = __byte_perm(a, c, 0x5410);
-        packed[5] = __byte_perm(a, c, 0x7632);
-        packed[6] = __byte_perm(b, e, 0x5410);
-        packed[7] = __byte_perm(b, e, 0x7632);
-      }
-      // K-blocked layout: block kb = 128 consecutive rows of Y holds [ncols][128] bytes contiguously, so a tile's
-      // digits form one streaming write (and one GEMM operand box = 128 columns x 128 bytes is contiguous too)
-      const uint64_t row0 = tile * tile_rows;
-      int8_t *dst = Q + ((row0 >> 7) * ((uint64_t)nfeat * S) + (uint64_t)q * S) * 128 + (row0 & 127) + 4 * sub;
+        for (int i = 0; i < 4; ++i) f[i] = a[i];
+      } else {
+        lds_rows4(xs, d.v, pitch, half, sub, b);
+        if (d.type == 1) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) *reinterpret_cast<uint32_t *>(dst + s * 128) = packed[s];
+          for (int i = 0; i < 4; ++i) f[i] = __dmul_rn(a[i], b[i]);
+        } else if (d.type == 2) {
+          double c[4];
+          lds_rows4(xs, d.w, pitch, half, sub, c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) f[i] = __dmul_rn(a[i], __dsub_rn(b[i], c[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double t = __dsub_rn(a[i], b[i]);
+            f[i] = __dmul_rn(t, t);
+          }
+        }
+      }
+      emit_digits4<S>(f, sc, qtile + (uint64_t)q * S * 128);
+    }
+    // pair products BA_j * AB_k, two per lane in flight
+    if (g < npairs) {
+      int j = j0, k = k0;
+      double sc1 = scale[nhead + g];
+      double sc2 = g + G < npairs ? scale[nhead + g + G] : 0.0;
+      for (int p = g; p < npairs; p += 2 * G) {
+        const bool two = p + G < npairs;
+        int j2 = j, k2 = k;
+        if (two) advance_pair(Dg, G, j2, k2);
+        const double s1 = sc1, s2 = sc2;
+        if (p + 2 * G < npairs) sc1 = scale[nhead + p + 2 * G];
+        if (p + 3 * G < npairs) sc2 = scale[nhead + p + 3 * G];
+        double ba1[4], ab1[4], ba2[4], ab2[4], f1[4], f2[4];
+        lds_rows4(xs, 1 + Dg + j, pitch, half, sub, ba1);
+        lds_rows4(xs, 1 + k, pitch, half, sub, ab1);
+        lds_rows4(xs, 1 + Dg + j2, pitch, half, sub, ba2);
+        lds_rows4(xs, 1 + k2, pitch, half, sub, ab2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f1[i] = __dmul_rn(ba1[i], ab1[i]);
+          f2[i] = __dmul_rn(ba2[i], ab2[i]);
+        }
+        emit_digits4<S>(f1, s1, qtile + (uint64_t)(nhead + p) * S * 128);
+        if (two) emit_digits4<S>(f2, s2, qtile + (uint64_t)(nhead + p + G) * S * 128);
+        j = j2;
+        k = k2;
+        if (p + 2 * G < npairs) advance_pair(Dg, G, j, k);
+      }
     }
   }
 }
@@ -1122,6 +1258,15 @@ static int feature_tile_rows(int step, int extra, size_t budget, int max_rows) {
   return 0;
 }
 
+// Rows per tile of the split kernel: step * (rows + 2) doubles; 64 rows while three blocks fit an SM, then fewer.
+static int split_tile_rows(int step) {
+  for (int rows = 64; rows >= 8; rows >>= 1)
+    if ((size_t)step * (rows + 2) * 8 <= 72 * 1024) return rows;
+  for (int rows = 64; rows >= 8; rows >>= 1)  // long rows: one block per SM
+    if ((size_t)step * (rows + 2) * 8 <= 200 * 1024) return rows;
+  return 0;
+}
+
 }  // namespace dg
 }  // namespace sa
 
@@ -1163,7 +1308,7 @@ extern "C" int sa_digit_pair_plan(uint64_t tiles_m, uint64_t tiles_n, uint64_t k
 }
 
 extern "C" size_t sa_digit_features_workspace_bytes(int nfeat) {
-  return (size_t)round_up((uint64_t)nfeat * (sizeof(FeatDesc) + 8 + 8), 256);
+  return (size_t)round_up((uint64_t)nfeat * (sizeof(FeatDesc) + 8 + 8) + 8, 256);
 }
 
 extern "C" size_t sa_digit_sums_workspace_bytes(uint64_t N, int nfeat, int ndigits, uint64_t count) {
@@ -1216,31 +1361,33 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
   SA_REQUIRE(work_bytes >= sa_digit_features_workspace_bytes(nfeat), SA_ERR_WORKSPACE,
              "sa_digit_features_i8: workspace too small");
   const int rows_max = feature_tile_rows(step, nfeat, 54 * 1024, 32);   // 4 blocks per SM
-  const int rows = feature_tile_rows(step, 0, 72 * 1024, 64);          // 3 blocks per SM
+  const int rows = split_tile_rows(step);                              // 3 blocks per SM while step allows
   SA_REQUIRE(rows >= 8 && rows_max >= 8, SA_ERR_UNSUPPORTED,
              "sa_digit_features_i8: %d outputs per base row do not fit shared memory", step);
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t Kp = sa_digit_row_pitch(N);
-  unsigned long long *fmax = (unsigned long long *)d_work;
-  double *scale = (double *)(fmax + nfeat);
+  unsigned long long *fmax = (unsigned long long *)d_work;   // [nfeat] + the guard counter
+  double *scale = (double *)(fmax + nfeat + 1);
   FeatDesc *tab = (FeatDesc *)(scale + nfeat);
   const int fb = (nfeat + 255) / 256;
-  SA_CUDA(cudaMemsetAsync(fmax, 0, (size_t)nfeat * 8, st));
+  SA_CUDA(cudaMemsetAsync(fmax, 0, ((size_t)nfeat + 1) * 8, st));
   feature_table_kernel<<<fb, 256, 0, st>>>(Dg, step, nfeat, tab);
   const size_t smem_max = ((size_t)step * (rows_max + 1) + nfeat) * 8;
-  const size_t smem_split = (size_t)step * (rows + 1) * 8;
+  const size_t smem_split = (size_t)step * (rows + 2) * 8;
+  const int nhead = 5 + 2 * Dg;
   SA_CUDA(cudaFuncSetAttribute(feature_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const uint64_t tiles = ceil_div_u64(N, rows_max), slots = 4 * (uint64_t)sm_count();
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax);
-  feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv);
+  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax, fmax + nfeat);
+  feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv, fmax + nfeat);
   const uint64_t tiles2 = Kp / rows, slots2 = 3 * (uint64_t)sm_count();
   const unsigned grid2 = (unsigned)(tiles2 < slots2 ? tiles2 : slots2);
 #define SA_SPLIT(S)                                                                                               \
   case S:                                                                                                         \
     SA_CUDA(cudaFuncSetAttribute(digit_split_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                  (int)smem_split));                                                               \
-    digit_split_kernel<S><<<grid2, 256, smem_split, st>>>(d_Y, N, step, nfeat, tab, d_stats, scale, rows, Kp, d_Q); \
+    digit_split_kernel<S><<<grid2, 256, smem_split, st>>>(d_Y, N, step, Dg, nhead, nfeat, tab, d_stats, scale,    \
+                                                          rows, Kp, d_Q);                                        \
     break;
   switch (ndigits) {
     SA_SPLIT(2) SA_SPLIT(3) SA_SPLIT(4) SA_SPLIT(5) SA_SPLIT(6) SA_SPLIT(7) SA_SPLIT(8)

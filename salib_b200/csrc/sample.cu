@@ -736,11 +736,8 @@ extern "C" int sa_saltelli_eval_sobol_g_f64(void *stream, const uint32_t *d_sv, 
     const size_t smem = (size_t)BR * pitch_bytes;
     uint64_t blocks = ceil_div_u64(n, BR);
     if (blocks > (uint64_t)sm_count() * 16) blocks = (uint64_t)sm_count() * 16;
-    static size_t pairs_attr = 48 * 1024;
-    if (smem > pairs_attr) {
+    if (smem > 48 * 1024)  // per device: no process-wide cache of the opt-in
       SA_CUDA(cudaFuncSetAttribute(saltelli_eval_g_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      pairs_attr = 96 * 1024;
-    }
     saltelli_eval_g_pairs_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
         d_sv, d_shift, first_index, n, D, step, second_order, cs, d_a, d_delta, d_alpha, d_Y, d_flag, BR);
   } else {

@@ -347,6 +347,10 @@ def _gloo_worker(rank, world, port, R, nest, q):
     st = combine_moments(parts)
     ref = moments(data)[1]
     ok = ok and len(parts) == 3 and bool(np.allclose(st[:6], ref[:6], rtol=1e-14, atol=0))
+    # decisions every rank must share before it issues collectives (engine family, batch sizes): MAX over ranks
+    from salib_b200.analyze.sobol import _agree
+
+    ok = ok and _agree([rank, 10 - rank, 7]) == [world - 1, 10, 7]
     q.put((rank, ok))
     dist.destroy_process_group()
 
@@ -416,3 +420,52 @@ def test_persistent_pair_plan_covers_every_tile_once(tm, tn, ksteps, pairs, band
     if rem_tiles and ksteps >= 256:
         rounds = -(-rem_tiles * rsplit // P)
         assert rounds * rper / ksteps <= rem_tiles / P + 0.15
+
+
+def test_numpy_resample_stream_can_be_drawn_in_row_blocks():
+    """analyze/sobol.py:113-117,144 draws r = rng(N, size=(N, R)) in one call; the drop-in streams the same draw in
+    row blocks (bounded host memory).  One generator continues one stream: the blocks concatenate to the single
+    call, for the seeded Generator and for the legacy global RNG (seed falsy)."""
+    N, R = 5000, 37
+    whole = np.random.default_rng(1234).integers(N, size=(N, R))
+    g = np.random.default_rng(1234).integers
+    parts = [g(N, size=(b - a, R)) for a, b in [(0, 1), (1, 700), (700, 4099), (4099, N)]]
+    assert np.array_equal(np.concatenate(parts), whole)
+    np.random.seed(99)
+    whole = np.random.randint(N, size=(N, R))
+    np.random.seed(99)
+    parts = [np.random.randint(N, size=(b - a, R)) for a, b in [(0, 333), (333, 334), (334, N)]]
+    assert np.array_equal(np.concatenate(parts), whole)
+    # ranges that need 64-bit draws too
+    big = 2 ** 33 + 5
+    whole = np.random.default_rng(7).integers(big, size=(2000, 3))
+    g = np.random.default_rng(7).integers
+    assert np.array_equal(np.concatenate([g(big, size=(1234, 3)), g(big, size=(766, 3))]), whole)
+
+
+def test_digits_batches_and_reduce_scatter_bookkeeping():
+    """Host logic of the pipelined row route (analyze/sobol.py: digits_batch, batch_share): batches cover [0, R) in
+    whole tiles, and the rows each rank keeps after the reduce-scatter tile every batch exactly once, the row of
+    ones (the point estimate) landing on exactly one rank."""
+    from salib_b200.analyze.sobol import batch_share, digits_batch
+
+    assert digits_batch(10000, 1 << 20) == 2560
+    assert digits_batch(100, 1 << 20) == 100
+    assert digits_batch(0, 1 << 20) == 1
+    for R, npad in [(10000, 1 << 20), (10000, 1 << 17), (777, 1 << 22), (5000, 1 << 24), (1, 128)]:
+        B = digits_batch(R, npad)
+        assert B == R or B % 256 == 0
+        batches = [(c, min(c + B, R)) for c in range(0, R, B)]
+        assert batches[0][0] == 0 and batches[-1][1] == R
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(R, dtype=int)
+            owners = 0
+            for c0, c1 in batches:
+                n = c1 - c0
+                count = n + (1 if c1 == R else 0)
+                for g in range(world):
+                    chunk, lo, valid = batch_share(n, count, world, g)
+                    assert chunk * world >= count
+                    seen[c0 + lo:c0 + lo + valid] += 1
+                    owners += int(count > n and lo <= n < lo + chunk)
+            assert (seen == 1).all() and owners == 1
