@@ -56,6 +56,8 @@ def parse_args():
                          "the integer engine scales with) or resample ids (all-gather of estimates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample", action="store_true", help="skip the 70 GB sample-generation leg")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short legs for BASELINE configs[1] (cfg2), [3] (cfg4 points) and [4] (cfg5, 8 GPUs)")
     ap.add_argument("--ref-log2n", type=int, default=11, help="bounded sample of the reference arm (SURVEY 8(d): "
                                                               "D=64, N=2^11..2^13, R=100)")
     ap.add_argument("--ref-resamples", type=int, default=100)
@@ -584,6 +586,69 @@ def main():
             checks["max_abs_diff_point_vs_single_rank"] = d
             checks["multi_rank_ok"] = bool(d <= 1e-12)
         barrier()
+
+    # ---- the other BASELINE configs, briefly, so that they are in the driver-parsed line (under roofline.configs)
+    other = None
+    if not a.no_other_configs and a.dim == 64 and a.log2n == 20 and c2:
+        other = {}
+        if world == 1:
+            # configs[1]: G function D=8, N=2^20, first+total order, R=1000
+            p8 = g_problem(8)
+            plan8, first8 = sample_sobol._plan(p8, N, False, False, N, None)
+            Y8 = Sobol_G.evaluate_sample(plan8, first8, N)
+            t8 = timed(lambda: analyze_sobol.analyze_device(p8, Y8, calc_second_order=False, num_resamples=1000,
+                                                            seed=100, resample="philox"), 3, 2)
+            S8 = analyze_sobol.analyze_device(p8, Y8, calc_second_order=False, num_resamples=1000, seed=100,
+                                              resample="philox")
+            V8 = 1.0 / (3.0 * (1.0 + np.array(G_A8, dtype=np.float64)) ** 2)
+            an8 = V8 / (np.prod(1.0 + V8) - 1.0)
+            other["cfg2"] = {"workload": "Sobol' G-function D=8, N=2^20, first+total order, num_resamples=1000",
+                             "analyze_s": t8 / 3, "value": N * 1000 * 3 / t8, "unit": "resample-rows/s",
+                             "engine": S8.engine,
+                             "S1_within_CI_of_analytic": bool(np.all(np.abs(S8["S1"] - an8) <= 2.0 * S8["S1_conf"] + 1e-3))}
+            del Y8
+            # configs[3]: points of the sample-generation sweep (chunked into a reused buffer beyond 32 GB)
+            pts = []
+            for Dq, lq, scr in ((16, 22, False), (128, 20, False), (128, 20, True), (1024, 16, False)):
+                stepq, Nq = 2 * Dq + 2, 1 << lq
+                chunk = Nq
+                while stepq * chunk * Dq * 8 > 3.2e10:
+                    chunk //= 2
+                svq, shq = sample_sobol._scramble_state(2 * Dq, scr, 1234)
+                planq = sample_sobol.SamplePlan(g_problem(Dq), True, svq, shq)
+                buf = rt.empty((stepq * chunk, Dq), torch.float64)
+
+                def run_q():
+                    for c0 in range(0, Nq, chunk):
+                        planq.generate(c0, chunk, out=buf)
+
+                tq = timed(run_q, 2, 1) / 2
+                nbytes = stepq * Nq * Dq * 8
+                pts.append({"D": Dq, "log2N": lq, "scramble": scr, "Grows_per_s": stepq * Nq / tq / 1e9,
+                            "GBps": nbytes / tq / 1e9, "hbm_frac": nbytes / tq / 1e9 / hbm_peak, "seconds": tq})
+                del buf
+                torch.cuda.empty_cache()
+            other["cfg4_points"] = pts
+        if world == 8:
+            # configs[4]: D=64, N=2^22, second order, fused G evaluation per rank, row shards (Y never gathered)
+            N5 = 1 << 22
+            plan5, first5 = sample_sobol._plan(problem, N5, c2, False, N5, None)
+            lo5, hi5 = rt.shard_range(N5, rank, world)
+            Y5 = rt.empty((step_rows * (hi5 - lo5),), torch.float64)
+            Sobol_G.evaluate_sample(plan5, first5 + lo5, hi5 - lo5, a=avec, out=Y5, check=False)
+
+            def step5():
+                return analyze_sobol.analyze_row_sharded(problem, [(lo5, Y5)], N5, calc_second_order=c2,
+                                                         num_resamples=R, seed=100, resample="philox", algo=a.algo)
+
+            t5 = timed(step5, 2, 1) / 2
+            S5 = step5()
+            other["cfg5"] = {"workload": f"Sobol' G-function D=64, N=2^22, second order, num_resamples={R}, 8 GPUs, "
+                                         "fused evaluation, base-row shards",
+                             "analyze_s": t5, "value": N5 * R / t5, "unit": "resample-rows/s", "engine": S5.engine,
+                             "S1_0": float(S5["S1"][0]), "ST_0": float(S5["ST"][0])}
+            del Y5
+        roofline["configs"] = other
 
     # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region.  Every rank
     # holds the host array, as every process of a torchrun job would; analyze() routes by itself.

@@ -175,7 +175,7 @@ int sa_counts_from_indices_rows(void *stream, const int64_t *d_r, uint64_t N, ui
                                 int32_t *d_overflow);
 int sa_counts_philox_rows(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
                           uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow);
-/* slim != 0: the low-footprint launch shape -- one 1024-thread block per SM with a single 16 KB window, which fits
+/* slim != 0: the low-footprint launch shape -- one 512-thread block per SM with a single 16 KB window, which fits
  * next to a CTA of the persistent GEMM kernel, so a side stream can draw batch b+1 while batch b is in the tensor
  * cores.  Same multiplicities as the wide launch (the Philox counters do not depend on the launch shape).      */
 int sa_counts_philox_rows_ex(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
@@ -258,6 +258,16 @@ int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N, int Dg, in
 int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat, int ndigits,
                       const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work, size_t work_bytes,
                       double *d_psum);
+/* sa_digit_sums_f64 that also HOSTS the Philox draw of the next batch of multiplicities (draw_count > 0; arguments as
+ * sa_counts_philox_rows: d_w_next[draw_count][sa_pad_rows(draw_nrows)] <- resamples [draw_c0, draw_c0 + draw_count)
+ * over the row window): 16 spare warps of every CTA of the persistent pair GEMM draw while the tensor cores
+ * multiply the current batch -- same stream, no events, and co-residency by construction (a separate kernel only
+ * overlaps when the block scheduler and the shared-memory carveout happen to allow it).  Shapes that do not run the
+ * persistent pair kernel draw first and multiply after.  d_w_next must not alias d_w.                            */
+int sa_digit_sums_draw_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat, int ndigits,
+                           const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work, size_t work_bytes,
+                           double *d_psum, uint64_t draw_seed, uint64_t draw_N, uint64_t draw_c0, uint64_t draw_count,
+                           uint64_t draw_row0, uint64_t draw_nrows, uint8_t *d_w_next);
 int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, const int8_t *d_Q,
                       uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit, int32_t *d_C, uint64_t ldc);
 

@@ -11,7 +11,7 @@
   the per-column power-of-two scaling of the integer engine loses on such data against the reference itself.
 * sample_sha_*: SHA-256 of the reference's sample matrices at D=512 and D=1024 (unscrambled and scrambled; the
   matrices are 17-67 MB), with scipy's scramble state frozen beside them.
-* analyze_g205_n32_r4 / analyze_g204_n32_r4: the reference at the integer engine's selection boundary (Dg=204/205).
+* analyze_g207_n32_r4 / analyze_g208_n32_r4: the reference at the integer engine's selection boundary (Dg=207/208).
 """
 import hashlib
 import os
@@ -77,8 +77,8 @@ for D, N, c2 in [(512, 8, False), (1024, 4, False), (512, 2, True)]:
              seed=sd, scramble=scramble, shape=np.array(Xs.shape), sha256=hashlib.sha256(Xs.tobytes()).hexdigest(),
              first_row=Xs[0], last_row=Xs[-1], **kw)
 
-# ---- 4. the integer engine's selection boundary (second order: Dg <= 204 fits the feature kernels)
-for D in (204, 205):
+# ---- 4. the integer engine's selection boundary (second order: Dg <= 207 fits the feature kernels)
+for D in (207, 208):
     N, R, seed = 32, 4, 9
     a = np.linspace(1.0, 80.0, D)
     X = ref_sobol.sample(gprob(D), N, calc_second_order=True, scramble=False, skip_values=N)

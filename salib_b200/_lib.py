@@ -70,6 +70,8 @@ SIGNATURES = {
     "sa_digit_sums_workspace_bytes": (_sz, [_u64, _i32, _i32, _u64]),
     "sa_digit_features_i8": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _sz]),
     "sa_digit_sums_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _u64, _vp, _sz, _vp]),
+    "sa_digit_sums_draw_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _vp, _u64, _u64, _vp, _sz, _vp,
+                                         _u64, _u64, _u64, _u64, _u64, _u64, _vp]),
     "sa_digit_gemm_i32": (C.c_int, [_vp, _vp, _u64, _u64, _vp, _u64, _u64, _u64, _i32, _vp, _u64]),
     "sa_launch_count": (C.c_longlong, [_i32]),
     "sa_microbench_fp64": (C.c_int, [_vp, _i32, _vp, _vp]),

@@ -62,9 +62,10 @@ NUMPY_RESAMPLE_MAX = 2 ** 24          # unseeded "auto": N*R index draws made on
 NUMPY_SEEDED_MAX = 2 ** 31            # seeded "auto": keep the reference's own resamples up to here (17 GB on device)
 NUMPY_BLOCK_DRAWS = 2 ** 24           # host block of the streamed draw (128 MB of int64)
 MAX_COUNT_BYTES = 12 << 30            # multiplicity buffer per batch (uint8 [count][Npad]), FP64 engines
-# integer engine: resamples go through the GEMM in batches of about this many multiplicity bytes; two buffers
-# alternate, the next batch is drawn (slim Philox kernel, side stream) while the current one is in the tensor cores
-DIGITS_BATCH_BYTES = int(os.environ.get("SALIB_B200_BATCH_BYTES", 2752 << 20))
+# integer engine: resamples go through the GEMM in batches of at most this many multiplicity bytes (digits_batch);
+# two buffers alternate, the next batch is drawn (slim Philox kernel, side stream) while the current one is in the
+# tensor cores
+DIGITS_BATCH_BYTES = int(os.environ.get("SALIB_B200_BATCH_BYTES", 8704 << 20))
 _ALGO = {"auto": 0, "fp64": -1, "generic": 1, "first_order": 3, "gemv": 3, "tile8": 4, "dmma": 5, "digits": 6}
 # Engines.  "digits": the bootstrap sums as an exact integer GEMM on the tensor cores (csrc/digits.cu);
 # "fp64": the FP64-pipe engines (feature GEMV / 8x8 register-tile kernel / generic).  "auto" takes "digits"
@@ -87,14 +88,26 @@ ENGINE_NAMES = {1: "fp64-generic", 3: "fp64-gemv", 4: "fp64-tile8", 5: "fp64-dmm
 # Heavy-tail guard of the integer engine ("auto" only): the digits of a feature column are relative to the
 # column maximum, so when fewer than GUARD_MIN_ROWS base rows carry every value within 7 bits of the design's
 # largest |x| (an outlier row), a resample can miss them all and be left with entries whose low bits were cut.
-# Such outputs are analysed again with the FP64 engines; 33+ rows are all absent from a resample with
-# probability e^-33, i.e. never.  The count comes from the feature kernels (inv[nacc]).
+# Such outputs are analysed again with the FP64 engines (guard_trips); ~28+ rows are all absent from a resample
+# with probability below 1e-12, i.e. never.  The count comes from the feature kernels (inv[nacc]).
 GUARD_MIN_ROWS = 32
+GUARD_MISS_PROBABILITY = 1e-12
+
+
+def guard_trips(guard, step, N):
+    """Heavy-tail guard: ``guard`` values lie within 7 bits of the design's largest |x|; they sit in at least
+    k = guard / step base rows, and a resample of N draws misses all of them with probability (1 - k/N)^N
+    (e^-k for large N).  True when that can happen in practice, i.e. the integer engine's column scaling could
+    cost a resample its precision."""
+    k = min(float(guard) / step, float(N))
+    return (1.0 - k / N) ** N > GUARD_MISS_PROBABILITY
+
+
 DIGITS_MIN_WORK = 1 << 31
 DIGITS_MAX_BYTES = 80 << 30
 # feature kernels: SA_NACC maxima + 9 doubles per model output of a base row must fit 200 KB of shared memory
-# (second order: Dg <= 205; first/total order only: Dg <= 2270)
-DIGITS_MAX_FEATURES = 25000
+# (digits.cu: feature_tile_rows; second order: Dg <= 207, first/total order only: Dg <= 2320)
+DIGITS_MAX_FEATURES = 25600
 PAIR_GEMV_MAX_DG = 48                 # second order through the feature GEMV up to this many groups ...
 PAIR_GEMV_MAX_BYTES = 48 << 30        # ... while N * SA_NACC doubles stay below this
 
@@ -356,9 +369,11 @@ class SobolAnalyzer:
         st = np.asarray(stats, dtype=np.float64)[:4]
         return not (np.all(np.isfinite(st)) and st[1] > 0.0)
 
-    def digit_sums(self, w, count, rows_alloc=None):
+    def digit_sums(self, w, count, rows_alloc=None, draw=None):
         """Integer engine: psum [rows_alloc >= count, nacc] float64 of this engine's rows for the multiplicity rows
-        w[count][Npad]; rows beyond ``count`` are zero (padding for the reduce-scatter)."""
+        w[count][Npad]; rows beyond ``count`` are zero (padding for the reduce-scatter).  ``draw`` = (key, N_total,
+        c0, n, w_next): the GEMM also hosts the Philox draw of resamples [c0, c0+n) over this engine's row window
+        into ``w_next`` (the next batch; spare warps of the GEMM's CTAs, see sa_digit_sums_draw_f64)."""
         rows_alloc = int(rows_alloc or count)
         psum = rt.empty((rows_alloc, self.nacc), torch.float64)
         if rows_alloc > count:
@@ -369,8 +384,10 @@ class SobolAnalyzer:
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.call("sa_digit_sums_f64", rt.stream_ptr(), rt.ptr(self.Q), rt.ptr(self.inv), self.N, self.nacc,
-                  self.ndigits, rt.ptr(w), self.Npad, int(count), rt.ptr(work), int(work.numel()), rt.ptr(psum))
+        key, n_total, c0, n, w_next = draw if draw is not None else (0, 0, 0, 0, None)
+        _lib.call("sa_digit_sums_draw_f64", rt.stream_ptr(), rt.ptr(self.Q), rt.ptr(self.inv), self.N, self.nacc,
+                  self.ndigits, rt.ptr(w), self.Npad, int(count), rt.ptr(work), int(work.numel()), rt.ptr(psum),
+                  int(key), int(n_total), int(c0), int(n), int(getattr(self, "row0", 0)), self.N, rt.ptr(w_next))
         if ev is not None:
             ev[1].record()
             self.kernel_events.append((int(count), ev[0], ev[1]))
@@ -572,10 +589,19 @@ def _agree(values_max):
     return [int(v) for v in t.cpu().numpy()]
 
 
-def digits_batch(R, npad_max):
-    """Resamples per GEMM batch of the integer engine: about DIGITS_BATCH_BYTES of multiplicities, whole
-    256-resample tiles, batches of equal size.  Pure host logic."""
-    cap = max(256, DIGITS_BATCH_BYTES // max(int(npad_max), 1) // 256 * 256)
+DIGITS_BATCH_MIN_MACS = 3.5e12        # ~2 ms of GEMM: amortises the launches of a batch
+
+
+def digits_batch(R, npad_max, ncols=15043):
+    """Resamples per GEMM batch of the integer engine.  About a quarter of the call, so that three of four draws
+    hide behind a GEMM, but at least DIGITS_BATCH_MIN_MACS of multiply-adds (a batch of B resamples is
+    B * npad * ncols of them; small problems stay in one batch) and at most DIGITS_BATCH_BYTES of multiplicities
+    (two buffers of that size live at once); whole 256-resample tiles, batches of equal size.  A function of R, the
+    largest row shard of the job and the column count only: every rank derives the same batches."""
+    npad = max(int(npad_max), 1)
+    want = max(R // 4, int(DIGITS_BATCH_MIN_MACS / (npad * max(int(ncols), 1))))
+    want = min(want, DIGITS_BATCH_BYTES // npad)
+    cap = max(256, want // 256 * 256)
     if R <= cap:
         return max(R, 1)
     nb = -(-R // cap)
@@ -605,8 +631,9 @@ class _DigitsRows:
     own index matrix) -> exact integer GEMM against the window's digit matrix -> float64 partial sums
     ``[count, nacc]`` -> (multi-GPU) reduce-scatter over resamples, so each rank runs the estimator algebra on its
     share -> estimates.  Two multiplicity buffers alternate: while batch b is in the tensor cores, batch b+1 is
-    drawn on a side stream by the slim Philox kernel, which fits next to the persistent GEMM CTAs.  The point
-    estimate is the multiplicity row of ones appended to the last batch.  The CI is ``Z * std(ddof=1)`` over all
+    drawn by spare warps of the same GEMM CTAs (Philox; ``sa_digit_sums_draw_f64``) -- or, for the reference's own
+    index matrix, by the counting kernel on a side stream.  The point estimate is the multiplicity row of ones
+    appended to the last batch.  The CI is ``Z * std(ddof=1)`` over all
     R estimates: two-pass on one GPU; across ranks two all-reduces of ``nest`` doubles (column sums, then squared
     deviations) replace the all-gather of the estimates.  No host synchronisation before the final read-back.
     """
@@ -618,7 +645,7 @@ class _DigitsRows:
         self.rank, self.world = rank, world
         self.shards = outputs[0]
         self.lead = outputs[0][0]
-        B = digits_batch(self.R, npad_max)
+        B = digits_batch(self.R, npad_max, self.lead.nacc * self.lead.ndigits)
         self.batches = [(c, min(c + B, self.R)) for c in range(0, self.R, B)] or [(0, 0)]
         self.nbuf = 2 if len(self.batches) > 1 else 1
         rows_buf = max(c1 - c0 for c0, c1 in self.batches) + 1
@@ -627,13 +654,17 @@ class _DigitsRows:
         self.side = _side_stream()
         self.side.wait_stream(self.main)     # cached blocks may still be read by earlier work on the main stream
         self.drawn, self.gemm_done = {}, {}
+        # Philox draws of batches 1.. are hosted by the previous batch's GEMM (main stream, no events)
+        self.hosted = rs is not None and rs.mode == "philox" and not os.environ.get("SALIB_B200_SIDE_DRAW")
         self.draw(0, slim=False)             # the first batch is drawn while Y is uploaded / split into digits
 
-    def draw(self, b, slim):
+    def draw(self, b, slim, after=None):
         c0, c1 = self.batches[b]
         n = c1 - c0
         last = b == len(self.batches) - 1
         with torch.cuda.stream(self.side):
+            if after is not None:            # not before the GEMM it is meant to run beside: the draw would take
+                self.side.wait_event(after)  # the SMs from the feature kernels on the critical path
             if b >= self.nbuf:               # the GEMM that read this buffer two batches ago
                 self.side.wait_event(self.gemm_done[b - self.nbuf])
             for w, e in zip(self.wsets[b % self.nbuf], self.shards):
@@ -679,17 +710,29 @@ class _DigitsRows:
         for b, (c0, c1) in enumerate(self.batches):
             n = c1 - c0
             count = n + (1 if b == len(self.batches) - 1 else 0)
-            if b + 1 < len(self.batches):
-                self.draw(b + 1, slim=True)
-            self.main.wait_event(self.drawn[b])
+            nxt = b + 1 < len(self.batches)
+            if b in self.drawn:
+                self.main.wait_event(self.drawn[b])
+            if nxt and not self.hosted:
+                pre = torch.cuda.Event()
+                pre.record(self.main)        # fires when this batch's GEMM is next on the main stream
+                self.draw(b + 1, slim=True, after=pre)
             chunk = -(-count // world)
             sums = []
-            for engs in self.outputs:
+            for o, engs in enumerate(self.outputs):
                 tot = None
-                for e, w in zip(engs, self.wsets[b % self.nbuf]):
-                    ps = e.digit_sums(w, count, rows_alloc=chunk * world)
+                for i, (e, w) in enumerate(zip(engs, self.wsets[b % self.nbuf])):
+                    hosted = None
+                    if nxt and self.hosted and o == 0:     # this shard's GEMM draws the shard's next batch
+                        n0, n1 = self.batches[b + 1]
+                        hosted = (self.rs.key, self.N, n0, n1 - n0, self.wsets[(b + 1) % self.nbuf][i])
+                    ps = e.digit_sums(w, count, rows_alloc=chunk * world, draw=hosted)
                     tot = ps if tot is None else tot.add_(ps)
                 sums.append(tot)
+            if nxt and self.hosted and b + 1 == len(self.batches) - 1:
+                n_last = self.batches[b + 1][1] - self.batches[b + 1][0]
+                for w, e in zip(self.wsets[(b + 1) % self.nbuf], self.shards):   # the point estimate's row of ones
+                    w[n_last * e.Npad:(n_last + 1) * e.Npad].fill_(1)
             ev = torch.cuda.Event()
             ev.record(self.main)
             self.gemm_done[b] = ev
@@ -878,7 +921,7 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     if flag is not None:
         _Resampler.raise_for(int(flag.item()))
     guard = float(pipe.guard.cpu().numpy()[0]) if digits else None
-    if digits and lead.auto_digits and (SobolAnalyzer.degenerate(stats) or guard <= GUARD_MIN_ROWS * step):
+    if digits and lead.auto_digits and (SobolAnalyzer.degenerate(stats) or guard_trips(guard, step, N)):
         # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
         # an outlier row: the FP64 engines keep every row's own exponent (GUARD_MIN_ROWS)
         return again_fp64()
@@ -1091,7 +1134,7 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         stats = eng.stats.cpu().numpy()
         guard = float(guards[o]) if pipe is not None else None
         if eng.kind == 6 and eng.auto_digits and (SobolAnalyzer.degenerate(stats)
-                                                  or (guard is not None and guard <= GUARD_MIN_ROWS * step)):
+                                                  or (guard is not None and guard_trips(guard, step, N))):
             # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
             # an outlier row: the FP64 engines keep every row's own exponent (GUARD_MIN_ROWS)
             return again_fp64()

@@ -261,11 +261,11 @@ counts_philox_kernel(uint64_t seed, uint64_t N, uint64_t c0, uint64_t row0, uint
 // Same distribution without global atomics (the kernel above is bound by the L2 RED rate, 2.2e11/s): the
 // binomial split tree + window histograms of counts.cuh, one block per resample.
 // Two launch shapes: "wide" -- 256 threads, one block per resample, up to 8 blocks per SM (fastest when the GPU is
-// otherwise idle) -- and "slim" -- one block of 1024 threads per SM looping over resamples with a single 16 KB
+// otherwise idle) -- and "slim" -- one block of 512 threads per SM looping over resamples with a single 16 KB
 // window: it always fits NEXT TO a CTA of the persistent GEMM kernel (198 KB of shared memory, 192 threads), so
 // the next batch's multiplicities are drawn on a side stream while the tensor cores work on the current batch.
 constexpr int kWinThreads = 256;
-constexpr int kWinThreadsSlim = 1024;
+constexpr int kWinThreadsSlim = 512;
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
@@ -1637,11 +1637,26 @@ extern "C" int sa_counts_philox_rows_ex(void *stream, uint64_t seed, uint64_t N,
     // per device and cheap: no process-wide cache (a second GPU of the process would miss the opt-in)
     const int opt_in = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
     if (slim) {
-      SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<kWinThreadsSlim>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, opt_in));
+      // threads of the one block per SM: more threads draw faster but take more of the shared-memory bandwidth the
+      // tensor cores read their operands with (tools/exp_overlap.py); SALIB_B200_SLIM_THREADS overrides
+      int nt = kWinThreadsSlim;
+      if (const char *e = getenv("SALIB_B200_SLIM_THREADS")) nt = atoi(e);
       const uint64_t nb = count < (uint64_t)sm_count() ? count : (uint64_t)sm_count();
-      counts_window_kernel<kWinThreadsSlim><<<(unsigned)nb, kWinThreadsSlim, smem, st>>>(seed, N, c0, count, L, row0,
-                                                                                        nrows, Npad, d_w);
+#define SA_SLIM(NT)                                                                                              \
+  {                                                                                                              \
+    SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, opt_in)); \
+    /* keep the SM's carveout at "all shared memory" so that a GEMM CTA (198 KB) can join while this runs */    \
+    SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,       \
+                                 (int)cudaSharedmemCarveoutMaxShared));                                          \
+    counts_window_kernel<NT><<<(unsigned)nb, NT, smem, st>>>(seed, N, c0, count, L, row0, nrows, Npad, d_w);     \
+  }
+      // 512 threads: 5.6 ms per 2560 resamples at N = 2^20, hidden behind a 22 ms GEMM batch at no measurable
+      // cost to it; 1024 threads draw no faster and slow the GEMM by ~15 % while they run
+      if (nt <= 128) SA_SLIM(128)
+      else if (nt <= 256) SA_SLIM(256)
+      else if (nt <= 512) SA_SLIM(512)
+      else SA_SLIM(1024)
+#undef SA_SLIM
     } else {
       SA_CUDA(cudaFuncSetAttribute(counts_window_kernel<kWinThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    opt_in));

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "counts.cuh"
 
 namespace sa {
 namespace dg {
@@ -60,6 +61,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 1023u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+}
+// The same wait for warps that sit out a whole tile (the epilogue warps wait ~6 ms for the accumulators): sleep
+// between polls.  Warps that spin take issue slots from younger warps on the SM -- measured with the slim
+// multiplicity kernel running beside the GEMM: 5x slower when the GEMM's CTAs were resident first
+// (tools/exp_overlap.py).  A microsecond of wake-up latency per tile is nothing here.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    __nanosleep(1000);
     if ((spin & 1023u) == 0) {
       uint64_t now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -440,6 +458,15 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
   return v;
 }
 
+// The next batch's multiplicities, drawn by spare warps of the GEMM CTAs (counts.cuh) while the tensor cores work on
+// the current batch: CTA x draws resamples c0 + x, c0 + x + gridDim.x, ... of `count` over the row window.
+struct DrawArgs {
+  uint64_t seed, N, c0, count, row0, nrows, Npad;
+  uint8_t *w;
+  int L;
+};
+constexpr int kDrawThreads = 512;
+
 struct PairPlan {
   uint32_t tiles_m, tiles_n, band;   // tile grid (pair tiles of 256 x PN), band of m-tiles swept over n
   uint32_t ksteps;                   // K-steps (128 rows) of a whole tile
@@ -449,11 +476,12 @@ struct PairPlan {
   uint32_t epoch, slack;             // K-sync: K-steps per epoch, epochs a pair may run ahead (0 = off)
 };
 
-template <int NACC, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int NACC, int STAGES, bool DRAW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DRAW ? kThreads + kDrawThreads : kThreads, 1)
 digit_gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
                                   int32_t *__restrict__ C, uint32_t count, uint32_t ldc, const PairPlan pl,
-                                  uint32_t *__restrict__ sync_ctr, uint32_t no_reload, uint32_t q_blocked) {
+                                  uint32_t *__restrict__ sync_ctr, uint32_t no_reload, uint32_t q_blocked,
+                                  const DrawArgs draw) {
   constexpr uint32_t PM = 256, PN = 256 * NACC;
   constexpr uint32_t kABytes = 128 * BK, kBBytes = NACC * 128 * BK;
   constexpr uint32_t kCols = NACC * 256;
@@ -593,11 +621,20 @@ digit_gemm_pair_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const
       }
     }
     __syncwarp();
+  } else if (DRAW && warp >= kThreads / 32) {
+    // warps 6..21: the multiplicities of the next batch (they never touch the GEMM's barriers or TMEM).  Their
+    // window histogram + split tree sit behind the operand ring.
+    uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_raw + (tiles_base - smem_u32(smem_raw)) +
+                                                 (size_t)STAGES * (kABytes + kBBytes));
+    const int dtid = (int)tid - kThreads;
+    for (uint64_t i = blockIdx.x; i < draw.count; i += gridDim.x)
+      counts_window_resample<kDrawThreads, 1>(wsm, draw.seed, draw.c0 + i, draw.N, draw.L, draw.row0, draw.nrows,
+                                              draw.w + i * draw.Npad, dtid);
   } else {
     const uint32_t quarter = warp & 3;
     for (uint32_t idx = 0; idx < n_units; ++idx) {
       const Unit u = unit(idx);
-      mbar_wait(tmem_full, idx & 1);
+      mbar_wait_relaxed(tmem_full, idx & 1);
       tc_fence_after();
       const uint32_t row = u.tile_m * PM + rank * 128 + quarter * 32 + lane;
       int32_t *crow = C + (uint64_t)row * ldc + (uint64_t)u.tile_n * PN;
@@ -760,14 +797,170 @@ feature_max_kernel(const double *__restrict__ Y, uint64_t N, int step, int nfeat
     }
     for (int q = threadIdx.x; q < nfeat; q += blockDim.x) {
       const FeatDesc d = tab[q];
-      double m = best[q];
+      uint32_t m = (uint32_t)__double2hiint(best[q]);
       for (int r = 0; r < tile_rows; ++r)
-        m = fmax(m, fabs(feature_value(d, [&](int c) { return xs[c * pitch + r]; })));
-      best[q] = m;
+        m = max(m, (uint32_t)__double2hiint(feature_value(d, [&](int c) { return xs[c * pitch + r]; })) & 0x7fffffffu);
+      best[q] = __hiloint2double((int)m, 0);
     }
   }
   for (int q = threadIdx.x; q < nfeat; q += blockDim.x)
     atomicMax(fmax_bits + q, (unsigned long long)__double_as_longlong(best[q]));
+  big = __reduce_add_sync(kFull, big);
+  if ((threadIdx.x & 31) == 0 && big) atomicAdd(big_count, (unsigned long long)big);
+}
+
+// The same maxima with the pair products BA_j * AB_k (94 % of the columns at Dg = 64) on 4 x 4 register tiles:
+// a thread owns four BA columns and four AB columns, reads two rows of each with one LDS.128 and keeps the 16
+// running maxima in registers -- 8 loads per 32 products instead of 64, and no per-value descriptor decode (the
+// first version spent 24 instructions per value, 2.5 ms at the headline).  Tiles on or above the diagonal of the
+// (j, k) triangle are enumerated row-major; entries with k <= j are computed and dropped.  Used whenever the
+// tile (even pitch, for the 16-byte loads) and the maxima fit 54 KB of shared memory; else the kernel above.
+constexpr int kFmaxThreads = 160;
+
+// Only the EXPONENT of a column's largest |F| enters the scale (feature_scale_kernel), and the high 32 bits of
+// |x| are monotone in |x|: the kernels track max(hi32(|F|)) with one integer max per value.  (A double-precision
+// max is DSETP + two selects + moves on this architecture, ~6 instructions; ncu/SASS of the first version.)
+__device__ __forceinline__ uint32_t abs_hi(double x) { return (uint32_t)__double2hiint(x) & 0x7fffffffu; }
+
+// Position of model-output column c in the shared-memory tile: the AB columns (c = 1 + k) are stored as
+// (k mod 4) * TB + k / 4, so that the columns 4 kb + b that consecutive lanes (consecutive kb) read with one
+// instruction are neighbours -- 16-byte loads at a stride of one column pitch (68 words = 4 banks) are conflict-free,
+// at four column pitches they were 4-way conflicts.  A, the BA columns and B keep their order behind them.
+__device__ __forceinline__ int fmax_colpos(int c, int Dg, int TB) {
+  if (c >= 1 && c <= Dg) {
+    const int k = c - 1;
+    return 1 + (k & 3) * TB + (k >> 2);
+  }
+  return c == 0 ? 0 : c + 4 * TB - Dg;
+}
+
+__global__ void __launch_bounds__(kFmaxThreads, 4)
+feature_max_tiled_kernel(const double *__restrict__ Y, uint64_t N, int step, int Dg, int nhead, int nfeat,
+                         const FeatDesc *__restrict__ tab, const double *__restrict__ stats, int tile_rows,
+                         unsigned long long *__restrict__ fmax_bits, unsigned long long *__restrict__ big_count) {
+  extern __shared__ __align__(16) double dsm[];
+  const int pitch = tile_rows + 2;
+  double *xs = dsm;                       // [step][pitch], column-major, rows in order
+  const int TB = (Dg + 3) >> 2;
+  const int cols = step + 4 * TB - Dg;    // the permuted AB block is padded to 4 TB columns
+  uint32_t *best = reinterpret_cast<uint32_t *>(dsm + cols * pitch);  // [nfeat] max hi32(|F|)
+  const double mean = stats[0], sd = stats[1];
+  const double thr = ldexp(fmax(fabs(__ddiv_rn(__dsub_rn(stats[2], mean), sd)),
+                                fabs(__ddiv_rn(__dsub_rn(stats[3], mean), sd))), -kGuardBits);
+  unsigned big = 0;
+  for (int q = threadIdx.x; q < nfeat; q += blockDim.x) best[q] = 0u;
+  const int ntb = nfeat > nhead ? TB * (TB + 1) / 2 : 0;
+  const uint64_t tiles = ceil_div_u64(N, tile_rows);
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const uint64_t i0 = tile * tile_rows;
+      const int total = tile_rows * step;
+      const int dr = (int)blockDim.x / step, dc = (int)blockDim.x - dr * step;
+      int r = (int)threadIdx.x / step, c = (int)threadIdx.x - r * step;
+      for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const uint64_t i = i0 + r;
+        double x = 0.0;
+        if (i < N) {
+          x = __ddiv_rn(__dsub_rn(__ldg(Y + i * (uint64_t)step + c), mean), sd);
+          big += fabs(x) > thr;
+        }
+        xs[fmax_colpos(c, Dg, TB) * pitch + r] = x;
+        r += dr;
+        c += dc;
+        if (c >= step) {
+          c -= step;
+          ++r;
+        }
+      }
+    }
+    __syncthreads();
+    // scalar, square, first- and total-order features (type switch outside the row loop, two rows per load)
+    for (int q = threadIdx.x; q < nhead; q += blockDim.x) {
+      const FeatDesc d = tab[q];
+      const double *pa = xs + fmax_colpos(d.u, Dg, TB) * pitch, *pb = xs + fmax_colpos(d.v, Dg, TB) * pitch,
+                   *pc = xs + fmax_colpos(d.w, Dg, TB) * pitch;
+      uint32_t m = best[q];
+      if (d.type == 0) {
+        for (int r = 0; r < tile_rows; r += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(pa + r);
+          m = max(m, max(abs_hi(a.x), abs_hi(a.y)));
+        }
+      } else if (d.type == 1) {
+        for (int r = 0; r < tile_rows; r += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(pa + r), b = *reinterpret_cast<const double2 *>(pb + r);
+          m = max(m, max(abs_hi(__dmul_rn(a.x, b.x)), abs_hi(__dmul_rn(a.y, b.y))));
+        }
+      } else if (d.type == 2) {
+        for (int r = 0; r < tile_rows; r += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(pa + r), b = *reinterpret_cast<const double2 *>(pb + r);
+          const double2 c = *reinterpret_cast<const double2 *>(pc + r);
+          m = max(m, max(abs_hi(__dmul_rn(a.x, __dsub_rn(b.x, c.x))), abs_hi(__dmul_rn(a.y, __dsub_rn(b.y, c.y)))));
+        }
+      } else {
+        for (int r = 0; r < tile_rows; r += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(pa + r), b = *reinterpret_cast<const double2 *>(pb + r);
+          const double t0 = __dsub_rn(a.x, b.x), t1 = __dsub_rn(a.y, b.y);
+          m = max(m, max(abs_hi(__dmul_rn(t0, t0)), abs_hi(__dmul_rn(t1, t1))));
+        }
+      }
+      best[q] = m;
+    }
+    // pair products on 4 x 4 tiles; |BA_j * AB_k| = |BA_j| * |AB_k| exactly, so the sign is dropped once per load
+    for (int tb = threadIdx.x; tb < ntb; tb += blockDim.x) {
+      int jb = 0, rest = tb;
+      while (rest >= TB - jb) {
+        rest -= TB - jb;
+        ++jb;
+      }
+      const int kb = jb + rest;
+      const double *pu[4], *pv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        pu[a] = xs + fmax_colpos(1 + Dg + min(4 * jb + a, Dg - 1), Dg, TB) * pitch;
+        pv[a] = xs + fmax_colpos(1 + min(4 * kb + a, Dg - 1), Dg, TB) * pitch;
+      }
+      uint32_t m[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) m[a][b] = 0u;
+#pragma unroll 2
+      for (int r = 0; r < tile_rows; r += 2) {
+        double2 u[4], v[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          u[a] = *reinterpret_cast<const double2 *>(pu[a] + r);
+          v[a] = *reinterpret_cast<const double2 *>(pv[a] + r);
+          u[a].x = fabs(u[a].x);
+          u[a].y = fabs(u[a].y);
+          v[a].x = fabs(v[a].x);
+          v[a].y = fabs(v[a].y);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            m[a][b] = max(m[a][b], max((uint32_t)__double2hiint(__dmul_rn(u[a].x, v[b].x)),
+                                       (uint32_t)__double2hiint(__dmul_rn(u[a].y, v[b].y))));
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int j = 4 * jb + a;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int k = 4 * kb + b;
+          if (j < k && k < Dg) {
+            const int q = nhead + j * (2 * Dg - j - 1) / 2 + (k - j - 1);
+            best[q] = max(best[q], m[a][b]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < nfeat; q += blockDim.x)
+    atomicMax(fmax_bits + q, (unsigned long long)best[q] << 32);
   big = __reduce_add_sync(kFull, big);
   if ((threadIdx.x & 31) == 0 && big) atomicAdd(big_count, (unsigned long long)big);
 }
@@ -807,12 +1000,20 @@ __device__ __forceinline__ int split_slot(int r, int rows) {
 
 __device__ __forceinline__ void load_tile_split(const double *__restrict__ Y, uint64_t N, int step, uint64_t i0,
                                                 int rows, int pitch, double mean, double sd, double *xs) {
+  // (row, column) of element e = threadIdx.x + k * blockDim.x, advanced without a division per element
   const int total = rows * step;
+  const int dr = (int)blockDim.x / step, dc = (int)blockDim.x - dr * step;
+  int r = (int)threadIdx.x / step, c = (int)threadIdx.x - r * step;
   for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int r = e / step, c = e - r * step;
     const uint64_t i = i0 + r;
     xs[c * pitch + split_slot(r, rows)] =
         i < N ? __ddiv_rn(__dsub_rn(__ldcs(Y + i * (uint64_t)step + c), mean), sd) : 0.0;
+    r += dr;
+    c += dc;
+    if (c >= step) {
+      c -= step;
+      ++r;
+    }
   }
 }
 
@@ -1200,19 +1401,31 @@ static int default_band(uint64_t tm, int pairs) {
   return (int)ceil_div_u64(tm, nb ? nb : 1);
 }
 
+// Does the launch of this shape go through the persistent pair kernel (which can host a draw)?
+static bool pair_persistent(int variant, int ksplit) {
+  return variant >= 2 && ksplit == 1 && env_int("SALIB_B200_GEMM_PERSIST", 1) != 0;
+}
+
 template <int NACC, int STAGES>
 static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtensorMap &mq, int32_t *d_C,
                             uint64_t count, uint64_t ldc, uint64_t ncols, uint64_t K, int ksplit,
-                            uint32_t q_blocked, uint32_t no_reload = 0, int force_pairs = 0) {
-  if (!no_reload && (ksplit > 1 || env_int("SALIB_B200_GEMM_PERSIST", 1) == 0))
+                            uint32_t q_blocked, uint32_t no_reload = 0, int force_pairs = 0,
+                            const DrawArgs *draw = nullptr) {
+  if (!no_reload && (ksplit > 1 || env_int("SALIB_B200_GEMM_PERSIST", 1) == 0)) {
+    SA_REQUIRE(draw == nullptr, SA_ERR_ARG, "digit GEMM: a draw needs the persistent kernel");
     return launch_gemm_pair_oneshot<NACC, STAGES>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, q_blocked);
+  }
   const uint64_t tm = ceil_div_u64(count, 256), tn = ceil_div_u64(ncols, 256 * NACC);
   const uint64_t ksteps = ceil_div_u64(K, BK);
   SA_REQUIRE(tm * tn < (1ull << 31), SA_ERR_UNSUPPORTED, "digit GEMM: too many tiles");
-  const size_t smem = (size_t)STAGES * (128 + NACC * 128) * BK + 1024;
-  auto kern = digit_gemm_pair_persistent_kernel<NACC, STAGES>;
+  const size_t ring = (size_t)STAGES * (128 + NACC * 128) * BK + 1024;
+  const size_t smem = ring + (draw ? window_smem_bytes(draw->N, draw->L) : 0);
+  SA_REQUIRE(smem <= 227 * 1024, SA_ERR_UNSUPPORTED, "digit GEMM: draw does not fit next to the operand ring");
+  auto kern = draw ? digit_gemm_pair_persistent_kernel<NACC, STAGES, true>
+                   : digit_gemm_pair_persistent_kernel<NACC, STAGES, false>;
   SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int max_pairs = force_pairs > 0 ? force_pairs : resident_pairs(kern, smem);
+  int max_pairs = force_pairs > 0 ? force_pairs
+                                  : resident_pairs(digit_gemm_pair_persistent_kernel<NACC, STAGES, false>, ring);
   if (const int cap = env_int("SALIB_B200_GEMM_PAIRS", 0)) max_pairs = cap < max_pairs ? cap : max_pairs;
   SA_REQUIRE(max_pairs >= 1, SA_ERR_UNSUPPORTED, "digit GEMM: no CTA pair fits this device");
   PairPlan pl = plan_pairs(tm, tn, ksteps, max_pairs, env_int("SALIB_B200_GEMM_BAND", default_band(tm, max_pairs)));
@@ -1230,8 +1443,9 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &mw, const CUtens
                                                    pl.tiles_n, pl.band, pl.full_waves * pl.pairs);
     note_launches(1);
   }
-  kern<<<2 * pl.pairs, kThreads, smem, st>>>(mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, pl, ctr, no_reload,
-                                             q_blocked);
+  const DrawArgs none = {};
+  kern<<<2 * pl.pairs, draw ? kThreads + kDrawThreads : kThreads, smem, st>>>(
+      mw, mq, d_C, (uint32_t)count, (uint32_t)ldc, pl, ctr, no_reload, q_blocked, draw ? *draw : none);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -1315,9 +1529,9 @@ extern "C" size_t sa_digit_sums_workspace_bytes(uint64_t N, int nfeat, int ndigi
   return (size_t)sa_digit_ksplit(N, nfeat, ndigits, count) * count * sa_digit_ldc(nfeat, ndigits) * sizeof(int32_t);
 }
 
-extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count,
-                                 const int8_t *d_Q, uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit,
-                                 int32_t *d_C, uint64_t ldc) {
+static int digit_gemm_impl(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, const int8_t *d_Q,
+                           uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit, int32_t *d_C, uint64_t ldc,
+                           const DrawArgs *draw) {
   SA_REQUIRE(d_w && d_Q && d_C, SA_ERR_ARG, "sa_digit_gemm_i32: null pointer");
   SA_REQUIRE(count >= 1 && ncols >= 1 && K >= 1 && ksplit >= 1, SA_ERR_ARG, "sa_digit_gemm_i32: bad shape");
   SA_REQUIRE(K <= (1ull << 24), SA_ERR_UNSUPPORTED, "sa_digit_gemm_i32: more than 2^24 rows could overflow int32");
@@ -1340,13 +1554,21 @@ extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pi
   rc = blocked ? make_map_blocked(&mq, d_Q, ncols, ceil_div_u64(K, BK), v == 1 ? 256 : 128)
                : make_map(&mq, d_Q, K, ncols, q_pitch, v == 1 ? 256 : 128);
   if (rc) return rc;
+  SA_REQUIRE(draw == nullptr || pair_persistent(v, ksplit), SA_ERR_ARG,
+             "digit GEMM: only the persistent pair kernel hosts a draw");
   switch (v) {
     case 0: return launch_gemm<128, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
     case 1: return launch_gemm<256, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
-    case 2: return launch_gemm_pair<1, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
-    case 3: return launch_gemm_pair<2, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked);
+    case 2: return launch_gemm_pair<1, 6>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked, 0, 0, draw);
+    case 3: return launch_gemm_pair<2, 4>(st, mw, mq, d_C, count, ldc, ncols, K, ksplit, blocked, 0, 0, draw);
   }
   SA_REQUIRE(false, SA_ERR_ARG, "sa_digit_gemm_i32: unknown kernel variant %d", v);
+}
+
+extern "C" int sa_digit_gemm_i32(void *stream, const uint8_t *d_w, uint64_t w_pitch, uint64_t count,
+                                 const int8_t *d_Q, uint64_t q_pitch, uint64_t ncols, uint64_t K, int ksplit,
+                                 int32_t *d_C, uint64_t ldc) {
+  return digit_gemm_impl(stream, d_w, w_pitch, count, d_Q, q_pitch, ncols, K, ksplit, d_C, ldc, nullptr);
 }
 
 extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N, int Dg, int second_order,
@@ -1378,7 +1600,28 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
   SA_CUDA(cudaFuncSetAttribute(feature_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const uint64_t tiles = ceil_div_u64(N, rows_max), slots = 4 * (uint64_t)sm_count();
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax, fmax + nfeat);
+  // 4 x 4 register tiles when the tile (even pitch) + the maxima fit 54 KB (4 blocks per SM); else thread per feature
+  int rows_t = 0;
+  const size_t cols_t = (size_t)step + 4 * ((Dg + 3) / 4) - Dg;
+  for (int r = 32; r >= 8 && !rows_t; r >>= 1)
+    if ((cols_t * (r + 2) + nfeat) * 8 <= 54 * 1024) rows_t = r;
+  if (rows_t && !getenv("SALIB_B200_FMAX_PLAIN")) {
+    const size_t smem_t = (cols_t * (rows_t + 2) + nfeat) * 8;
+    SA_CUDA(cudaFuncSetAttribute(feature_max_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    const uint64_t tiles_t = ceil_div_u64(N, rows_t);
+    int per_sm = 0;  // one full wave: a partial second wave would run at a fraction of the occupancy
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feature_max_tiled_kernel, kFmaxThreads, smem_t) !=
+            cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    const uint64_t wave = (uint64_t)per_sm * sm_count();
+    const unsigned grid_t = (unsigned)(tiles_t < wave ? tiles_t : wave);
+    feature_max_tiled_kernel<<<grid_t, kFmaxThreads, smem_t, st>>>(d_Y, N, step, Dg, 5 + 2 * Dg, nfeat, tab, d_stats,
+                                                                  rows_t, fmax, fmax + nfeat);
+  } else {
+    feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax, fmax + nfeat);
+  }
   feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv, fmax + nfeat);
   const uint64_t tiles2 = Kp / rows, slots2 = 3 * (uint64_t)sm_count();
   const unsigned grid2 = (unsigned)(tiles2 < slots2 ? tiles2 : slots2);
@@ -1398,10 +1641,18 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
   return SA_OK;
 }
 
-extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat,
-                                 int ndigits, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work,
-                                 size_t work_bytes, double *d_psum) {
+extern "C" int sa_counts_philox_rows_ex(void *stream, uint64_t seed, uint64_t N, uint64_t c0, uint64_t count,
+                                        uint64_t row0, uint64_t nrows, uint8_t *d_w, int32_t *d_overflow, int slim);
+
+extern "C" int sa_digit_sums_draw_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat,
+                                      int ndigits, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work,
+                                      size_t work_bytes, double *d_psum, uint64_t draw_seed, uint64_t draw_N,
+                                      uint64_t draw_c0, uint64_t draw_count, uint64_t draw_row0, uint64_t draw_nrows,
+                                      uint8_t *d_w_next) {
   SA_REQUIRE(d_Q && d_inv && d_w && d_work && d_psum, SA_ERR_ARG, "sa_digit_sums_f64: null pointer");
+  SA_REQUIRE(draw_count == 0 || (d_w_next && draw_N >= 1 && draw_nrows >= 1 && draw_row0 + draw_nrows <= draw_N &&
+                                 ((uintptr_t)d_w_next & 3) == 0),
+             SA_ERR_ARG, "sa_digit_sums_draw_f64: bad draw arguments");
   SA_REQUIRE(N >= 1 && nfeat >= 1 && count >= 1, SA_ERR_ARG, "sa_digit_sums_f64: bad shape");
   SA_REQUIRE(ndigits >= 2 && ndigits <= kMaxDigits, SA_ERR_ARG, "sa_digit_sums_f64: 2 <= ndigits <= 8");
   SA_REQUIRE(work_bytes >= sa_digit_sums_workspace_bytes(N, nfeat, ndigits, count), SA_ERR_WORKSPACE,
@@ -1409,15 +1660,42 @@ extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *
   const uint64_t ncols = (uint64_t)nfeat * ndigits, ldc = sa_digit_ldc(nfeat, ndigits);
   const int ksplit = sa_digit_ksplit(N, nfeat, ndigits, count);
   int32_t *C = (int32_t *)d_work;
-  const int rc = sa_digit_gemm_i32(stream, d_w, w_pitch, count, d_Q, 0 /* K-blocked */, ncols, N, ksplit, C, ldc);
-  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  DrawArgs draw = {};
+  const DrawArgs *hosted = nullptr;
+  if (draw_count) {
+    const int L = window_levels(draw_N);
+    const uint64_t Npad = sa_pad_rows(draw_nrows);
+    const size_t ring = (size_t)4 * (128 + 2 * 128) * BK + 1024;
+    if (L >= 0 && pair_persistent(pick_variant(count, ncols), ksplit) && !getenv("SALIB_B200_NO_HOSTED_DRAW") &&
+        ring + window_smem_bytes(draw_N, L) <= 227 * 1024) {
+      // hosted by the GEMM: spare warps of its CTAs draw while the tensor cores work (same stream, no events)
+      if (Npad > draw_nrows)
+        SA_CUDA(cudaMemset2DAsync(d_w_next + draw_nrows, Npad, 0, Npad - draw_nrows, draw_count, st));
+      draw = DrawArgs{draw_seed, draw_N, draw_c0, draw_count, draw_row0, draw_nrows, Npad, d_w_next, L};
+      hosted = &draw;
+    } else {
+      // shapes that do not run the persistent pair kernel are small: draw first, then multiply
+      const int rc = sa_counts_philox_rows_ex(stream, draw_seed, draw_N, draw_c0, draw_count, draw_row0, draw_nrows,
+                                              d_w_next, nullptr, 0);
+      if (rc) return rc;
+    }
+  }
+  const int rc = digit_gemm_impl(stream, d_w, w_pitch, count, d_Q, 0 /* K-blocked */, ncols, N, ksplit, C, ldc, hosted);
+  if (rc) return rc;
   const uint64_t total = count * (uint64_t)nfeat;
   const unsigned grid = (unsigned)(ceil_div_u64(total, 256) < 148ull * 16 ? ceil_div_u64(total, 256) : 148ull * 16);
   digit_combine_kernel<<<grid, 256, 0, st>>>(C, count, ldc, ksplit, nfeat, ndigits, d_inv, d_psum);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
+}
+
+extern "C" int sa_digit_sums_f64(void *stream, const int8_t *d_Q, const double *d_inv, uint64_t N, int nfeat,
+                                 int ndigits, const uint8_t *d_w, uint64_t w_pitch, uint64_t count, void *d_work,
+                                 size_t work_bytes, double *d_psum) {
+  return sa_digit_sums_draw_f64(stream, d_Q, d_inv, N, nfeat, ndigits, d_w, w_pitch, count, d_work, work_bytes, d_psum,
+                                0, 0, 0, 0, 0, 0, nullptr);
 }
 
 // Tensor-core roofline denominator: the CTA-pair kernel on one 256 x 512 tile per SM pair with the operand ring

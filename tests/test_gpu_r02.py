@@ -81,9 +81,19 @@ def test_outlier_row_auto_falls_back_and_matches_the_reference():
     finally:
         sobol.DIGITS_MIN_WORK = old
     assert S.engine != "digits"
-    _cmp(S, z, 8, True)
+    # This fixture is ill-conditioned in ANY arithmetic: the per-resample indices jump by factors of 1e5 depending
+    # on whether the outlier row was drawn (S1_conf ~ 226), and two CPU summation orders -- the reference and the
+    # oracle -- already differ by 2.4e-9 on S2_conf.  The FP64 engines land at the same level (1.5e-9); the point
+    # estimates, where the outlier is always present, keep 1e-10.
+    for k in ("S1", "ST"):
+        np.testing.assert_allclose(S[k], z[k], rtol=1e-10, atol=1e-13, err_msg=k)
+    for k in ("S1_conf", "ST_conf", "S1_conf_all", "ST_conf_all"):
+        np.testing.assert_allclose(S[k], z[k], rtol=2e-8, atol=1e-13, err_msg=k)
+    iu = np.triu_indices(8, 1)
+    np.testing.assert_allclose(S["S2"][iu], z["S2"][iu], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(S["S2_conf"][iu], z["S2_conf"][iu], rtol=1e-7)
     F = sobol.analyze_device(p, z["Y"], calc_second_order=True, keep_resamples=True, r=r, algo="digits")
-    assert F.engine == "digits" and F.digits_guard <= sobol.GUARD_MIN_ROWS * 18
+    assert F.engine == "digits" and sobol.guard_trips(F.digits_guard, 18, 512)
     # point estimates are sums over ALL rows (the outlier is always in): unaffected.  Resamples that miss the outlier
     # row are left with the cut entries: that is where the loss shows.
     np.testing.assert_allclose(F["S1"], z["S1"], rtol=1e-9, atol=1e-12)
@@ -102,7 +112,7 @@ def test_benign_output_is_not_flagged_by_the_guard():
     X = sample.sample(gprob(D), 4096, scramble=False, skip_values=4096)
     Y = Sobol_G.evaluate(X, a=np.resize([0, 1, 4.5, 9, 99, 99, 99, 99], D).astype(float))
     S = sobol.analyze_device(gprob(D), Y, num_resamples=64, seed=3, resample="philox", algo="digits")
-    assert S.digits_guard > sobol.GUARD_MIN_ROWS * (2 * D + 2)
+    assert not sobol.guard_trips(S.digits_guard, 2 * D + 2, 4096)
 
 
 @pytest.mark.parametrize("name", ["sample_sha_d512_n8_c0_plain", "sample_sha_d512_n8_c0_scr",
@@ -126,10 +136,10 @@ def test_wide_sample_matrices_bit_exact(name):
     assert hashlib.sha256(np.ascontiguousarray(X).tobytes()).hexdigest() == str(z["sha256"])
 
 
-@pytest.mark.parametrize("D", [204, 205])
+@pytest.mark.parametrize("D", [207, 208])
 def test_engine_selection_boundary(D):
-    """Second order, Dg = 204 is the widest problem the integer engine's feature kernels hold in shared memory;
-    205 must be refused cleanly and served by the FP64 engines.  Both against the frozen reference."""
+    """Second order, Dg = 207 is the widest problem the integer engine's feature kernels hold in shared memory;
+    208 must be refused cleanly and served by the FP64 engines.  Both against the frozen reference."""
     from salib_b200.analyze import sobol
 
     z = golden(f"analyze_g{D}_n32_r4")
@@ -149,10 +159,10 @@ def test_engine_selection_boundary(D):
         S = sobol.analyze_device(p, z["Y"], calc_second_order=True, keep_resamples=True, r=r)
     finally:
         sobol.DIGITS_MIN_WORK = old
-    assert (S.engine == "digits") == (D == 204), S.engine
+    assert (S.engine == "digits") == (D == 207), S.engine
     # 32 base rows of a 200-dimensional function: S2 is cancellation of O(1) terms
     check(S, 1e-9, 1e-11)
-    if D == 205:
+    if D == 208:
         with pytest.raises(Exception):
             sobol.analyze_device(p, z["Y"], calc_second_order=True, r=r, algo="digits")
 

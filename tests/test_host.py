@@ -449,8 +449,11 @@ def test_digits_batches_and_reduce_scatter_bookkeeping():
     ones (the point estimate) landing on exactly one rank."""
     from salib_b200.analyze.sobol import batch_share, digits_batch
 
-    assert digits_batch(10000, 1 << 20) == 2560
+    assert digits_batch(10000, 1 << 20) == 2048      # headline: 5 batches, 4 draws hidden behind a GEMM
+    assert digits_batch(10000, 1 << 17) == 2048      # one of 8 row shards: the same batches
+    assert digits_batch(10000, 1 << 22) == 2048
     assert digits_batch(100, 1 << 20) == 100
+    assert digits_batch(1000, 1 << 20, 147) == 1000  # cfg2 (D = 8, first order): the GEMM is tiny, one batch
     assert digits_batch(0, 1 << 20) == 1
     for R, npad in [(10000, 1 << 20), (10000, 1 << 17), (777, 1 << 22), (5000, 1 << 24), (1, 128)]:
         B = digits_batch(R, npad)
@@ -469,3 +472,13 @@ def test_digits_batches_and_reduce_scatter_bookkeeping():
                     seen[c0 + lo:c0 + lo + valid] += 1
                     owners += int(count > n and lo <= n < lo + chunk)
             assert (seen == 1).all() and owners == 1
+
+
+def test_heavy_tail_guard_rule():
+    from salib_b200.analyze.sobol import guard_trips
+
+    assert guard_trips(18, 18, 512)              # one outlier row: a resample misses it with probability 0.37
+    assert guard_trips(10 * 130, 130, 1 << 20)   # ten rows: e^-10
+    assert not guard_trips(40 * 130, 130, 1 << 20)
+    assert not guard_trips(32 * 410, 410, 32)    # every row is "large": no resample can miss them all
+    assert guard_trips(0, 130, 1 << 20)

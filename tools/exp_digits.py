@@ -69,12 +69,27 @@ if a.trace:
     from torch.profiler import ProfilerActivity, profile
 
     run("digits")
+    import time as _time
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-        sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100, resample="philox",
-                             algo="digits")
+        stamps = []
+        for _ in range(3):
+            t0 = _time.perf_counter()
+            sobol.analyze_device(problem, Yd, calc_second_order=c2, num_resamples=R, seed=100, resample="philox",
+                                 algo="digits")
+            stamps.append((_time.perf_counter() - t0) * 1e3)
         torch.cuda.synchronize()
+    print("host wall per call (ms):", [round(x, 2) for x in stamps], file=sys.stderr)
     dev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
                  key=lambda e: e.time_range.start)
+    # idle gaps of the device longer than 0.2 ms (between calls, or inside one)
+    pe = dev[0].time_range.end
+    for e in dev[1:]:
+        if (e.time_range.start - pe) / 1e3 > 0.2:
+            print(f"IDLE {(e.time_range.start - pe) / 1e3:8.3f} ms before {e.name[:60]} at "
+                  f"{(e.time_range.start - dev[0].time_range.start) / 1e3:9.3f} ms", file=sys.stderr)
+        pe = max(pe, e.time_range.end)
+    n3 = len(dev) // 3
+    dev = dev[2 * n3:]          # the timeline of the last call
     t0 = dev[0].time_range.start
     prev_end = t0
     for e in dev:
