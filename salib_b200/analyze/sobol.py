@@ -608,10 +608,16 @@ def digits_batch(R, npad_max, ncols=15043):
     return min(cap, -(-(-(-R // nb)) // 256) * 256)
 
 
+_SIDE_STREAMS = {}
+
+
 def _side_stream():
-    """Stream of the multiplicity draws that run beside the GEMM (the slim Philox kernel needs no priority: it
-    fits next to a GEMM CTA whichever kernel reaches an SM first)."""
-    return torch.cuda.Stream()
+    """Stream of the first batch's multiplicity draw (and of the index-matrix counting kernels), which run beside
+    the upload of Y and the feature kernels.  One per device, created once."""
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = torch.cuda.Stream()
+    return _SIDE_STREAMS[dev]
 
 
 def batch_share(n, count, world, g):
@@ -774,8 +780,12 @@ class _DigitsRows:
         # heavy-tail guard: values near the design's largest |x|, over all local shards (and ranks)
         self.guard = torch.stack([torch.stack([e.inv[e.nacc] for e in engs]).sum() for engs in self.outputs])
         if world > 1:
-            dist.all_reduce(point)           # zero everywhere but on the rank that owned the row of ones
-            dist.all_reduce(self.guard)
+            # one collective: the point estimates (zero everywhere but on the rank that owned the row of ones) and
+            # the guard counts
+            both = torch.cat([point.reshape(-1), self.guard])
+            dist.all_reduce(both)
+            point = both[:nout * nest].reshape(nout, nest)
+            self.guard = both[nout * nest:]
         kept = [None] * nout
         if keep:
             for o in range(nout):
@@ -842,7 +852,8 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
 
     engines = build(algo)
     # every rank must take the same engine family and the same batches: one tiny all-reduce
-    not_digits, npad_max = _agree([0 if all(e.kind == 6 for e in engines) else 1, max(e.Npad for e in engines)])
+    not_digits, npad_max, nsh = _agree([0 if all(e.kind == 6 for e in engines) else 1,
+                                        max(e.Npad for e in engines), len(engines)])
     if not_digits and any(e.kind == 6 for e in engines):
         engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
     digits = not not_digits
@@ -876,10 +887,9 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         Yd = rt.to_device(Y, torch.float64, non_blocking=True).reshape(-1)
         eng.moments(Yd)
         loaded.append(Yd)
-        parts[i, 0] = float(Yd.numel())
+        parts[i, 0].fill_(float(Yd.numel()))     # a fill kernel, not a pageable host-to-device copy
         parts[i, 1:].copy_(eng.stats)
     if world > 1:
-        nsh = _agree([len(engines)])[0]
         mine = rt.zeros((nsh, 9), torch.float64)
         mine[:len(engines)] = parts
         parts = rt.empty((world * nsh, 9), torch.float64)
@@ -911,16 +921,19 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         point, conf, kept, flag = _row_sharded_fp64(engines, N, R, rs, Z, bool(keep_resamples), npad_max, prefetch,
                                                     world)
 
-    # one read-back: results, statistics, flags
-    point_h, conf_h = point.reshape(-1).cpu().numpy(), conf.cpu().numpy()
-    stats = lead.stats.cpu().numpy()
-    if stats9 is not None:
-        total = int(round(float(stats9.cpu().numpy()[8])))
-        if total != N * step:
-            raise RuntimeError(f"row shards hold {total // step} base rows, expected {N}")
-    if flag is not None:
-        _Resampler.raise_for(int(flag.item()))
-    guard = float(pipe.guard.cpu().numpy()[0]) if digits else None
+    # ONE read-back (one synchronisation): results, statistics, row count, flags, guard
+    nest = lead.nest
+    one = torch.ones((1,), dtype=torch.float64, device=rt.device())
+    host = torch.cat([point.reshape(-1)[:nest], conf.reshape(-1)[:nest], lead.stats.reshape(-1)[:8],
+                      stats9[8:9] if stats9 is not None else one * float(N * step),
+                      flag.to(torch.float64) if flag is not None else one * 0.0,
+                      pipe.guard[:1] if digits else one * 0.0]).cpu().numpy()
+    point_h, conf_h, stats = host[:nest], host[nest:2 * nest], host[2 * nest:2 * nest + 8]
+    total = int(round(float(host[2 * nest + 8])))
+    if total != N * step:
+        raise RuntimeError(f"row shards hold {total // step} base rows, expected {N}")
+    _Resampler.raise_for(int(host[2 * nest + 9]))
+    guard = float(host[2 * nest + 10]) if digits else None
     if digits and lead.auto_digits and (SobolAnalyzer.degenerate(stats) or guard_trips(guard, step, N)):
         # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
         # an outlier row: the FP64 engines keep every row's own exponent (GUARD_MIN_ROWS)
@@ -1106,7 +1119,7 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         points = [p.reshape(1, -1) for p, _, _ in res]
         confs = [c for _, c, _ in res]
         kepts = [k for _, _, k in res]
-        guards = pipe.guard.cpu().numpy()
+        guards = pipe.guard
     else:
         points = []
         ests = [None] * len(engines)
@@ -1129,10 +1142,21 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
 
     out = []
     step = 2 * Dg + 2 if calc_second_order else Dg + 2
-    for o, (eng, point, conf, kept) in enumerate(zip(engines, points, confs, kepts)):
-        point_h, conf_h = point[0].cpu().numpy(), conf.cpu().numpy()
-        stats = eng.stats.cpu().numpy()
-        guard = float(guards[o]) if pipe is not None else None
+    # ONE read-back for all outputs: results, statistics, guard counts, the resampler's flag
+    nest = engines[0].nest
+    zero = torch.zeros((1,), dtype=torch.float64, device=rt.device())
+    pieces = []
+    for o, (eng, point, conf) in enumerate(zip(engines, points, confs)):
+        pieces += [point.reshape(-1)[:nest], conf.reshape(-1)[:nest], eng.stats.reshape(-1)[:8],
+                   guards[o:o + 1] if pipe is not None else zero]
+    pieces.append(rs.flag.to(torch.float64) if rs is not None else zero)
+    host = torch.cat(pieces).cpu().numpy()
+    _Resampler.raise_for(int(host[-1]))
+    per = 2 * nest + 9
+    for o, (eng, kept) in enumerate(zip(engines, kepts)):
+        h = host[o * per:(o + 1) * per]
+        point_h, conf_h, stats = h[:nest], h[nest:2 * nest], h[2 * nest:2 * nest + 8]
+        guard = float(h[2 * nest + 8]) if pipe is not None else None
         if eng.kind == 6 and eng.auto_digits and (SobolAnalyzer.degenerate(stats)
                                                   or (guard is not None and guard_trips(guard, step, N))):
             # non-finite / constant outputs: the reference's behaviour comes from the FP64 engines;
@@ -1151,8 +1175,6 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         S.resample_mode = rs.mode if rs is not None else None
         S.digits_guard = guard
         out.append(S)
-    if rs is not None:
-        rs.check()
     return out
 
 
