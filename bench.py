@@ -607,12 +607,12 @@ def main():
                              "engine": S8.engine,
                              "S1_within_CI_of_analytic": bool(np.all(np.abs(S8["S1"] - an8) <= 2.0 * S8["S1_conf"] + 1e-3))}
             del Y8
-            # configs[3]: points of the sample-generation sweep (chunked into a reused buffer beyond 32 GB)
+            # configs[3]: points of the sample-generation sweep (chunked into a reused buffer beyond 64 GB)
             pts = []
             for Dq, lq, scr in ((16, 22, False), (128, 20, False), (128, 20, True), (1024, 16, False)):
                 stepq, Nq = 2 * Dq + 2, 1 << lq
                 chunk = Nq
-                while stepq * chunk * Dq * 8 > 3.2e10:
+                while stepq * chunk * Dq * 8 > 6.4e10:
                     chunk //= 2
                 svq, shq = sample_sobol._scramble_state(2 * Dq, scr, 1234)
                 planq = sample_sobol.SamplePlan(g_problem(Dq), True, svq, shq)

@@ -608,6 +608,23 @@ def digits_batch(R, npad_max, ncols=15043):
     return min(cap, -(-(-(-R // nb)) // 256) * 256)
 
 
+def digits_batches(R, npad_max, ncols=15043, first=None):
+    """The [c0, c1) resample ranges of the integer engine's GEMM batches.  Equal batches of ``digits_batch``; with
+    ``first`` (module default DIGITS_FIRST_BATCH, a multiple of 256 below the batch size) the first batch is that
+    short: it is the only one whose multiplicities are drawn by a kernel of their own, in front of the first GEMM
+    -- every later batch is drawn inside the previous batch's GEMM."""
+    B = digits_batch(R, npad_max, ncols)
+    first = DIGITS_FIRST_BATCH if first is None else int(first)
+    if not first or R <= B or first >= B:
+        return [(c, min(c + B, R)) for c in range(0, R, B)] or [(0, 0)]
+    rest = R - first
+    nb = -(-rest // B)
+    Bs = min(B, -(-(-(-rest // nb)) // 256) * 256)
+    return [(0, first)] + [(c, min(c + Bs, R)) for c in range(first, R, Bs)]
+
+
+DIGITS_FIRST_BATCH = int(os.environ.get("SALIB_B200_FIRST_BATCH", "0"))
+
 _SIDE_STREAMS = {}
 
 
@@ -651,8 +668,7 @@ class _DigitsRows:
         self.rank, self.world = rank, world
         self.shards = outputs[0]
         self.lead = outputs[0][0]
-        B = digits_batch(self.R, npad_max, self.lead.nacc * self.lead.ndigits)
-        self.batches = [(c, min(c + B, self.R)) for c in range(0, self.R, B)] or [(0, 0)]
+        self.batches = digits_batches(self.R, npad_max, self.lead.nacc * self.lead.ndigits)
         self.nbuf = 2 if len(self.batches) > 1 else 1
         rows_buf = max(c1 - c0 for c0, c1 in self.batches) + 1
         self.wsets = [[rt.empty((rows_buf * e.Npad,), torch.uint8) for e in self.shards] for _ in range(self.nbuf)]
@@ -812,7 +828,7 @@ class _DigitsRows:
 
 def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resamples=100, conf_level=0.95,
                         keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
-                        kernel_events=None):
+                        kernel_events=None, agreed=None):
     """``analyze`` for a model output partitioned by base-row range ("when Y exceeds one GPU") --
     and the route of the integer engine in general (one GPU = one shard with every row).
 
@@ -852,8 +868,11 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
 
     engines = build(algo)
     # every rank must take the same engine family and the same batches: one tiny all-reduce
-    not_digits, npad_max, nsh = _agree([0 if all(e.kind == 6 for e in engines) else 1,
-                                        max(e.Npad for e in engines), len(engines)])
+    mine = [0 if all(e.kind == 6 for e in engines) else 1, max(e.Npad for e in engines), len(engines)]
+    if agreed is not None and not agreed[0] and not mine[0]:
+        not_digits, npad_max, nsh = agreed  # the caller (analyze_device, "auto") has asked every rank already
+    else:
+        not_digits, npad_max, nsh = _agree(mine)
     if not_digits and any(e.kind == 6 for e in engines):
         engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
     digits = not not_digits
@@ -1193,6 +1212,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
     the strategy switch the reference makes inside ``analyze`` (analyze/sobol.py:147,183).
     """
     rank, world = rt.world() if distributed else (0, 1)
+    agreed = None
     if shard == "auto":
         shard = "resamples"
         if world > 1:
@@ -1201,9 +1221,13 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
             N = _n_from_size(size, Dg, calc_second_order)
             lo, hi = rt.shard_range(N, rank, world)
             R_req = np.shape(r)[1] if r is not None else int(num_resamples)
-            mine = hi > lo and SobolAnalyzer(Dg, hi - lo, calc_second_order, algo=algo, resamples=R_req,
-                                             total_rows=N).kind == 6
-            if not _agree([0 if mine else 1])[0]:
+            eng = SobolAnalyzer(Dg, hi - lo, calc_second_order, algo=algo, resamples=R_req,
+                                total_rows=N) if hi > lo else None
+            mine = eng is not None and eng.kind == 6
+            # the one agreement of the call: engine family, largest row shard, shards per rank (handed on to
+            # analyze_row_sharded, which would otherwise ask again)
+            agreed = _agree([0 if mine else 1, eng.Npad if mine else 0, 1])
+            if not agreed[0]:
                 shard, algo = "rows", "digits"
     if shard == "rows":
         _, Dg = extract_group_names(problem)
@@ -1216,7 +1240,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
                                    calc_second_order=calc_second_order, num_resamples=num_resamples,
                                    conf_level=conf_level, keep_resamples=keep_resamples, seed=seed,
                                    resample=resample, r=r, algo=algo, distributed=distributed,
-                                   kernel_events=kernel_events)
+                                   kernel_events=kernel_events, agreed=agreed)
     if shard != "resamples":
         raise ValueError(f"unknown shard mode {shard!r}")
     return analyze_outputs(problem, [Y], calc_second_order=calc_second_order, num_resamples=num_resamples,

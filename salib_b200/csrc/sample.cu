@@ -99,9 +99,14 @@ __global__ void __launch_bounds__(256, MINB)
 saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict__ shift,
                     uint64_t first_index, uint64_t n, int D, int Dg,
                     const int32_t *__restrict__ gcol, int step, int second_order, const ColScale cs,
-                    double *__restrict__ out, int rows_per_warp) {
+                    double *__restrict__ out, int rows_per_warp, int cb_split) {
+  // cb_split > 1 (few rows of a wide design): the 64-column blocks of a row run are dealt to cb_split
+  // neighbouring warps instead of being walked by one -- a chunk of 1024 rows at D = 1024 is 16 K warps
+  // instead of 1 K, and the warps of a block write neighbouring 512-byte pieces of the same rows
   const int lane = threadIdx.x & 31;
-  const uint64_t gw = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t gwc = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t gw = gwc / (uint64_t)cb_split;
+  const int cb_part = (int)(gwc - gw * (uint64_t)cb_split);
   const uint64_t r0 = gw * (uint64_t)rows_per_warp;
   if (r0 >= n) return;
   const uint64_t r1 = (r0 + rows_per_warp < n) ? r0 + rows_per_warp : n;
@@ -120,7 +125,8 @@ saltelli_reg_kernel(const uint32_t *__restrict__ sv, const uint32_t *__restrict_
     jp_lane = lane - sub * halfD;
   }
 
-  for (int cb = 0; cb < ncb; ++cb) {
+  const int cb_per = ncb / cb_split;  // the launcher picks a divisor of ncb
+  for (int cb = cb_part * cb_per; cb < (cb_part + 1) * cb_per; ++cb) {
     const int j0 = 2 * (cb * 32 + jp_lane);
     const int j1 = j0 + 1;
     const int g0 = GROUPED ? gcol[j0] : j0;
@@ -595,7 +601,16 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     uint64_t rpw = n / ((uint64_t)sms * 8 * 8);
     if (rpw < 1) rpw = 1;
     if (rpw > 16) rpw = 16;
-    const uint64_t warps = ceil_div_u64(n, rpw);
+    // few rows of a wide design: deal the 64-column blocks of a row over neighbouring warps (the smallest divisor
+    // of ncb that brings the grid to ~64 warps per SM, else all of them)
+    const int ncb = D >= 64 ? D / 64 : 1;
+    int cb_split = 1;
+    for (int d = 1; d <= ncb; ++d) {
+      if (ncb % d) continue;
+      cb_split = d;
+      if (ceil_div_u64(n, rpw) * (uint64_t)d >= (uint64_t)sms * 64) break;
+    }
+    const uint64_t warps = ceil_div_u64(n, rpw) * (uint64_t)cb_split;
     const uint64_t blocks = ceil_div_u64(warps, 8);
     SA_REQUIRE(blocks < (1ull << 31), SA_ERR_UNSUPPORTED, "sa_saltelli_sample_f64: grid too large");
     // D < 64: more of the time goes into the per-row Sobol' update, two resident blocks per SM (<= 128
@@ -607,7 +622,7 @@ extern "C" int sa_saltelli_sample_f64(void *stream, const uint32_t *d_sv, const 
     };
     auto kern = D < 64 ? pick(std::integral_constant<int, 2>{}) : pick(std::integral_constant<int, 1>{});
     kern<<<(unsigned)blocks, 256, 0, st>>>(d_sv, d_shift, first_index, n, D, Dg, d_group_of_col, step,
-                                          second_order, cs, d_out, (int)rpw);
+                                          second_order, cs, d_out, (int)rpw, cb_split);
   } else {
     const size_t row_bytes = 2 * (size_t)D * sizeof(double);
     SA_REQUIRE(row_bytes <= 200 * 1024, SA_ERR_UNSUPPORTED,

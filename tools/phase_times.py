@@ -1,0 +1,119 @@
+"""Where a headline analyze call goes, WITHOUT a profiler attached: CUDA events around the call and around every GEMM
+batch (the library's own `kernel_events` hook) give prologue (call start -> first GEMM), GEMM phase (first GEMM start
+-> last GEMM end, i.e. GEMMs + what sits between them) and tail (last GEMM end -> results on the host), next to the
+host wall clock.  One process, or any torchrun world size (row shards; max over ranks).
+
+    python tools/phase_times.py [--first-batch 0,512,1024] [--reps 5]
+    torchrun --nproc-per-node 2 tools/phase_times.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--dim", type=int, default=64)
+ap.add_argument("--log2n", type=int, default=20)
+ap.add_argument("--resamples", type=int, default=10000)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_BATCH values to compare")
+ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
+a = ap.parse_args()
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+from salib_b200 import _runtime as rt  # noqa: E402
+from salib_b200.analyze import sobol  # noqa: E402
+from salib_b200.sample import sobol as sample_sobol  # noqa: E402
+from salib_b200.test_functions import Sobol_G  # noqa: E402
+
+D, N, R = a.dim, 1 << a.log2n, a.resamples
+step = 2 * D + 2
+problem = {"num_vars": D, "names": [f"x{i + 1}" for i in range(D)], "bounds": [[0.0, 1.0]] * D}
+avec = np.resize(np.array([0, 1, 4.5, 9, 99, 99, 99, 99], dtype=np.float64), D)
+plan, first = sample_sobol._plan(problem, N, True, False, N, None)
+lo, hi = rt.shard_range(N, rank, world)
+Y = rt.empty((step * (hi - lo),), torch.float64)
+Sobol_G.evaluate_sample(plan, first + lo, hi - lo, a=avec, out=Y, check=False)
+Yfull = None
+if a.drop_in:
+    Yfull = rt.empty((step * N,), torch.float64)
+    Sobol_G.evaluate_sample(plan, first, N, a=avec, out=Yfull, check=False)
+
+
+def once(events=None):
+    if a.drop_in:
+        return sobol.analyze_device(problem, Yfull, num_resamples=R, seed=100, resample="philox",
+                                    kernel_events=events)
+    return sobol.analyze_row_sharded(problem, [(lo, Y)], N, num_resamples=R, seed=100, resample="philox",
+                                     kernel_events=events)
+
+
+_host_marks = []
+_orig_digit_sums = sobol.SobolAnalyzer.digit_sums
+
+
+def _marked_digit_sums(self, *args, **kw):
+    _host_marks.append(time.perf_counter())      # when the HOST reaches each GEMM launch
+    return _orig_digit_sums(self, *args, **kw)
+
+
+sobol.SobolAnalyzer.digit_sums = _marked_digit_sums
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+for fb in [int(x) for x in a.first_batch.split(",")]:
+    sobol.DIGITS_FIRST_BATCH = fb
+    for _ in range(3):
+        S = once()
+    rows = []
+    for _ in range(a.reps):
+        barrier()
+        ev = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del _host_marks[:]
+        t0 = time.perf_counter()
+        e0.record()
+        S = once(ev)
+        t_ret = time.perf_counter()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        gemm = sum(x[1].elapsed_time(x[2]) for x in ev)
+        rows.append([wall, e0.elapsed_time(e1), e0.elapsed_time(ev[0][1]), ev[0][1].elapsed_time(ev[-1][2]),
+                     ev[-1][2].elapsed_time(e1), gemm, len(ev), (_host_marks[0] - t0) * 1e3,
+                     (_host_marks[-1] - t0) * 1e3, (t_ret - t0) * 1e3])
+    t = torch.tensor(rows, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        med = t.median(dim=0).values.tolist()
+        print(json.dumps({"world": world, "first_batch": fb, "drop_in": a.drop_in, "reps": a.reps,
+                          "median_ms": {"wall": med[0], "device": med[1], "prologue": med[2], "gemm_phase": med[3],
+                                        "tail": med[4], "gemm_calls_sum": med[5], "batches": int(med[6]),
+                                        "host_reaches_first_gemm": med[7], "host_reaches_last_gemm": med[8],
+                                        "host_returns": med[9]},
+                          "S1_0": float(S["S1"][0]), "ST_conf_0": float(S["ST_conf"][0])}), flush=True)
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
