@@ -575,18 +575,46 @@ def allgather_moments(local, world):
     return [(row[0], row[1:]) for row in everyone.cpu().numpy() if row[0] > 0]
 
 
-def _agree(values_max):
-    """One small all-reduce (MAX) + host read: quantities every rank must agree on before it issues collectives
-    (engine family, batch sizes).  Returns the agreed python ints; identity without a process group."""
-    rank, world = rt.world()
-    if world == 1:
-        return [int(v) for v in values_max]
-    import torch.distributed as dist
+class _Agreement:
+    """One small all-reduce (MAX) of quantities every rank must agree on before it issues collectives (engine family,
+    batch sizes), started now and read later: the collective and its read-back run on the side stream, so device
+    work queued on the main stream in between (the upload of Y, the moments) neither waits for it nor is waited for.
+    ``result()`` -> the agreed python ints; identity without a process group."""
 
-    t = torch.tensor([int(v) for v in values_max], dtype=torch.int64,
-                     device=rt.device() if torch.cuda.is_available() else "cpu")   # "cpu": the gloo tests
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return [int(v) for v in t.cpu().numpy()]
+    def __init__(self, values_max, world=None):
+        self.values = [int(v) for v in values_max]
+        self.t = self.event = None
+        if world is None:
+            world = rt.world()[1]
+        if world == 1:
+            return
+        import torch.distributed as dist
+
+        if not torch.cuda.is_available():    # the gloo tests
+            self.t = torch.tensor(self.values, dtype=torch.int64)
+            dist.all_reduce(self.t, op=dist.ReduceOp.MAX)
+            return
+        side = _side_stream()
+        with torch.cuda.stream(side):
+            t = torch.tensor(self.values, dtype=torch.int64, device=rt.device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self.t = torch.empty(t.shape, dtype=torch.int64, pin_memory=True)
+            self.t.copy_(t, non_blocking=True)
+            t.record_stream(side)
+            self.event = torch.cuda.Event()
+            self.event.record(side)
+
+    def result(self):
+        if self.t is None:
+            return self.values
+        if self.event is not None:
+            self.event.synchronize()
+        return [int(v) for v in self.t.numpy()]
+
+
+def _agree(values_max):
+    """Start and read an ``_Agreement`` at once."""
+    return _Agreement(values_max).result()
 
 
 DIGITS_BATCH_MIN_MACS = 3.5e12        # ~2 ms of GEMM: amortises the launches of a batch
@@ -712,7 +740,12 @@ class _DigitsRows:
         chunk_max = max(-(-(c1 - c0 + 1) // world) for c0, c1 in self.batches)
         est_loc = [rt.empty((-(-R // world) + len(self.batches) + 2 * chunk_max, nest), torch.float64)
                    for _ in range(nout)]
-        point = rt.zeros((nout, nest), torch.float64)
+        # multi-GPU: the record every rank contributes to the ONE collective behind the last batch -- per output
+        # (n_local, mean[nest], M2[nest]) of its share of the estimates, the point estimate (zero on every rank but
+        # the one whose share holds the row of ones) and the guard count
+        stride = 3 * nest + 2
+        rec = rt.zeros((nout, stride), torch.float64)
+        point = rec[:, 1 + 2 * nest:1 + 3 * nest]
         pos, ids = 0, []
         pending = None
 
@@ -776,32 +809,34 @@ class _DigitsRows:
         finish(pending)
         self.main.wait_stream(self.side)     # never leave the side stream unjoined
 
-        confs = []
-        for o in range(nout):
-            if R == 0:
-                confs.append(torch.full((nest,), float("nan"), dtype=torch.float64, device=rt.device()))
-            elif world == 1:
-                confs.append(lead.conf(est_loc[o][:R], Z))
-            else:
-                mean = rt.empty((nest,), torch.float64)
-                _lib.call("sa_col_moment_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, 0, rt.ptr(mean))
-                dist.all_reduce(mean)
-                _lib.call("sa_conf_finish_f64", rt.stream_ptr(), rt.ptr(mean), nest, 1.0 / R, 0.0, R, 0)
-                ss = rt.empty((nest,), torch.float64)
-                _lib.call("sa_col_moment_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, rt.ptr(mean),
-                          rt.ptr(ss))
-                dist.all_reduce(ss)
-                _lib.call("sa_conf_finish_f64", rt.stream_ptr(), rt.ptr(ss), nest, 1.0, float(Z), R, 1)
-                confs.append(ss)
         # heavy-tail guard: values near the design's largest |x|, over all local shards (and ranks)
         self.guard = torch.stack([torch.stack([e.inv[e.nacc] for e in engs]).sum() for engs in self.outputs])
-        if world > 1:
-            # one collective: the point estimates (zero everywhere but on the rank that owned the row of ones) and
-            # the guard counts
-            both = torch.cat([point.reshape(-1), self.guard])
-            dist.all_reduce(both)
-            point = both[:nout * nest].reshape(nout, nest)
-            self.guard = both[nout * nest:]
+        confs = []
+        if world == 1 or R == 0:
+            for o in range(nout):
+                confs.append(lead.conf(est_loc[o][:R], Z) if R else
+                             torch.full((nest,), float("nan"), dtype=torch.float64, device=rt.device()))
+            if world > 1:
+                both = torch.cat([point.reshape(-1), self.guard])
+                dist.all_reduce(both)
+                point = both[:nout * nest].reshape(nout, nest)
+                self.guard = both[nout * nest:]
+        else:
+            # CI = Z * std(ddof=1) over all R estimates without gathering them, point estimates and guard counts:
+            # one all-gather of 3 nest + 2 doubles per output and rank, combined on every rank (Chan et al.)
+            rec[:, stride - 1] = self.guard
+            for o in range(nout):
+                _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, rt.ptr(rec[o]))
+            recs = rt.empty((world, nout, stride), torch.float64)
+            dist.all_gather_into_tensor(recs.view(-1), rec.view(-1))
+            extra = rt.empty((nout, nest + 1), torch.float64)
+            for o in range(nout):
+                conf = rt.empty((nest,), torch.float64)
+                _lib.call("sa_conf_combine_f64", rt.stream_ptr(), rt.ptr(recs[0, o]), world, nout * stride, nest,
+                          nest + 1, float(Z), rt.ptr(conf), rt.ptr(extra[o]))
+                confs.append(conf)
+            point = extra[:, :nest]
+            self.guard = extra[:, nest].contiguous()
         kept = [None] * nout
         if keep:
             for o in range(nout):
@@ -867,20 +902,36 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         return engs
 
     engines = build(algo)
-    # every rank must take the same engine family and the same batches: one tiny all-reduce
+    # every rank must take the same engine family and the same batches: one tiny all-reduce, read only
+    # after the upload of Y and the moments have been queued (they are the same for every engine family)
     mine = [0 if all(e.kind == 6 for e in engines) else 1, max(e.Npad for e in engines), len(engines)]
-    if agreed is not None and not agreed[0] and not mine[0]:
-        not_digits, npad_max, nsh = agreed  # the caller (analyze_device, "auto") has asked every rank already
-    else:
-        not_digits, npad_max, nsh = _agree(mine)
-    if not_digits and any(e.kind == 6 for e in engines):
-        engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
-    digits = not not_digits
+    # ``agreed``: the question analyze_device ("auto") has already put to every rank, still in flight
+    agreement = agreed if agreed is not None else _Agreement(mine, world)
     rows_here = sum(e.N for e in engines)
     if world == 1 and rows_here != N:        # with several ranks the count is checked on the combined moments
         raise RuntimeError(f"row shards hold {rows_here} base rows, expected {N}")
-    lead = engines[0]
     Z = norm.ppf(0.5 + conf_level / 2)
+
+    # moments of the whole design: per-shard records -> all-gather -> combined on the device (no host round trip)
+    loaded = []
+    parts = rt.zeros((len(engines), 9), torch.float64)
+    for i, (eng, (_, Y)) in enumerate(zip(engines, shards)):
+        Yd = rt.to_device(Y, torch.float64, non_blocking=True).reshape(-1)
+        eng.moments(Yd)
+        loaded.append(Yd)
+        parts[i, 0].fill_(float(Yd.numel()))     # a fill kernel, not a pageable host-to-device copy
+        parts[i, 1:].copy_(eng.stats)
+
+    not_digits, npad_max, nsh = agreement.result()
+    if not_digits and agreed is not None:
+        return None                          # "auto": some rank cannot take the integer engine -> resample shards
+    if not_digits and any(e.kind == 6 for e in engines):
+        first = engines
+        engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
+        for eng, was in zip(engines, first):
+            eng.stats.copy_(was.stats)
+    digits = not not_digits
+    lead = engines[0]
 
     if r is not None:
         rs = _Resampler.from_indices(r)
@@ -899,15 +950,6 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         first = plan_batches(lead.kind, 0, R, npad_max, lead.sms, groups=lead.groups)[0]
         prefetch = _CountsPrefetch(rs, first, [(e.Npad, (e.row0, e.N)) for e in engines])
 
-    # moments of the whole design: per-shard records -> all-gather -> combined on the device (no host round trip)
-    loaded = []
-    parts = rt.zeros((len(engines), 9), torch.float64)
-    for i, (eng, (_, Y)) in enumerate(zip(engines, shards)):
-        Yd = rt.to_device(Y, torch.float64, non_blocking=True).reshape(-1)
-        eng.moments(Yd)
-        loaded.append(Yd)
-        parts[i, 0].fill_(float(Yd.numel()))     # a fill kernel, not a pageable host-to-device copy
-        parts[i, 1:].copy_(eng.stats)
     if world > 1:
         mine = rt.zeros((nsh, 9), torch.float64)
         mine[:len(engines)] = parts
@@ -1212,7 +1254,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
     the strategy switch the reference makes inside ``analyze`` (analyze/sobol.py:147,183).
     """
     rank, world = rt.world() if distributed else (0, 1)
-    agreed = None
+    agreed, algo_asked = None, algo
     if shard == "auto":
         shard = "resamples"
         if world > 1:
@@ -1224,11 +1266,13 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
             eng = SobolAnalyzer(Dg, hi - lo, calc_second_order, algo=algo, resamples=R_req,
                                 total_rows=N) if hi > lo else None
             mine = eng is not None and eng.kind == 6
-            # the one agreement of the call: engine family, largest row shard, shards per rank (handed on to
-            # analyze_row_sharded, which would otherwise ask again)
-            agreed = _agree([0 if mine else 1, eng.Npad if mine else 0, 1])
-            if not agreed[0]:
+            # the one agreement of the call: engine family, largest row shard, shards per rank.  It is read inside
+            # analyze_row_sharded, after the upload of this rank's rows and their moments have been queued.
+            agreed = _Agreement([0 if mine else 1, eng.Npad if mine else 0, 1], world)
+            if mine:
                 shard, algo = "rows", "digits"
+            else:
+                agreed.result()              # every other rank learns it from the same all-reduce
     if shard == "rows":
         _, Dg = extract_group_names(problem)
         size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
@@ -1236,11 +1280,14 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
         step = size // N
         lo, hi = rt.shard_range(N, rank, world)
         flat = Y.reshape(-1)
-        return analyze_row_sharded(problem, [(lo, flat[lo * step:hi * step])], N,
-                                   calc_second_order=calc_second_order, num_resamples=num_resamples,
-                                   conf_level=conf_level, keep_resamples=keep_resamples, seed=seed,
-                                   resample=resample, r=r, algo=algo, distributed=distributed,
-                                   kernel_events=kernel_events, agreed=agreed)
+        S = analyze_row_sharded(problem, [(lo, flat[lo * step:hi * step])], N,
+                                calc_second_order=calc_second_order, num_resamples=num_resamples,
+                                conf_level=conf_level, keep_resamples=keep_resamples, seed=seed,
+                                resample=resample, r=r, algo=algo, distributed=distributed,
+                                kernel_events=kernel_events, agreed=agreed)
+        if S is not None:
+            return S
+        shard, algo = "resamples", algo_asked    # the ranks did not agree on the integer engine
     if shard != "resamples":
         raise ValueError(f"unknown shard mode {shard!r}")
     return analyze_outputs(problem, [Y], calc_second_order=calc_second_order, num_resamples=num_resamples,

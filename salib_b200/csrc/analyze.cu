@@ -1433,6 +1433,78 @@ conf_finish_kernel(double *__restrict__ x, int ncols, double scale, double z, ui
   x[col] = finish ? z * sqrt(x[col] / (double)(R - 1)) : x[col] * scale;
 }
 
+// The CI over estimates that are spread over the ranks of a row-sharded analyze with ONE collective: every rank
+// reduces its own estimates to (n_g, mean_g[col], M2_g[col] = sum (x - mean_g)^2) -- two passes inside one kernel --,
+// the records are all-gathered, and every rank combines them (Chan, Golub & LeVeque):
+//   M2 = sum_g M2_g + sum_g n_g (mean_g - mean)^2,   conf = z * sqrt(M2 / (n - 1))      (analyze/sobol.py:159,173)
+// rec: [0] = n_g, [1 .. ncols] = mean_g, [1 + ncols .. 2 ncols] = M2_g.
+__global__ void __launch_bounds__(512)
+conf_local_kernel(const double *__restrict__ est, uint64_t R, int ncols, double *__restrict__ rec) {
+  __shared__ double sh[16][33];
+  __shared__ double mean_sh[32];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int ty = threadIdx.y;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ty == 0) rec[0] = (double)R;
+  double s = 0.0;
+  if (col < ncols)
+    for (uint64_t c = ty; c < R; c += 16) s += est[c * (uint64_t)ncols + col];
+  sh[ty][threadIdx.x] = s;
+  __syncthreads();
+  if (ty == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 16; ++q) t += sh[q][threadIdx.x];
+    mean_sh[threadIdx.x] = R ? t / (double)R : 0.0;
+  }
+  __syncthreads();
+  const double m = mean_sh[threadIdx.x];
+  s = 0.0;
+  if (col < ncols)
+    for (uint64_t c = ty; c < R; c += 16) {
+      const double d = est[c * (uint64_t)ncols + col] - m;
+      s = fma(d, d, s);
+    }
+  __syncthreads();
+  sh[ty][threadIdx.x] = s;
+  __syncthreads();
+  if (ty == 0 && col < ncols) {
+    double t = 0.0;
+    for (int q = 0; q < 16; ++q) t += sh[q][threadIdx.x];
+    rec[1 + col] = m;
+    rec[1 + ncols + col] = t;
+  }
+}
+
+// recs: k records `pitch` doubles apart, each [n_g, mean_g[ncols], M2_g[ncols], extra[nextra]];
+// conf[col] as above, extra_sum[e] = sum_g extra_g[e] (the point estimates -- zero on every rank but one -- and
+// the guard counts ride in the same all-gather).
+__global__ void __launch_bounds__(256)
+conf_combine_kernel(const double *__restrict__ recs, int k, size_t pitch, int ncols, int nextra, double z,
+                    double *__restrict__ conf, double *__restrict__ extra_sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncols) {
+    double n = 0.0, sum = 0.0;
+    for (int g = 0; g < k; ++g) {
+      const double c = recs[g * pitch];
+      n += c;
+      sum += c * recs[g * pitch + 1 + i];
+    }
+    const double mean = sum / n;
+    double m2 = 0.0;
+    for (int g = 0; g < k; ++g) {
+      const double c = recs[g * pitch];
+      if (!(c > 0.0)) continue;
+      const double d = recs[g * pitch + 1 + i] - mean;
+      m2 += recs[g * pitch + 1 + ncols + i] + c * d * d;
+    }
+    conf[i] = z * sqrt(m2 / (n - 1.0));
+  } else if (i < ncols + nextra) {
+    const int e = i - ncols;
+    double t = 0.0;
+    for (int g = 0; g < k; ++g) t += recs[g * pitch + 1 + 2 * (size_t)ncols + e];
+    extra_sum[e] = t;
+  }
+}
+
 // Statistics of the union of k row shards from per-shard (n_values, stats8) records (Chan, Golub & LeVeque), on
 // the device so that a row-sharded analyze needs no host round trip between the moments and the features:
 // out[0..7] = mean, population std, min, max, min/max over the A and B columns, 0, 0; out[8] = total n_values.
@@ -1825,6 +1897,27 @@ extern "C" int sa_conf_finish_f64(void *stream, double *d_x, int ncols, double s
                                   int finish) {
   SA_REQUIRE(d_x && ncols >= 1, SA_ERR_ARG, "sa_conf_finish_f64: bad arguments");
   conf_finish_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, ncols, scale, z, R, finish);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_conf_local_f64(void *stream, const double *d_est, uint64_t R, int ncols, double *d_rec) {
+  SA_REQUIRE(d_rec && ncols >= 1 && (d_est || R == 0), SA_ERR_ARG, "sa_conf_local_f64: bad arguments");
+  dim3 block(32, 16);
+  conf_local_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, d_rec);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_conf_combine_f64(void *stream, const double *d_recs, int k, uint64_t pitch, int ncols, int nextra,
+                                   double z, double *d_conf, double *d_extra_sum) {
+  SA_REQUIRE(d_recs && d_conf && k >= 1 && ncols >= 1 && nextra >= 0 && pitch >= (uint64_t)(1 + 2 * ncols + nextra) &&
+                 (d_extra_sum || nextra == 0),
+             SA_ERR_ARG, "sa_conf_combine_f64: bad arguments");
+  conf_combine_kernel<<<(unsigned)((ncols + nextra + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_recs, k, (size_t)pitch, ncols, nextra, z, d_conf, d_extra_sum);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

@@ -240,6 +240,34 @@ def test_device_combined_moments_match_the_host_formula():
     assert got[8] == 1549.0
 
 
+def test_one_collective_ci_matches_numpy_std():
+    """sa_conf_local_f64 + sa_conf_combine_f64 (the row-sharded CI with one all-gather) against np.std(ddof=1) of the
+    whole estimate matrix, for uneven shares including an empty one; the trailing doubles are summed."""
+    import torch
+    from scipy.stats import norm
+    from salib_b200 import _lib, _runtime as rt
+
+    rng = np.random.default_rng(11)
+    ncols, nextra = 77, 5
+    est = rng.normal(size=(1000, ncols)) * rng.uniform(1e-6, 10.0, size=ncols) + rng.normal(size=ncols) * 100.0
+    shares = [(0, 400), (400, 400), (400, 993), (993, 1000)]
+    pitch = 1 + 2 * ncols + nextra + 3          # a pitch wider than the record
+    recs = torch.zeros((len(shares), pitch), dtype=torch.float64, device="cuda")
+    extras = rng.normal(size=(len(shares), nextra))
+    for g, (lo, hi) in enumerate(shares):
+        e = torch.from_numpy(np.ascontiguousarray(est[lo:hi])).cuda()
+        _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(e), hi - lo, ncols, rt.ptr(recs[g]))
+        recs[g, 1 + 2 * ncols:1 + 2 * ncols + nextra] = torch.from_numpy(extras[g]).cuda()
+    Z = norm.ppf(0.975)
+    conf = torch.empty(ncols, dtype=torch.float64, device="cuda")
+    extra = torch.empty(nextra, dtype=torch.float64, device="cuda")
+    _lib.call("sa_conf_combine_f64", rt.stream_ptr(), rt.ptr(recs), len(shares), pitch, ncols, nextra, float(Z),
+              rt.ptr(conf), rt.ptr(extra))
+    np.testing.assert_allclose(conf.cpu().numpy(), Z * est.std(axis=0, ddof=1), rtol=1e-13)
+    np.testing.assert_allclose(extra.cpu().numpy(), extras.sum(axis=0), rtol=1e-14, atol=1e-15)
+    assert recs[2, 0].item() == 593.0 and recs[1, 0].item() == 0.0
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r})

@@ -27,6 +27,7 @@ ap.add_argument("--resamples", type=int, default=10000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_BATCH values to compare")
 ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
+ap.add_argument("--host-y", action="store_true", help="the e2e leg: Y in pinned host memory, through the drop-in")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -51,13 +52,18 @@ lo, hi = rt.shard_range(N, rank, world)
 Y = rt.empty((step * (hi - lo),), torch.float64)
 Sobol_G.evaluate_sample(plan, first + lo, hi - lo, a=avec, out=Y, check=False)
 Yfull = None
-if a.drop_in:
+if a.drop_in or a.host_y:
     Yfull = rt.empty((step * N,), torch.float64)
     Sobol_G.evaluate_sample(plan, first, N, a=avec, out=Yfull, check=False)
+if a.host_y:
+    Yh = torch.empty(Yfull.shape, dtype=torch.float64, pin_memory=True)
+    Yh.copy_(Yfull)
+    torch.cuda.synchronize()
+    Yfull = Yh.numpy()
 
 
 def once(events=None):
-    if a.drop_in:
+    if a.drop_in or a.host_y:
         return sobol.analyze_device(problem, Yfull, num_resamples=R, seed=100, resample="philox",
                                     kernel_events=events)
     return sobol.analyze_row_sharded(problem, [(lo, Y)], N, num_resamples=R, seed=100, resample="philox",
@@ -108,7 +114,7 @@ for fb in [int(x) for x in a.first_batch.split(",")]:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         med = t.median(dim=0).values.tolist()
-        print(json.dumps({"world": world, "first_batch": fb, "drop_in": a.drop_in, "reps": a.reps,
+        print(json.dumps({"world": world, "first_batch": fb, "drop_in": a.drop_in, "host_y": a.host_y, "reps": a.reps,
                           "median_ms": {"wall": med[0], "device": med[1], "prologue": med[2], "gemm_phase": med[3],
                                         "tail": med[4], "gemm_calls_sum": med[5], "batches": int(med[6]),
                                         "host_reaches_first_gemm": med[7], "host_reaches_last_gemm": med[8],
