@@ -218,11 +218,13 @@ int sa_sobol_conf_f64(void *stream, const double *d_est, uint64_t R, int ncols, 
 int sa_col_moment_f64(void *stream, const double *d_est, uint64_t R, int ncols, const double *d_mean, double *d_out);
 int sa_conf_finish_f64(void *stream, double *d_x, int ncols, double scale, double z, uint64_t R, int finish);
 /* The same CI with ONE collective: sa_conf_local_f64 reduces the local estimates d_est [R_local, ncols] to the record
- * d_rec = (R_local, mean[ncols], sum of squared deviations from that mean [ncols]); the records of all ranks are
+ * d_rec = (R_local, mean[ncols], sum of squared deviations from that mean [ncols]) -- or, with slices > 1, to one
+ * such record per contiguous row slice (d_rec[slices][1 + 2 ncols]; fills the GPU for a long estimate matrix on one
+ * rank, the slices are then combined like ranks); the records of all ranks are
  * all-gathered (k records `pitch` doubles apart, each followed by `nextra` doubles that are simply summed over the
  * records: the point estimates and guard counts of the row-sharded analyze ride along) and sa_conf_combine_f64
  * combines them (Chan/Golub/LeVeque) into d_conf[col] = z * std(all estimates, ddof=1) and d_extra_sum[nextra].   */
-int sa_conf_local_f64(void *stream, const double *d_est, uint64_t R, int ncols, double *d_rec);
+int sa_conf_local_f64(void *stream, const double *d_est, uint64_t R, int ncols, int slices, double *d_rec);
 int sa_conf_combine_f64(void *stream, const double *d_recs, int k, uint64_t pitch, int ncols, int nextra, double z,
                         double *d_conf, double *d_extra_sum);
 /* Mean / population std / min / max of the union of k row shards from per-shard records

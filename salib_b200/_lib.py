@@ -54,7 +54,7 @@ SIGNATURES = {
     "sa_sobol_conf_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp]),
     "sa_col_moment_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp]),
     "sa_conf_finish_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _u64, _i32]),
-    "sa_conf_local_f64": (C.c_int, [_vp, _vp, _u64, _i32, _vp]),
+    "sa_conf_local_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp]),
     "sa_conf_combine_f64": (C.c_int, [_vp, _vp, _i32, _u64, _i32, _i32, _dbl, _vp, _vp]),
     "sa_combine_moments_f64": (C.c_int, [_vp, _vp, _i32, _vp]),
     "sa_chunked_feature_doubles": (C.c_int, [_i32]),

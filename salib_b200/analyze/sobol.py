@@ -457,9 +457,19 @@ class SobolAnalyzer:
         return bootstrap_shared([self], resampler, lo, hi)[0]
 
     def conf(self, est, z):
+        """z * std(est, axis=0, ddof=1) -> [nest].  A long estimate matrix is reduced in row slices that fill the
+        GPU (one column block per CTA reads est twice from 67 CTAs at the headline: 0.3 ms) and the slices' moments
+        are combined (Chan et al.), the same two calls the row-sharded route uses across ranks."""
+        R = int(est.shape[0])
         out = rt.empty((self.nest,), torch.float64)
-        _lib.call("sa_sobol_conf_f64", rt.stream_ptr(), rt.ptr(est), int(est.shape[0]), self.nest, float(z),
-                  rt.ptr(out))
+        slices = min(16, R // 512)
+        if slices >= 2:
+            recs = rt.empty((slices, 1 + 2 * self.nest), torch.float64)
+            _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(est), R, self.nest, slices, rt.ptr(recs))
+            _lib.call("sa_conf_combine_f64", rt.stream_ptr(), rt.ptr(recs), slices, 1 + 2 * self.nest, self.nest, 0,
+                      float(z), rt.ptr(out), 0)
+        else:
+            _lib.call("sa_sobol_conf_f64", rt.stream_ptr(), rt.ptr(est), R, self.nest, float(z), rt.ptr(out))
         return out
 
 
@@ -652,6 +662,13 @@ def digits_batches(R, npad_max, ncols=15043, first=None):
 
 
 DIGITS_FIRST_BATCH = int(os.environ.get("SALIB_B200_FIRST_BATCH", "0"))
+PREDRAW_MAX_BYTES = int(float(os.environ.get("SALIB_B200_PREDRAW_GB", "24")) * (1 << 30))
+
+
+def _free_bytes():
+    """Device memory this process can still get: free + cached by the allocator."""
+    free, _ = torch.cuda.mem_get_info()
+    return free + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
 
 _SIDE_STREAMS = {}
 
@@ -689,9 +706,12 @@ class _DigitsRows:
     deviations) replace the all-gather of the estimates.  No host synchronisation before the final read-back.
     """
 
-    def __init__(self, outputs, N, R, rs, npad_max, rank, world):
+    def __init__(self, outputs, N, R, rs, npad_max, rank, world, upload=False):
         """outputs[o] = the engines (kind 6, ``row0`` set) of model output o, one per local row shard; all outputs
-        share the row shards (and therefore the multiplicities)."""
+        share the row shards (and therefore the multiplicities).  ``upload``: Y is coming from host memory -- the
+        GPU idles behind PCIe for about as long as all multiplicities take to draw, so (Philox, memory permitting)
+        every batch gets its own buffer and is drawn by the stand-alone kernel on the side stream right now, and
+        the GEMMs host nothing (a hosted draw costs a power-capped GEMM ~4 % of its clock)."""
         self.outputs, self.N, self.R, self.rs = outputs, int(N), int(R), rs
         self.rank, self.world = rank, world
         self.shards = outputs[0]
@@ -699,14 +719,23 @@ class _DigitsRows:
         self.batches = digits_batches(self.R, npad_max, self.lead.nacc * self.lead.ndigits)
         self.nbuf = 2 if len(self.batches) > 1 else 1
         rows_buf = max(c1 - c0 for c0, c1 in self.batches) + 1
+        philox = rs is not None and rs.mode == "philox"
+        all_bytes = len(self.batches) * rows_buf * sum(e.Npad for e in self.shards)
+        self.predrawn = bool(upload and philox and len(self.batches) > 2 and all_bytes <= PREDRAW_MAX_BYTES
+                             and all_bytes + (8 << 30) <= _free_bytes())
+        if self.predrawn:
+            self.nbuf = len(self.batches)
         self.wsets = [[rt.empty((rows_buf * e.Npad,), torch.uint8) for e in self.shards] for _ in range(self.nbuf)]
         self.main = torch.cuda.current_stream()
         self.side = _side_stream()
         self.side.wait_stream(self.main)     # cached blocks may still be read by earlier work on the main stream
         self.drawn, self.gemm_done = {}, {}
         # Philox draws of batches 1.. are hosted by the previous batch's GEMM (main stream, no events)
-        self.hosted = rs is not None and rs.mode == "philox" and not os.environ.get("SALIB_B200_SIDE_DRAW")
+        self.hosted = philox and not self.predrawn and not os.environ.get("SALIB_B200_SIDE_DRAW")
         self.draw(0, slim=False)             # the first batch is drawn while Y is uploaded / split into digits
+        if self.predrawn:
+            for b in range(1, len(self.batches)):
+                self.draw(b, slim=False)
 
     def draw(self, b, slim, after=None):
         c0, c1 = self.batches[b]
@@ -725,6 +754,11 @@ class _DigitsRows:
             ev = torch.cuda.Event()
             ev.record(self.side)
             self.drawn[b] = ev
+
+    @property
+    def draws(self):
+        """How the batches after the first got their multiplicities (reported as ``ResultDict.draws``)."""
+        return "predrawn" if self.predrawn else "hosted" if self.hosted else "side-stream"
 
     def abandon(self):
         """Join the side stream before the buffers go back to the allocator (the engine fell back to FP64)."""
@@ -768,7 +802,7 @@ class _DigitsRows:
             nxt = b + 1 < len(self.batches)
             if b in self.drawn:
                 self.main.wait_event(self.drawn[b])
-            if nxt and not self.hosted:
+            if nxt and not self.hosted and not self.predrawn:
                 pre = torch.cuda.Event()
                 pre.record(self.main)        # fires when this batch's GEMM is next on the main stream
                 self.draw(b + 1, slim=True, after=pre)
@@ -826,7 +860,7 @@ class _DigitsRows:
             # one all-gather of 3 nest + 2 doubles per output and rank, combined on every rank (Chan et al.)
             rec[:, stride - 1] = self.guard
             for o in range(nout):
-                _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, rt.ptr(rec[o]))
+                _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(est_loc[o]), int(pos), nest, 1, rt.ptr(rec[o]))
             recs = rt.empty((world, nout, stride), torch.float64)
             dist.all_gather_into_tensor(recs.view(-1), rec.view(-1))
             extra = rt.empty((nout, nest + 1), torch.float64)
@@ -944,7 +978,8 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
 
     pipe = prefetch = None
     if digits:
-        pipe = _DigitsRows([engines], N, R, rs, npad_max, rank, world)      # starts drawing batch 0 right away
+        pipe = _DigitsRows([engines], N, R, rs, npad_max, rank, world,      # starts drawing right away
+                           upload=not isinstance(shards[0][1], torch.Tensor))
     elif R > 0 and rs.mode == "philox":
         # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of the shards
         first = plan_batches(lead.kind, 0, R, npad_max, lead.sms, groups=lead.groups)[0]
@@ -1013,6 +1048,7 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     S.engine = ENGINE_NAMES[lead.kind]
     S.resample_mode = rs.mode if rs is not None else None
     S.digits_guard = guard
+    S.draws = pipe.draws if digits else None
     return S
 
 
@@ -1160,7 +1196,8 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
     # one GPU + integer engine: the pipelined row route with a single shard that holds every row
     pipe = None
     if world == 1 and all(e.kind == 6 for e in engines):
-        pipe = _DigitsRows([[e] for e in engines], N, R, rs, engines[0].Npad, 0, 1)
+        pipe = _DigitsRows([[e] for e in engines], N, R, rs, engines[0].Npad, 0, 1,
+                           upload=not isinstance(Ys[0], torch.Tensor))
     lo, hi = rt.shard_range(R, rank, world)
     # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of Y
     prefetch = None
@@ -1235,6 +1272,7 @@ def analyze_outputs(problem, Ys, calc_second_order=True, num_resamples=100, conf
         S.engine = ENGINE_NAMES[eng.kind]
         S.resample_mode = rs.mode if rs is not None else None
         S.digits_guard = guard
+        S.draws = pipe.draws if pipe is not None else None
         out.append(S)
     return out
 

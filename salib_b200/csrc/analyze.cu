@@ -1439,9 +1439,15 @@ conf_finish_kernel(double *__restrict__ x, int ncols, double scale, double z, ui
 //   M2 = sum_g M2_g + sum_g n_g (mean_g - mean)^2,   conf = z * sqrt(M2 / (n - 1))      (analyze/sobol.py:159,173)
 // rec: [0] = n_g, [1 .. ncols] = mean_g, [1 + ncols .. 2 ncols] = M2_g.
 __global__ void __launch_bounds__(512)
-conf_local_kernel(const double *__restrict__ est, uint64_t R, int ncols, double *__restrict__ rec) {
+conf_local_kernel(const double *__restrict__ est, uint64_t R_all, int ncols, double *__restrict__ rec_all) {
   __shared__ double sh[16][33];
   __shared__ double mean_sh[32];
+  // blockIdx.y = one of gridDim.y contiguous row slices, each with its own record (they are combined like ranks)
+  const uint64_t per = (R_all + gridDim.y - 1) / gridDim.y;
+  const uint64_t r_lo = min(R_all, per * blockIdx.y), r_hi = min(R_all, r_lo + per);
+  const uint64_t R = r_hi - r_lo;
+  est += r_lo * (uint64_t)ncols;
+  double *rec = rec_all + (size_t)blockIdx.y * (1 + 2 * (size_t)ncols);
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int ty = threadIdx.y;
   if (blockIdx.x == 0 && threadIdx.x == 0 && ty == 0) rec[0] = (double)R;
@@ -1902,10 +1908,11 @@ extern "C" int sa_conf_finish_f64(void *stream, double *d_x, int ncols, double s
   return SA_OK;
 }
 
-extern "C" int sa_conf_local_f64(void *stream, const double *d_est, uint64_t R, int ncols, double *d_rec) {
-  SA_REQUIRE(d_rec && ncols >= 1 && (d_est || R == 0), SA_ERR_ARG, "sa_conf_local_f64: bad arguments");
-  dim3 block(32, 16);
-  conf_local_kernel<<<(unsigned)((ncols + 31) / 32), block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, d_rec);
+extern "C" int sa_conf_local_f64(void *stream, const double *d_est, uint64_t R, int ncols, int slices, double *d_rec) {
+  SA_REQUIRE(d_rec && ncols >= 1 && slices >= 1 && slices <= 65535 && (d_est || R == 0), SA_ERR_ARG,
+             "sa_conf_local_f64: bad arguments");
+  dim3 block(32, 16), grid((unsigned)((ncols + 31) / 32), (unsigned)slices);
+  conf_local_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_est, R, ncols, d_rec);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;

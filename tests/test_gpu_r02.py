@@ -205,6 +205,13 @@ def test_pipelined_batches_equal_one_batch(monkeypatch):
     many = sobol.analyze_device(p, Y, algo="digits", **kw)
     for k in one:
         assert np.array_equal(np.asarray(one[k]), np.asarray(many[k]), equal_nan=True), k
+    # a host Y: every batch is drawn by the stand-alone kernel behind the upload; a device Y: batches 1.. are drawn
+    # by spare warps of the previous batch's GEMM.  Same multiplicities, same results.
+    import torch
+    dev = sobol.analyze_device(p, torch.from_numpy(Y).cuda(), algo="digits", **kw)
+    assert (many.draws, dev.draws) == ("predrawn", "hosted")
+    for k in one:
+        assert np.array_equal(np.asarray(one[k]), np.asarray(dev[k]), equal_nan=True), k
     # two outputs share the multiplicities of every batch
     both = sobol.analyze_outputs(p, [Y, 2.0 * Y + 1.0], algo="digits", **kw)
     for k in one:
@@ -256,7 +263,7 @@ def test_one_collective_ci_matches_numpy_std():
     extras = rng.normal(size=(len(shares), nextra))
     for g, (lo, hi) in enumerate(shares):
         e = torch.from_numpy(np.ascontiguousarray(est[lo:hi])).cuda()
-        _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(e), hi - lo, ncols, rt.ptr(recs[g]))
+        _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(e), hi - lo, ncols, 1, rt.ptr(recs[g]))
         recs[g, 1 + 2 * ncols:1 + 2 * ncols + nextra] = torch.from_numpy(extras[g]).cuda()
     Z = norm.ppf(0.975)
     conf = torch.empty(ncols, dtype=torch.float64, device="cuda")
@@ -266,6 +273,13 @@ def test_one_collective_ci_matches_numpy_std():
     np.testing.assert_allclose(conf.cpu().numpy(), Z * est.std(axis=0, ddof=1), rtol=1e-13)
     np.testing.assert_allclose(extra.cpu().numpy(), extras.sum(axis=0), rtol=1e-14, atol=1e-15)
     assert recs[2, 0].item() == 593.0 and recs[1, 0].item() == 0.0
+    # row slices of one matrix (how a single rank fills the GPU): 7 slices of 1000 rows, the last one short
+    sl = torch.zeros((7, 1 + 2 * ncols), dtype=torch.float64, device="cuda")
+    e = torch.from_numpy(est).cuda()
+    _lib.call("sa_conf_local_f64", rt.stream_ptr(), rt.ptr(e), 1000, ncols, 7, rt.ptr(sl))
+    _lib.call("sa_conf_combine_f64", rt.stream_ptr(), rt.ptr(sl), 7, 1 + 2 * ncols, ncols, 0, float(Z), rt.ptr(conf), 0)
+    np.testing.assert_allclose(conf.cpu().numpy(), Z * est.std(axis=0, ddof=1), rtol=1e-13)
+    assert sl[:, 0].sum().item() == 1000.0 and sl[6, 0].item() == 1000 - 6 * 143
 
 
 WORKER = r'''

@@ -27,6 +27,7 @@ ap.add_argument("--resamples", type=int, default=10000)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_BATCH values to compare")
 ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
+ap.add_argument("--no-gc", action="store_true", help="gc.disable() around the timed calls (as timeit does)")
 ap.add_argument("--host-y", action="store_true", help="the e2e leg: Y in pinned host memory, through the drop-in")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -70,6 +71,19 @@ def once(events=None):
                                      kernel_events=events)
 
 
+import gc  # noqa: E402
+
+_gc_log, _gc_t = [], [0.0]
+
+
+def _gc_cb(phase, info):
+    if phase == "start":
+        _gc_t[0] = time.perf_counter()
+    else:
+        _gc_log.append((info["generation"], round((time.perf_counter() - _gc_t[0]) * 1e3, 2)))
+
+
+gc.callbacks.append(_gc_cb)
 _host_marks = []
 _orig_digit_sums = sobol.SobolAnalyzer.digit_sums
 
@@ -93,6 +107,10 @@ for fb in [int(x) for x in a.first_batch.split(",")]:
     for _ in range(3):
         S = once()
     rows = []
+    del _gc_log[:]
+    if a.no_gc:
+        gc.collect()
+        gc.disable()
     for _ in range(a.reps):
         barrier()
         ev = []
@@ -109,9 +127,19 @@ for fb in [int(x) for x in a.first_batch.split(",")]:
         rows.append([wall, e0.elapsed_time(e1), e0.elapsed_time(ev[0][1]), ev[0][1].elapsed_time(ev[-1][2]),
                      ev[-1][2].elapsed_time(e1), gemm, len(ev), (_host_marks[0] - t0) * 1e3,
                      (_host_marks[-1] - t0) * 1e3, (t_ret - t0) * 1e3])
+    gc.enable()
+    if rank == 0 and os.environ.get("PHASE_VERBOSE"):
+        print("gc collections during the timed calls (generation, ms):", _gc_log)
     t = torch.tensor(rows, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0 and os.environ.get("PHASE_VERBOSE"):
+        st = torch.cuda.memory_stats()
+        print("per-rep [wall, device, prologue, gemm_phase, tail, gemm_sum, batches, host_first, host_last, host_ret]:")
+        for r_ in t.tolist():
+            print("   ", [round(x, 2) for x in r_])
+        print("allocator:", {k: st[k] for k in ("num_alloc_retries", "num_device_alloc", "num_device_free",
+                                                "reserved_bytes.all.current", "allocated_bytes.all.peak")})
     if rank == 0:
         med = t.median(dim=0).values.tolist()
         print(json.dumps({"world": world, "first_batch": fb, "drop_in": a.drop_in, "host_y": a.host_y, "reps": a.reps,
