@@ -14,6 +14,7 @@ Sample generation is timed in its own loop and reported under ``roofline.sample`
 The run exits non-zero if the result is wrong (see ``result_check``).  See DESIGN.md "Measurement".
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -230,7 +231,8 @@ def bench_config(a):
     """The workload both arms are quoted on (identical dict in the two JSON lines)."""
     return {"workload": workload_name(a), "a": "tile([0,1,4.5,9,99,99,99,99])", "scramble": False,
             "skip_values": 1 << a.log2n, "seed": 100,
-            "l2": "Y (1.09 GB) and the operands of the GEMM (26 GB) exceed the 126 MB L2; no explicit flush"}
+            "l2": "Y (1.09 GB) and the operands of the GEMM (26 GB) exceed the 126 MB L2; no explicit flush",
+            "gc": "Python's cyclic GC is disabled inside timed regions (collected before), as timeit does"}
 
 
 def profile_traffic(key):
@@ -345,13 +347,18 @@ def main():
         """W untimed calls, then K calls between CUDA events with barrier+sync on both sides; max over ranks."""
         for _ in range(warmup):
             fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
+        gc.collect()
+        gc.disable()          # as timeit does: a generation-2 collection is a ~60 ms host stall on any one rank
+        try:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        finally:
+            gc.enable()
         return max_over_ranks(e0.elapsed_time(e1) / 1e3)
 
     import warnings
@@ -653,6 +660,7 @@ def main():
     # ---- e2e: the public drop-in call with a HOST (pinned) Y, H2D + D2H inside the timed region.  Every rank
     # holds the host array, as every process of a torchrun job would; analyze() routes by itself.
     Yfull = full_y()
+    numa_cpus = rt.bind_host_to_gpu() if world > 1 else None   # staging buffer on the GPU's own NUMA node
     Yh = torch.empty(Yfull.shape, dtype=torch.float64, pin_memory=True)
     Yh.copy_(Yfull)
     torch.cuda.synchronize()
@@ -678,7 +686,8 @@ def main():
         else int(step_rows * N * 8)      # row shards: the ranks together upload Y once
     e2e = {"value": N * R * a.steps / t_e2e, "unit": "resample-rows/s", "analyze_s": t_e2e / a.steps,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((2 * nest + 8) * 8 + 4),
-           "call": "salib_b200.analyze.sobol.analyze(problem, Y_host, calc_second_order, num_resamples, seed=100)"}
+           "call": "salib_b200.analyze.sobol.analyze(problem, Y_host, calc_second_order, num_resamples, seed=100)",
+           "host_numa_bound": bool(numa_cpus)}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

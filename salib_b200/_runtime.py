@@ -10,10 +10,20 @@ import torch
 from . import _lib
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    """Raises unless a CUDA device and the native library are there.  Checked once per process: the helpers below
+    call this on every allocation, and torch.cuda.is_available() costs microseconds each time (a headline analyze
+    call made ~50 of them on its launch-bound multi-GPU prologue)."""
+    global _cuda_ok
+    if _cuda_ok:
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("salib_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     _lib.lib()
+    _cuda_ok = True
 
 
 def device():
@@ -68,6 +78,30 @@ def to_device_sharded(a, dtype, min_bytes=64 << 20):
     full = torch.empty((world_size * per,), dtype=dtype, device=device())
     dist.all_gather_into_tensor(full, part)
     return full[:n]
+
+
+def bind_host_to_gpu():
+    """Pin the calling thread to the CPUs NVML reports as local to the current GPU (its NUMA node).  A torchrun
+    worker that allocates its pinned staging buffers after this call gets host pages next to its own GPU: eight
+    ranks uploading at once otherwise share whatever socket their processes happened to start on.  Best effort:
+    returns the CPU list, or None when NVML or the affinity call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = torch.cuda.get_device_properties(torch.cuda.current_device()).uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 def empty(shape, dtype):

@@ -956,6 +956,16 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         parts[i, 0].fill_(float(Yd.numel()))     # a fill kernel, not a pageable host-to-device copy
         parts[i, 1:].copy_(eng.stats)
 
+    # (host work that needs no answer yet: the all-reduce is still in flight)
+    if r is not None:
+        rs = _Resampler.from_indices(r)
+        if rs.N != N:
+            raise ValueError(f"`r` must have {N} rows")
+        R = rs.R
+    else:
+        R = int(num_resamples)
+        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE, distributed=distributed) if R > 0 else None
+
     not_digits, npad_max, nsh = agreement.result()
     if not_digits and agreed is not None:
         return None                          # "auto": some rank cannot take the integer engine -> resample shards
@@ -966,15 +976,6 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
             eng.stats.copy_(was.stats)
     digits = not not_digits
     lead = engines[0]
-
-    if r is not None:
-        rs = _Resampler.from_indices(r)
-        if rs.N != N:
-            raise ValueError(f"`r` must have {N} rows")
-        R = rs.R
-    else:
-        R = int(num_resamples)
-        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE, distributed=distributed) if R > 0 else None
 
     pipe = prefetch = None
     if digits:

@@ -28,6 +28,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_BATCH values to compare")
 ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
 ap.add_argument("--no-gc", action="store_true", help="gc.disable() around the timed calls (as timeit does)")
+ap.add_argument("--numa", action="store_true", help="bind the process to the GPU's NUMA node before pinning Y")
 ap.add_argument("--host-y", action="store_true", help="the e2e leg: Y in pinned host memory, through the drop-in")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,6 +58,8 @@ if a.drop_in or a.host_y:
     Yfull = rt.empty((step * N,), torch.float64)
     Sobol_G.evaluate_sample(plan, first, N, a=avec, out=Yfull, check=False)
 if a.host_y:
+    if a.numa:
+        print("numa cpus", rank, (rt.bind_host_to_gpu() or [])[:4], flush=True)
     Yh = torch.empty(Yfull.shape, dtype=torch.float64, pin_memory=True)
     Yh.copy_(Yfull)
     torch.cuda.synchronize()
