@@ -525,6 +525,8 @@ def main():
         S_dig = analyze_sobol.digits_for((hi - lo) if row_mode else N)
         ops_per_row = 2 * nacc * S_dig        # int8 multiply-adds x 2 per (resample, row)
         burst, sustained = i8_peak_tops()
+        rows_here = (hi - lo) if row_mode else N
+        n_batches = len(analyze_sobol.digits_batches(R, int(L.sa_pad_rows(rows_here)), nacc * S_dig))
         achieved = ops_per_row * k_rows / (k_ms / 1e3) / 1e12 if k_ms > 0 else None
         tr, tr_src = profile_traffic(f"digits_d{D}_n{a.log2n}_r{R}_c{int(c2)}_g{world}")
         # MEASURED_PEAKS.json has no int8 entry: the int8 tensor rate is twice the bf16 rate on this part (8192
@@ -547,13 +549,17 @@ def main():
                     "traffic": tr, "traffic_source": tr_src,
                     "algorithmic_bytes": ((R + 1) + nacc * S_dig) * ((hi - lo) if row_mode else N)
                     + 4 * (R + 1) * nacc * S_dig,
+                    "operand_bytes_as_batched": ((R + 1) + n_batches * nacc * S_dig) * ((hi - lo) if row_mode else N)
+                    + 4 * (R + 1) * nacc * S_dig,
+                    "gemm_launches_per_step": n_batches,
                     "kernel": "digit_gemm_pair_persistent_kernel<2,4> (tcgen05.mma.cta_group::2.kind::i8)",
                     "kernel_ms_per_step": k_ms, "kernel_share_of_step": (k_ms / 1e3) / t_step,
                     "algorithmic_int8_ops_per_resample_row": ops_per_row, "digits": S_dig,
                     "note": "exact integer GEMM of the multiplicities with the int8 digits of the features; the work "
                             "moved from the FP64 pipe (4422 flop per resample-row, SURVEY 8(d)) to the int8 tensor "
-                            "pipe at 6.8x the raw operation count; ncu: tensor pipe 98.8 % active at the clock the "
-                            "1000 W cap allows (profiles/r02_pair_persist_v1_ncu_summary.csv)"}
+                            "pipe at 6.8x the raw operation count; ncu: tensor pipe 98 % active at the clock the "
+                            "1000 W cap allows (profiles/r02_step_ncu_full_summary.csv); achieved, kernel_ms and "
+                            "traffic are sums over the gemm_launches_per_step launches of one step"}
     else:
         roofline = fp64_roofline(k_ms, k_rows, t_step)
     roofline["sample"] = sample

@@ -1498,6 +1498,8 @@ static int feature_tile_rows(int step, int extra, size_t budget, int max_rows) {
 
 // Rows per tile of the split kernel: step * (rows + 2) doubles; 64 rows while three blocks fit an SM, then fewer.
 static int split_tile_rows(int step) {
+  if (const int r = env_int("SALIB_B200_SPLIT_ROWS", 0))  // experiments: 8, 16, 32 or 64
+    if ((r == 8 || r == 16 || r == 32 || r == 64) && (size_t)step * (r + 2) * 8 <= 200 * 1024) return r;
   for (int rows = 64; rows >= 8; rows >>= 1)
     if ((size_t)step * (rows + 2) * 8 <= 72 * 1024) return rows;
   for (int rows = 64; rows >= 8; rows >>= 1)  // long rows: one block per SM
@@ -1647,7 +1649,17 @@ extern "C" int sa_digit_features_i8(void *stream, const double *d_Y, uint64_t N,
     feature_max_kernel<<<grid, 256, smem_max, st>>>(d_Y, N, step, nfeat, tab, d_stats, rows_max, fmax, fmax + nfeat);
   }
   feature_scale_kernel<<<fb, 256, 0, st>>>(fmax, nfeat, 8 * ndigits - 2, scale, d_inv, fmax + nfeat);
-  const uint64_t tiles2 = Kp / rows, slots2 = 3 * (uint64_t)sm_count();
+  int split_per_sm = 3;  // resident blocks per SM of the split kernel (one full wave of blocks walks the tiles)
+  if (env_int("SALIB_B200_SPLIT_ROWS", 0)) {
+    int per_sm = 0;
+    auto kern = ndigits == 7 ? (const void *)digit_split_kernel<7> : (const void *)digit_split_kernel<6>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_split) == cudaSuccess && per_sm >= 1)
+      split_per_sm = per_sm;
+    else
+      cudaGetLastError();
+  }
+  const uint64_t tiles2 = Kp / rows, slots2 = (uint64_t)split_per_sm * sm_count();
   const unsigned grid2 = (unsigned)(tiles2 < slots2 ? tiles2 : slots2);
 #define SA_SPLIT(S)                                                                                               \
   case S:                                                                                                         \
