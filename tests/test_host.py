@@ -351,6 +351,11 @@ def _gloo_worker(rank, world, port, R, nest, q):
     from salib_b200.analyze.sobol import _agree
 
     ok = ok and _agree([rank, 10 - rank, 7]) == [world - 1, 10, 7]
+    # the same agreement started early and read late (what analyze_row_sharded does around the upload of Y)
+    from salib_b200.analyze.sobol import _Agreement
+
+    pending = _Agreement([3 * rank, 5, 1 - rank], world)
+    ok = ok and pending.result() == [3 * (world - 1), 5, 1] and _Agreement([4, 2], 1).result() == [4, 2]
     q.put((rank, ok))
     dist.destroy_process_group()
 
@@ -447,7 +452,15 @@ def test_digits_batches_and_reduce_scatter_bookkeeping():
     """Host logic of the pipelined row route (analyze/sobol.py: digits_batch, batch_share): batches cover [0, R) in
     whole tiles, and the rows each rank keeps after the reduce-scatter tile every batch exactly once, the row of
     ones (the point estimate) landing on exactly one rank."""
-    from salib_b200.analyze.sobol import batch_share, digits_batch
+    from salib_b200.analyze.sobol import batch_share, digits_batch, digits_batches
+
+    assert digits_batches(10000, 1 << 20) == [(0, 2048), (2048, 4096), (4096, 6144), (6144, 8192), (8192, 10000)]
+    assert digits_batches(0, 1 << 20) == [(0, 0)] and digits_batches(100, 1 << 20) == [(0, 100)]
+    short = digits_batches(10000, 1 << 20, first=512)      # a short first batch (experiment knob), the rest equal
+    assert short[0] == (0, 512) and short[-1][1] == 10000 and len(short) == 6
+    assert all(a1 == b0 for (_, a1), (b0, _) in zip(short, short[1:]))
+    assert all((c1 - c0) % 256 == 0 for c0, c1 in short[:-1])
+    assert digits_batches(10000, 1 << 20, first=4096) == digits_batches(10000, 1 << 20)   # not below the batch size
 
     assert digits_batch(10000, 1 << 20) == 2048      # headline: 5 batches, 4 draws hidden behind a GEMM
     assert digits_batch(10000, 1 << 17) == 2048      # one of 8 row shards: the same batches

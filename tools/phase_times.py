@@ -29,6 +29,7 @@ ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_B
 ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
 ap.add_argument("--no-gc", action="store_true", help="gc.disable() around the timed calls (as timeit does)")
 ap.add_argument("--numa", action="store_true", help="bind the process to the GPU's NUMA node before pinning Y")
+ap.add_argument("--sampler", action="store_true", help="run bench.py's NVML clock sampler thread beside the calls")
 ap.add_argument("--host-y", action="store_true", help="the e2e leg: Y in pinned host memory, through the drop-in")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -105,6 +106,12 @@ def barrier():
     torch.cuda.synchronize()
 
 
+_sampler = None
+if a.sampler:
+    import bench  # noqa: E402
+
+    _sampler = bench.ClockSampler(local)
+    _sampler.__enter__()
 for fb in [int(x) for x in a.first_batch.split(",")]:
     sobol.DIGITS_FIRST_BATCH = fb
     for _ in range(3):
@@ -151,6 +158,8 @@ for fb in [int(x) for x in a.first_batch.split(",")]:
                                         "host_reaches_first_gemm": med[7], "host_reaches_last_gemm": med[8],
                                         "host_returns": med[9]},
                           "S1_0": float(S["S1"][0]), "ST_conf_0": float(S["ST_conf"][0])}), flush=True)
+if _sampler is not None:
+    _sampler.__exit__()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
