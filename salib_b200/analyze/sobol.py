@@ -632,13 +632,14 @@ DIGITS_BATCH_MIN_MACS = 3.5e12        # ~2 ms of GEMM: amortises the launches of
 
 def digits_batch(R, npad_max, ncols=15043):
     """Resamples per GEMM batch of the integer engine.  About a quarter of the call, so that three of four draws
-    hide behind a GEMM, but at least DIGITS_BATCH_MIN_MACS of multiply-adds (a batch of B resamples is
+    hide behind a GEMM (rounded up to whole 256-resample tiles: R = 10^4 runs 4 batches of 2560, not 5 of 2048 --
+    every batch re-reads the digit matrix, 15.8 GB at the headline; same-box A/B 106.3-107.9 -> 105.2 ms), but at least DIGITS_BATCH_MIN_MACS of multiply-adds (a batch of B resamples is
     B * npad * ncols of them; small problems stay in one batch) and at most DIGITS_BATCH_BYTES of multiplicities
     (two buffers of that size live at once); whole 256-resample tiles, batches of equal size.  A function of R, the
     largest row shard of the job and the column count only: every rank derives the same batches."""
     npad = max(int(npad_max), 1)
     want = max(R // 4, int(DIGITS_BATCH_MIN_MACS / (npad * max(int(ncols), 1))))
-    want = min(want, DIGITS_BATCH_BYTES // npad)
+    want = min(-(-want // 256) * 256, DIGITS_BATCH_BYTES // npad)   # a quarter, rounded UP to whole tiles
     cap = max(256, want // 256 * 256)
     if R <= cap:
         return max(R, 1)

@@ -454,17 +454,17 @@ def test_digits_batches_and_reduce_scatter_bookkeeping():
     ones (the point estimate) landing on exactly one rank."""
     from salib_b200.analyze.sobol import batch_share, digits_batch, digits_batches
 
-    assert digits_batches(10000, 1 << 20) == [(0, 2048), (2048, 4096), (4096, 6144), (6144, 8192), (8192, 10000)]
+    assert digits_batches(10000, 1 << 20) == [(0, 2560), (2560, 5120), (5120, 7680), (7680, 10000)]
     assert digits_batches(0, 1 << 20) == [(0, 0)] and digits_batches(100, 1 << 20) == [(0, 100)]
     short = digits_batches(10000, 1 << 20, first=512)      # a short first batch (experiment knob), the rest equal
-    assert short[0] == (0, 512) and short[-1][1] == 10000 and len(short) == 6
+    assert short[0] == (0, 512) and short[-1][1] == 10000 and len(short) == 5
     assert all(a1 == b0 for (_, a1), (b0, _) in zip(short, short[1:]))
     assert all((c1 - c0) % 256 == 0 for c0, c1 in short[:-1])
     assert digits_batches(10000, 1 << 20, first=4096) == digits_batches(10000, 1 << 20)   # not below the batch size
 
-    assert digits_batch(10000, 1 << 20) == 2048      # headline: 5 batches, 4 draws hidden behind a GEMM
-    assert digits_batch(10000, 1 << 17) == 2048      # one of 8 row shards: the same batches
-    assert digits_batch(10000, 1 << 22) == 2048
+    assert digits_batch(10000, 1 << 20) == 2560      # headline: 4 batches, 3 draws hidden behind a GEMM
+    assert digits_batch(10000, 1 << 17) == 2560      # one of 8 row shards: the same batches
+    assert digits_batch(10000, 1 << 22) == 2048      # 8.5 GB of multiplicities per buffer at most
     assert digits_batch(100, 1 << 20) == 100
     assert digits_batch(1000, 1 << 20, 147) == 1000  # cfg2 (D = 8, first order): the GEMM is tiny, one batch
     assert digits_batch(0, 1 << 20) == 1

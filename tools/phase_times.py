@@ -29,6 +29,7 @@ ap.add_argument("--first-batch", default="0", help="comma list of DIGITS_FIRST_B
 ap.add_argument("--drop-in", action="store_true", help="go through analyze() (auto routing) instead of row shards")
 ap.add_argument("--no-gc", action="store_true", help="gc.disable() around the timed calls (as timeit does)")
 ap.add_argument("--numa", action="store_true", help="bind the process to the GPU's NUMA node before pinning Y")
+ap.add_argument("--batch", default="0", help="comma list of forced GEMM batch sizes (0 = the library's rule)")
 ap.add_argument("--sampler", action="store_true", help="run bench.py's NVML clock sampler thread beside the calls")
 ap.add_argument("--host-y", action="store_true", help="the e2e leg: Y in pinned host memory, through the drop-in")
 a = ap.parse_args()
@@ -112,8 +113,10 @@ if a.sampler:
 
     _sampler = bench.ClockSampler(local)
     _sampler.__enter__()
-for fb in [int(x) for x in a.first_batch.split(",")]:
+_rule = sobol.digits_batch
+for fb, forced in [(int(x), int(y)) for x in a.first_batch.split(",") for y in a.batch.split(",")]:
     sobol.DIGITS_FIRST_BATCH = fb
+    sobol.digits_batch = (lambda R_, npad_, ncols_=15043, _f=forced: min(_f, max(R_, 1))) if forced else _rule
     for _ in range(3):
         S = once()
     rows = []
@@ -152,7 +155,7 @@ for fb in [int(x) for x in a.first_batch.split(",")]:
                                                 "reserved_bytes.all.current", "allocated_bytes.all.peak")})
     if rank == 0:
         med = t.median(dim=0).values.tolist()
-        print(json.dumps({"world": world, "first_batch": fb, "drop_in": a.drop_in, "host_y": a.host_y, "reps": a.reps,
+        print(json.dumps({"world": world, "first_batch": fb, "batch": forced, "drop_in": a.drop_in, "host_y": a.host_y, "reps": a.reps,
                           "median_ms": {"wall": med[0], "device": med[1], "prologue": med[2], "gemm_phase": med[3],
                                         "tail": med[4], "gemm_calls_sum": med[5], "batches": int(med[6]),
                                         "host_reaches_first_gemm": med[7], "host_reaches_last_gemm": med[8],
