@@ -29,7 +29,7 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
-def main(rep, batches_per_step=5):
+def main(rep, batches_per_step=4):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -37,7 +37,7 @@ def main(rep, batches_per_step=5):
     out = os.path.join(ROOT, "profiles", "r02_step_ncu_full_summary.csv")
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none of the kernels of one headline step (command in "
-                "tools/make_traffic_json.py); D=64 N=2^20 R=10^4 second order, 5 GEMM batches, batches 0-3 host the "
+                "tools/make_traffic_json.py); D=64 N=2^20 R=10^4 second order, 4 GEMM batches of 2560 resamples, batches 0-2 host the "
                 "next batch's Philox draw; cold-cache, serialised launches\n")
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
@@ -61,8 +61,8 @@ def main(rep, batches_per_step=5):
         "bytes": int(total),
         "source": "profiles/r02_step_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the "
                   f"{batches_per_step} launches of digit_gemm_pair_persistent_kernel in one step ({per} GB; a launch "
-                  "that hosts a draw also writes the next batch's 2.1 GB of multiplicities); operands of one launch: "
-                  "W batch 2.1 + Q 15.8 + C 0.12 = 18.0 GB, i.e. 90 GB per step as batched, 26.9 GB if Q were read once",
+                  "that hosts a draw also writes the next batch's 2.7 GB of multiplicities); operands of one launch: "
+                  "W batch 2.7 + Q 15.8 + C 0.15 = 18.6 GB, i.e. 74.5 GB per step as batched, 26.9 GB if Q were read once",
         "launches_per_step": batches_per_step}
     with open(path, "w") as f:
         json.dump(t, f, indent=1)
