@@ -231,6 +231,13 @@ int sa_conf_combine_f64(void *stream, const double *d_recs, int k, uint64_t pitc
  * d_parts[k][9] = (n_values, the 8 statistics of sa_moments_f64) -> d_out[9] = the 8 statistics of the whole
  * design + n_values (replaces Y.mean(), Y.std() of analyze/sobol.py:141 when Y is partitioned over GPUs).  */
 int sa_combine_moments_f64(void *stream, const double *d_parts, int k, double *d_out);
+/* The same with the k records `pitch` >= 9 doubles apart (records that carry more than the moments).           */
+int sa_combine_moments_pitch_f64(void *stream, const double *d_parts, int k, uint64_t pitch, double *d_out);
+/* One record per rank for the single collective in front of a row-sharded analyze: d_rec[12] = the rank's k shard
+ * records d_parts[k][9] combined into (n_values, 8 statistics), then f0, f1, f2 -- what the ranks must agree on
+ * before they issue further collectives (engine family, largest shard, ...; reduced with max on the host after the
+ * all-gather).  Replaces the reference's Y.mean()/Y.std() (analyze/sobol.py:141) bookkeeping across GPUs.        */
+int sa_rank_record_f64(void *stream, const double *d_parts, int k, double f0, double f1, double f2, double *d_rec);
 
 /* ---- analyze: opt-in exact-integer tensor-core engine ("digits", csrc/digits.cu) ---------------------
  * The sums of sa_sobol_accumulate_f64 by another route: psum[c][q] = sum_i w[c][i] * F[i][q] with integer

@@ -57,6 +57,8 @@ SIGNATURES = {
     "sa_conf_local_f64": (C.c_int, [_vp, _vp, _u64, _i32, _i32, _vp]),
     "sa_conf_combine_f64": (C.c_int, [_vp, _vp, _i32, _u64, _i32, _i32, _dbl, _vp, _vp]),
     "sa_combine_moments_f64": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "sa_combine_moments_pitch_f64": (C.c_int, [_vp, _vp, _i32, _u64, _vp]),
+    "sa_rank_record_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _dbl, _vp]),
     "sa_chunked_feature_doubles": (C.c_int, [_i32]),
     "sa_finite_diff_expand_f64": (C.c_int, [_vp, _vp, _u64, _i32, _dbl, _vp, _vp, _vp]),
     "sa_dgsm_features_f64": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp]),

@@ -627,6 +627,47 @@ def _agree(values_max):
     return _Agreement(values_max).result()
 
 
+class _RankRecords:
+    """The ONE collective in front of a row-sharded analyze: every rank contributes a record of 12 doubles -- the
+    moments of its rows ``(n_values, stats8)`` (``sa_rank_record_f64`` combines several local shards) and three
+    numbers the ranks must agree on before they issue further collectives (engine family, largest shard, spare) --
+    in one all-gather.  The moments of the whole design are combined from the gathered records on the device
+    (``stats9``); the three numbers are copied to pinned memory behind the collective and reduced with max on the
+    host (``result``, the only host wait before the final read-back).  The round-2 first version asked with an
+    all-reduce and gathered the moments separately: two waits for the slowest rank instead of one."""
+
+    def __init__(self, parts, k, flags, world):
+        self.world = world
+        rec = rt.empty((12,), torch.float64)
+        _lib.call("sa_rank_record_f64", rt.stream_ptr(), rt.ptr(parts), int(k), float(flags[0]), float(flags[1]),
+                  float(flags[2]), rt.ptr(rec))
+        import torch.distributed as dist
+
+        self.all = rt.empty((world, 12), torch.float64)
+        dist.all_gather_into_tensor(self.all.view(-1), rec)
+        self.flags = torch.empty((world, 3), dtype=torch.float64, pin_memory=True)
+        self.flags.copy_(self.all[:, 9:], non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    @classmethod
+    def decline(cls, world):
+        """A rank that cannot take the integer engine (or holds no rows) still joins the collective, so that every
+        other rank learns it; returns after the answer is in."""
+        self = cls(rt.zeros((1, 9), torch.float64), 1, (1, 0, 0), world)
+        self.result()
+
+    def result(self):
+        self.event.synchronize()
+        f = self.flags.numpy()
+        return [int(f[:, j].max()) for j in range(3)]
+
+    def stats9(self):
+        out = rt.empty((9,), torch.float64)
+        _lib.call("sa_combine_moments_pitch_f64", rt.stream_ptr(), rt.ptr(self.all), self.world, 12, rt.ptr(out))
+        return out
+
+
 DIGITS_BATCH_MIN_MACS = 3.5e12        # ~2 ms of GEMM: amortises the launches of a batch
 
 
@@ -898,7 +939,7 @@ class _DigitsRows:
 
 def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resamples=100, conf_level=0.95,
                         keep_resamples=False, seed=None, resample=None, r=None, algo="auto", distributed=True,
-                        kernel_events=None, agreed=None):
+                        kernel_events=None, auto=False):
     """``analyze`` for a model output partitioned by base-row range ("when Y exceeds one GPU") --
     and the route of the integer engine in general (one GPU = one shard with every row).
 
@@ -937,17 +978,18 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         return engs
 
     engines = build(algo)
-    # every rank must take the same engine family and the same batches: one tiny all-reduce, read only
-    # after the upload of Y and the moments have been queued (they are the same for every engine family)
+    # every rank must take the same engine family and the same batches: what each rank would do on its
+    # own travels in the one all-gather of the moments (``_RankRecords``)
     mine = [0 if all(e.kind == 6 for e in engines) else 1, max(e.Npad for e in engines), len(engines)]
-    # ``agreed``: the question analyze_device ("auto") has already put to every rank, still in flight
-    agreement = agreed if agreed is not None else _Agreement(mine, world)
     rows_here = sum(e.N for e in engines)
     if world == 1 and rows_here != N:        # with several ranks the count is checked on the combined moments
         raise RuntimeError(f"row shards hold {rows_here} base rows, expected {N}")
     Z = norm.ppf(0.5 + conf_level / 2)
+    upload = not isinstance(shards[0][1], torch.Tensor)
+    ncols = engines[0].nacc * engines[0].ndigits
 
-    # moments of the whole design: per-shard records -> all-gather -> combined on the device (no host round trip)
+    # moments of the whole design: per-shard records -> (several ranks) one record per rank, all-gathered ->
+    # combined on the device
     loaded = []
     parts = rt.zeros((len(engines), 9), torch.float64)
     for i, (eng, (_, Y)) in enumerate(zip(engines, shards)):
@@ -956,20 +998,36 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
         loaded.append(Yd)
         parts[i, 0].fill_(float(Yd.numel()))     # a fill kernel, not a pageable host-to-device copy
         parts[i, 1:].copy_(eng.stats)
+    records = _RankRecords(parts, len(engines), mine, world) if world > 1 else None
 
-    # (host work that needs no answer yet: the all-reduce is still in flight)
-    if r is not None:
-        rs = _Resampler.from_indices(r)
-        if rs.N != N:
-            raise ValueError(f"`r` must have {N} rows")
-        R = rs.R
-    else:
-        R = int(num_resamples)
-        rs = _Resampler(N, R, seed, resample or RESAMPLE_MODE, distributed=distributed) if R > 0 else None
+    def resampler():
+        if r is not None:
+            rs_ = _Resampler.from_indices(r)
+            if rs_.N != N:
+                raise ValueError(f"`r` must have {N} rows")
+            return rs_, rs_.R
+        R_ = int(num_resamples)
+        return (_Resampler(N, R_, seed, resample or RESAMPLE_MODE, distributed=distributed) if R_ > 0 else None), R_
 
-    not_digits, npad_max, nsh = agreement.result()
-    if not_digits and agreed is not None:
+    # host work that needs no answer yet (the collective is in flight): the resampler -- unless it needs a
+    # collective of its own (the seedless key is rank 0's, broadcast), which must not be issued before every rank
+    # is known to take this route -- and, if this rank would take the integer engine, its pipeline, whose first
+    # multiplicity batch starts on the side stream right away
+    early = world == 1 or r is not None or bool(seed)
+    rs, R, pipe = None, None, None
+    if early:
+        rs, R = resampler()
+        if not mine[0]:
+            pipe = _DigitsRows([engines], N, R, rs, mine[1], rank, world, upload=upload)
+
+    not_digits, npad_max, _ = records.result() if records is not None else mine
+    if not_digits and pipe is not None:
+        pipe.abandon()
+        pipe = None
+    if not_digits and auto:
         return None                          # "auto": some rank cannot take the integer engine -> resample shards
+    if not early:
+        rs, R = resampler()
     if not_digits and any(e.kind == 6 for e in engines):
         first = engines
         engines = build("fp64")             # some rank (or shard) cannot run the integer engine: nobody does
@@ -978,23 +1036,22 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     digits = not not_digits
     lead = engines[0]
 
-    pipe = prefetch = None
-    if digits:
-        pipe = _DigitsRows([engines], N, R, rs, npad_max, rank, world,      # starts drawing right away
-                           upload=not isinstance(shards[0][1], torch.Tensor))
-    elif R > 0 and rs.mode == "philox":
+    prefetch = None
+    if digits and (pipe is None or pipe.batches != digits_batches(R, npad_max, ncols)):
+        if pipe is not None:
+            pipe.abandon()                   # a larger shard elsewhere changes the batches: every rank uses the same
+        pipe = _DigitsRows([engines], N, R, rs, npad_max, rank, world, upload=upload)
+    elif not digits and R > 0 and rs.mode == "philox":
         # device-drawn multiplicities do not depend on Y: start the first batch now, beside the upload of the shards
         first = plan_batches(lead.kind, 0, R, npad_max, lead.sms, groups=lead.groups)[0]
         prefetch = _CountsPrefetch(rs, first, [(e.Npad, (e.row0, e.N)) for e in engines])
 
-    if world > 1:
-        mine = rt.zeros((nsh, 9), torch.float64)
-        mine[:len(engines)] = parts
-        parts = rt.empty((world * nsh, 9), torch.float64)
-        dist.all_gather_into_tensor(parts, mine)
     if world > 1 or len(engines) > 1:
-        stats9 = rt.empty((9,), torch.float64)
-        _lib.call("sa_combine_moments_f64", rt.stream_ptr(), rt.ptr(parts), int(parts.shape[0]), rt.ptr(stats9))
+        if records is not None:
+            stats9 = records.stats9()
+        else:
+            stats9 = rt.empty((9,), torch.float64)
+            _lib.call("sa_combine_moments_f64", rt.stream_ptr(), rt.ptr(parts), int(parts.shape[0]), rt.ptr(stats9))
         for eng, Yd in zip(engines, loaded):
             eng.load(Yd, stats=stats9)
     else:
@@ -1294,7 +1351,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
     the strategy switch the reference makes inside ``analyze`` (analyze/sobol.py:147,183).
     """
     rank, world = rt.world() if distributed else (0, 1)
-    agreed, algo_asked = None, algo
+    auto, algo_asked = False, algo
     if shard == "auto":
         shard = "resamples"
         if world > 1:
@@ -1305,14 +1362,11 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
             R_req = np.shape(r)[1] if r is not None else int(num_resamples)
             eng = SobolAnalyzer(Dg, hi - lo, calc_second_order, algo=algo, resamples=R_req,
                                 total_rows=N) if hi > lo else None
-            mine = eng is not None and eng.kind == 6
-            # the one agreement of the call: engine family, largest row shard, shards per rank.  It is read inside
-            # analyze_row_sharded, after the upload of this rank's rows and their moments have been queued.
-            agreed = _Agreement([0 if mine else 1, eng.Npad if mine else 0, 1], world)
-            if mine:
-                shard, algo = "rows", "digits"
+            auto = True
+            if eng is not None and eng.kind == 6:
+                shard, algo = "rows", "digits"   # the ranks' agreement rides in analyze_row_sharded's one collective
             else:
-                agreed.result()              # every other rank learns it from the same all-reduce
+                _RankRecords.decline(world)      # every other rank learns it from the same all-gather
     if shard == "rows":
         _, Dg = extract_group_names(problem)
         size = int(Y.numel()) if isinstance(Y, torch.Tensor) else int(np.size(Y))
@@ -1324,7 +1378,7 @@ def analyze_device(problem, Y, calc_second_order=True, num_resamples=100, conf_l
                                 calc_second_order=calc_second_order, num_resamples=num_resamples,
                                 conf_level=conf_level, keep_resamples=keep_resamples, seed=seed,
                                 resample=resample, r=r, algo=algo, distributed=distributed,
-                                kernel_events=kernel_events, agreed=agreed)
+                                kernel_events=kernel_events, auto=auto)
         if S is not None:
             return S
         shard, algo = "resamples", algo_asked    # the ranks did not agree on the integer engine

@@ -1514,20 +1514,19 @@ conf_combine_kernel(const double *__restrict__ recs, int k, size_t pitch, int nc
 // Statistics of the union of k row shards from per-shard (n_values, stats8) records (Chan, Golub & LeVeque), on
 // the device so that a row-sharded analyze needs no host round trip between the moments and the features:
 // out[0..7] = mean, population std, min, max, min/max over the A and B columns, 0, 0; out[8] = total n_values.
-__global__ void combine_moments_kernel(const double *__restrict__ parts, int k, double *__restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void combine_moment_records(const double *__restrict__ parts, int k, size_t pitch, double *out) {
   double n = 0.0, sum = 0.0;
   for (int i = 0; i < k; ++i) {
-    const double c = parts[9 * i];
+    const double c = parts[pitch * i];
     if (c > 0.0) {
       n += c;
-      sum += c * parts[9 * i + 1];
+      sum += c * parts[pitch * i + 1];
     }
   }
   const double mean = sum / n;
   double m2 = 0.0, mn = INFINITY, mx = -INFINITY, amn = INFINITY, amx = -INFINITY;
   for (int i = 0; i < k; ++i) {
-    const double *p = parts + 9 * i;
+    const double *p = parts + pitch * i;
     if (!(p[0] > 0.0)) continue;
     const double d = p[1] - mean;
     m2 += p[0] * (p[2] * p[2] + d * d);
@@ -1547,6 +1546,31 @@ __global__ void combine_moments_kernel(const double *__restrict__ parts, int k, 
   out[6] = 0.0;
   out[7] = 0.0;
   out[8] = n;
+}
+
+__global__ void combine_moments_kernel(const double *__restrict__ parts, int k, size_t pitch,
+                                       double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  combine_moment_records(parts, k, pitch, out);
+}
+
+// One record per rank for the single collective in front of a row-sharded analyze: the rank's k shard records
+// combined into (n_values, stats8) -- a copy when k == 1 --, followed by three numbers every rank must agree on
+// (all-gathered with the moments, reduced with max on the host).
+__global__ void rank_record_kernel(const double *__restrict__ parts, int k, double f0, double f1, double f2,
+                                   double *__restrict__ rec) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (k == 1) {
+    for (int i = 0; i < 9; ++i) rec[i] = parts[i];
+  } else {
+    double st[9];
+    combine_moment_records(parts, k, 9, st);
+    rec[0] = st[8];
+    for (int i = 0; i < 8; ++i) rec[1 + i] = st[i];
+  }
+  rec[9] = f0;
+  rec[10] = f1;
+  rec[11] = f2;
 }
 
 }  // namespace sa
@@ -1930,9 +1954,22 @@ extern "C" int sa_conf_combine_f64(void *stream, const double *d_recs, int k, ui
   return SA_OK;
 }
 
+extern "C" int sa_combine_moments_pitch_f64(void *stream, const double *d_parts, int k, uint64_t pitch, double *d_out) {
+  SA_REQUIRE(d_parts && d_out && k >= 1 && pitch >= 9, SA_ERR_ARG, "sa_combine_moments_f64: bad arguments");
+  combine_moments_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_parts, k, (size_t)pitch, d_out);
+  note_launches(1);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
 extern "C" int sa_combine_moments_f64(void *stream, const double *d_parts, int k, double *d_out) {
-  SA_REQUIRE(d_parts && d_out && k >= 1, SA_ERR_ARG, "sa_combine_moments_f64: bad arguments");
-  combine_moments_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_parts, k, d_out);
+  return sa_combine_moments_pitch_f64(stream, d_parts, k, 9, d_out);
+}
+
+extern "C" int sa_rank_record_f64(void *stream, const double *d_parts, int k, double f0, double f1, double f2,
+                                  double *d_rec) {
+  SA_REQUIRE(d_parts && d_rec && k >= 1, SA_ERR_ARG, "sa_rank_record_f64: bad arguments");
+  rank_record_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_parts, k, f0, f1, f2, d_rec);
   note_launches(1);
   SA_LAUNCH_CHECK();
   return SA_OK;
