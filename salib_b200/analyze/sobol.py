@@ -748,12 +748,15 @@ class _DigitsRows:
     deviations) replace the all-gather of the estimates.  No host synchronisation before the final read-back.
     """
 
-    def __init__(self, outputs, N, R, rs, npad_max, rank, world, upload=False):
+    def __init__(self, outputs, N, R, rs, npad_max, rank, world, upload=False, after=None):
         """outputs[o] = the engines (kind 6, ``row0`` set) of model output o, one per local row shard; all outputs
         share the row shards (and therefore the multiplicities).  ``upload``: Y is coming from host memory -- the
         GPU idles behind PCIe for about as long as all multiplicities take to draw, so (Philox, memory permitting)
         every batch gets its own buffer and is drawn by the stand-alone kernel on the side stream right now, and
-        the GEMMs host nothing (a hosted draw costs a power-capped GEMM ~4 % of its clock)."""
+        the GEMMs host nothing (a hosted draw costs a power-capped GEMM ~4 % of its clock).  ``after``: an event
+        on the main stream behind which the side stream may start (default: everything queued on the main stream so
+        far) -- the caller recorded it before it queued work the draws need not wait for (the moments, the ranks'
+        all-gather) and has released no large block since."""
         self.outputs, self.N, self.R, self.rs = outputs, int(N), int(R), rs
         self.rank, self.world = rank, world
         self.shards = outputs[0]
@@ -770,7 +773,10 @@ class _DigitsRows:
         self.wsets = [[rt.empty((rows_buf * e.Npad,), torch.uint8) for e in self.shards] for _ in range(self.nbuf)]
         self.main = torch.cuda.current_stream()
         self.side = _side_stream()
-        self.side.wait_stream(self.main)     # cached blocks may still be read by earlier work on the main stream
+        if after is not None:                # cached blocks may still be read by earlier work on the main stream
+            self.side.wait_event(after)
+        else:
+            self.side.wait_stream(self.main)
         self.drawn, self.gemm_done = {}, {}
         # Philox draws of batches 1.. are hosted by the previous batch's GEMM (main stream, no events)
         self.hosted = philox and not self.predrawn and not os.environ.get("SALIB_B200_SIDE_DRAW")
@@ -977,6 +983,11 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
             engs.append(eng)
         return engs
 
+    # the side stream (multiplicity draws) may start behind this point: nothing queued from here on -- upload,
+    # moments, the ranks' all-gather -- is anything a draw has to wait for, and no large block is released before
+    # the pipeline allocates its buffers
+    entry = torch.cuda.Event()
+    entry.record()
     engines = build(algo)
     # every rank must take the same engine family and the same batches: what each rank would do on its
     # own travels in the one all-gather of the moments (``_RankRecords``)
@@ -1018,7 +1029,7 @@ def analyze_row_sharded(problem, shards, N, calc_second_order=True, num_resample
     if early:
         rs, R = resampler()
         if not mine[0]:
-            pipe = _DigitsRows([engines], N, R, rs, mine[1], rank, world, upload=upload)
+            pipe = _DigitsRows([engines], N, R, rs, mine[1], rank, world, upload=upload, after=entry)
 
     not_digits, npad_max, _ = records.result() if records is not None else mine
     if not_digits and pipe is not None:
